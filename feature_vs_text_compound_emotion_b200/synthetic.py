@@ -1,0 +1,179 @@
+"""Seeded synthetic weights and inputs in the reference's state_dict layout.
+
+Checkpoints (res50_ir_0.887.pth, vggish.pth, best-models/*/model.pt) are not available
+offline, so benches, tests and golden fixtures use randomly initialised weights whose *key
+layout and shapes* are exactly those the reference's strict ``load_state_dict`` calls pin
+(models/model.py:430, experiment.py:245-246).  BatchNorm running
+statistics and affines are randomised too -- the default identity BN would hide every
+BN-folding bug.
+
+Everything is generated on the CPU with an explicit ``torch.Generator`` so the same seed
+gives the same tensors in the build container and on the GPU box.
+"""
+from __future__ import annotations
+
+from collections import OrderedDict
+from typing import Dict, List, Sequence
+
+import torch
+
+# (in_channel, depth, stride) per residual unit of IR-50 as configured by the reference
+# (models/arcface_model.py:95-102: unit counts 3/4/14/3, first stage stride 1).
+IR50_UNITS = ([(64, 64, 1)] * 3
+              + [(64, 128, 2)] + [(128, 128, 1)] * 3
+              + [(128, 256, 2)] + [(256, 256, 1)] * 13
+              + [(256, 512, 2)] + [(512, 512, 1)] * 2)
+
+# configs.py:61-73 (tcn.channels) and models/model.py:388-393 (embedding_dim / encoder_dim)
+TCN_CHANNELS = {
+    "video": [256, 256, 128, 128], "cnn_res50": [256, 256, 128, 128],
+    "vggish": [64, 64, 32, 32], "logmel": [64, 64, 32, 32],
+    "bert": [256, 256, 128, 128], "mfcc": [32, 32, 32, 32], "egemaps": [32, 32, 32, 32],
+}
+EMBEDDING_DIM = {"video": 512, "bert": 768, "cnn_res50": 512, "mfcc": 39, "vggish": 128,
+                 "logmel": 128, "egemaps": 88}
+ENCODER_DIM = {"video": 128, "bert": 128, "cnn_res50": 128, "mfcc": 32, "vggish": 32,
+               "logmel": 32, "egemaps": 32}
+
+
+def _uniform(g, shape, bound):
+    return (torch.rand(shape, generator=g) * 2 - 1) * bound
+
+
+def _bn(sd, p, c, g):
+    """Randomised eval-mode BatchNorm (cfg 2)."""
+    sd[p + ".weight"] = torch.rand(c, generator=g) + 0.5
+    sd[p + ".bias"] = 0.1 * torch.randn(c, generator=g)
+    sd[p + ".running_mean"] = 0.1 * torch.randn(c, generator=g)
+    sd[p + ".running_var"] = torch.rand(c, generator=g) + 0.5
+    sd[p + ".num_batches_tracked"] = torch.tensor(0, dtype=torch.long)
+
+
+def _conv(sd, key, cout, cin, k, g):
+    fan_in = cin * k * k
+    sd[key] = _uniform(g, (cout, cin, k, k), fan_in ** -0.5)
+
+
+def visual_backbone_state_dict(seed: int = 0, units=IR50_UNITS, num_classes: int = 8,
+                               spatial: int = 5) -> "OrderedDict[str, torch.Tensor]":
+    """``VisualBackbone.state_dict()`` layout (models/backbone.py:69-130): prefix ``backbone.``
+    for the IR-50 and the unused ``logits.*`` head that strict loading still requires."""
+    g = torch.Generator().manual_seed(seed)
+    sd: "OrderedDict[str, torch.Tensor]" = OrderedDict()
+    b = "backbone."
+    _conv(sd, b + "input_layer.0.weight", 64, 3, 3, g)
+    _bn(sd, b + "input_layer.1", 64, g)
+    sd[b + "input_layer.2.weight"] = 0.25 + 0.1 * torch.randn(64, generator=g)
+    for i, (cin, depth, stride) in enumerate(units):
+        u = f"{b}body.{i}."
+        if cin != depth:
+            _conv(sd, u + "shortcut_layer.0.weight", depth, cin, 1, g)
+            _bn(sd, u + "shortcut_layer.1", depth, g)
+        _bn(sd, u + "res_layer.0", cin, g)
+        _conv(sd, u + "res_layer.1.weight", depth, cin, 3, g)
+        sd[u + "res_layer.2.weight"] = 0.25 + 0.1 * torch.randn(depth, generator=g)
+        _conv(sd, u + "res_layer.3.weight", depth, depth, 3, g)
+        _bn(sd, u + "res_layer.4", depth, g)
+    c = units[-1][1]
+    _bn(sd, b + "output_layer.0", c, g)
+    fin = c * spatial * spatial
+    sd[b + "output_layer.3.weight"] = _uniform(g, (512, fin), fin ** -0.5)
+    sd[b + "output_layer.3.bias"] = 0.1 * torch.randn(512, generator=g)
+    _bn(sd, b + "output_layer.4", 512, g)
+    sd["logits.weight"] = _uniform(g, (num_classes, 512), 512 ** -0.5)
+    sd["logits.bias"] = torch.zeros(num_classes)
+    # registration order in Backbone.__init__ is input_layer, output_layer, body (arcface_model.py:130-146)
+    order = [k for k in sd if ".input_layer." in k] + [k for k in sd if ".output_layer." in k] \
+        + [k for k in sd if ".body." in k] + [k for k in sd if k.startswith("logits.")]
+    return OrderedDict((k, sd[k]) for k in order)
+
+
+def head_state_dict(seed: int = 0, modalities: Sequence[str] = ("video", "vggish", "bert"),
+                    output_dim: int = 7, kernel_size: int = 5, modal_dim: int = 32,
+                    tcn_channels: Dict[str, List[int]] = None,
+                    embedding_dim: Dict[str, int] = None,
+                    encoder_dim: Dict[str, int] = None) -> "OrderedDict[str, torch.Tensor]":
+    """Everything of ``LFAN.state_dict()`` except ``spatial.*``: ``temporal.<m>.network.<i>.*``
+    (with the reference's duplicated ``conv1``/``net.0`` and ``conv2``/``net.4`` keys,
+    temporal_convolutional_model.py:24-37), ``bn.<m>.*``, ``fusion.layers.*``,
+    ``regressor.*`` (models/model.py:451-485)."""
+    tcn_channels = tcn_channels or TCN_CHANNELS
+    embedding_dim = embedding_dim or EMBEDDING_DIM
+    encoder_dim = encoder_dim or ENCODER_DIM
+    g = torch.Generator().manual_seed(seed)
+    sd: "OrderedDict[str, torch.Tensor]" = OrderedDict()
+    for m in modalities:
+        cin = embedding_dim[m]
+        for i, cout in enumerate(tcn_channels[m]):
+            p = f"temporal.{m}.network.{i}."
+            made = {}
+            for name, ci in (("conv1", cin), ("conv2", cout)):
+                v = _uniform(g, (cout, ci, kernel_size), (ci * kernel_size) ** -0.5)
+                gn = v.reshape(cout, -1).norm(dim=1).view(cout, 1, 1) * (torch.rand(cout, 1, 1, generator=g) + 0.5)
+                bias = _uniform(g, (cout,), (ci * kernel_size) ** -0.5)
+                made[name] = (bias, gn, v)
+            # module registration order: conv1, conv2, then net (net.0 is conv1, net.4 is conv2)
+            for nm, src in (("conv1", "conv1"), ("conv2", "conv2"), ("net.0", "conv1"), ("net.4", "conv2")):
+                sd[p + nm + ".bias"], sd[p + nm + ".weight_g"], sd[p + nm + ".weight_v"] = made[src]
+            if cin != cout:
+                sd[p + "downsample.weight"] = _uniform(g, (cout, cin, 1), cin ** -0.5)
+                sd[p + "downsample.bias"] = _uniform(g, (cout,), cin ** -0.5)
+            cin = cout
+    for m in modalities:
+        _bn(sd, f"bn.{m}", tcn_channels[m][-1], g)
+    a = "fusion.layers.self_attn."
+    for m in modalities:
+        d = encoder_dim[m]
+        sd[f"{a}qkv_proj.{m}.weight"] = _uniform(g, (3 * modal_dim, d), (6.0 / (d + 3 * modal_dim)) ** 0.5)
+        sd[f"{a}qkv_proj.{m}.bias"] = 0.05 * torch.randn(3 * modal_dim, generator=g)
+    e = modal_dim * len(modalities)
+    sd[a + "o_proj.weight"] = _uniform(g, (e, e), (3.0 / e) ** 0.5)
+    sd[a + "o_proj.bias"] = 0.05 * torch.randn(e, generator=g)
+    sd["fusion.layers.norm1.weight"] = torch.rand(e, generator=g) + 0.5
+    sd["fusion.layers.norm1.bias"] = 0.1 * torch.randn(e, generator=g)
+    fd = encoder_dim[modalities[0]] + e
+    sd["regressor.weight"] = _uniform(g, (output_dim, fd), fd ** -0.5)
+    sd["regressor.bias"] = _uniform(g, (output_dim,), fd ** -0.5)
+    return sd
+
+
+def lfan_state_dict(seed: int = 0, modalities: Sequence[str] = ("video", "vggish", "bert"),
+                    **kw) -> "OrderedDict[str, torch.Tensor]":
+    """Full ``LFAN.state_dict()`` layout; ``spatial.visual.*`` only when 'video' is a
+    modality (models/model.py:455-458).  Key order follows module registration order."""
+    sd: "OrderedDict[str, torch.Tensor]" = OrderedDict()
+    head = head_state_dict(seed + 1, modalities, **kw)
+    for k, v in head.items():
+        if k.startswith("temporal."):
+            sd[k] = v
+    if "video" in modalities:
+        for k, v in visual_backbone_state_dict(seed).items():
+            sd["spatial.visual." + k] = v
+    for k, v in head.items():
+        if not k.startswith("temporal."):
+            sd[k] = v
+    return sd
+
+
+def frames(n: int, seed: int = 1234, size: int = 40) -> torch.Tensor:
+    """Aligned face crops after the reference eval transform, i.e. uniform in [-1, 1]
+    (base/dataset.py:503-510): [n, 3, size, size] fp32 NCHW."""
+    g = torch.Generator().manual_seed(seed)
+    return torch.rand(n, 3, size, size, generator=g) * 2 - 1
+
+
+def feature_windows(batch: int, length: int = 300, seed: int = 1234,
+                    modalities: Sequence[str] = ("cnn_res50", "vggish", "bert"),
+                    embedding_dim: Dict[str, int] = None) -> Dict[str, torch.Tensor]:
+    """Pre-extracted feature windows [B,1,T,D_m] (shapes documented at trainer.py:461-465).
+    Visual embeddings are unit-norm (arcface_model.py:151); audio/text are z-scored
+    (base/dataset.py:529-536) => standard normal."""
+    embedding_dim = embedding_dim or EMBEDDING_DIM
+    g = torch.Generator().manual_seed(seed)
+    out = {}
+    for m in modalities:
+        x = torch.randn(batch, 1, length, embedding_dim[m], generator=g)
+        if m in ("video", "cnn_res50"):
+            x = torch.nn.functional.normalize(x, dim=-1)
+        out[m] = x
+    return out

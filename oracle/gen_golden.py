@@ -1,0 +1,117 @@
+"""Generate tests/golden/*.pt by running the UNMODIFIED reference modules.
+
+Run in the build container only (needs /root/reference):
+    python oracle/gen_golden.py
+
+What it pins (SURVEY.md section 8c -- the reference has no golden vectors of its own, so the
+reference modules, imported as they are, are the source of truth):
+  * ir50_n4.pt      -- VisualBackbone forward on 4 synthetic frames (weights: synthetic seed 0)
+  * head_b2.pt      -- LFAN(cnn_res50,vggish,bert) forward, B=2 x T=300  (BASELINE cfg 1 shape)
+  * lfan_b1.pt      -- LFAN(video,vggish,bert) forward from pixels, B=1 x T=300
+  * state_keys.json -- the reference's own state_dict key/shape listing (534 keys)
+  * windowing.json  -- Trainer.windowing outputs for a set of lengths
+Weights are NOT stored: they are regenerated from the seed by
+feature_vs_text_compound_emotion_b200.synthetic (identical on every machine), and are loaded
+into the reference modules with strict=True here, which also proves the key layout.
+"""
+import json
+import os
+import sys
+import tempfile
+import warnings
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = "/root/reference"
+sys.path.insert(0, ROOT)
+sys.path.insert(0, REF)
+warnings.filterwarnings("ignore")
+
+from feature_vs_text_compound_emotion_b200 import synthetic  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def main():
+    torch.manual_seed(0)
+    torch.set_grad_enabled(False)
+    import configs as ref_configs
+    from models.backbone import VisualBackbone
+    from models.model import LFAN
+
+    os.makedirs(OUT, exist_ok=True)
+
+    # ---- IR-50 -----------------------------------------------------------------------
+    vsd = synthetic.visual_backbone_state_dict(seed=0)
+    vb = VisualBackbone(use_pretrained=False)
+    vb.load_state_dict(vsd, strict=True)
+    vb.eval()
+    x = synthetic.frames(4, seed=1234)
+    emb = vb(x)
+    # a few intermediate activations, to localise a failure to a stage
+    h = vb.backbone.input_layer(x)
+    taps = {"stem": h[:, :, ::13, ::13].clone()}
+    for i, unit in enumerate(vb.backbone.body):
+        h = unit(h)
+        if i in (2, 3, 6, 7, 20, 21, 23):
+            taps[f"body{i}"] = h[:, ::17, ::3, ::3].clone()
+    torch.save({"x_seed": 1234, "n": 4, "weights_seed": 0, "emb": emb, "taps": taps},
+               os.path.join(OUT, "ir50_n4.pt"))
+    print("ir50", emb.shape, float(emb.abs().mean()), {k: float(v.abs().mean()) for k, v in taps.items()})
+
+    # ---- head only (cfg 1 shape) ---------------------------------------------------------
+    mods = ["cnn_res50", "vggish", "bert"]
+    tmp = tempfile.mkdtemp()
+    torch.save(vsd, os.path.join(tmp, "res50_ir_0.887.pth"))
+    model = LFAN(backbone_settings=ref_configs.config["backbone_settings"], output_dim=7,
+                 task="CLASSIFICATION", modality=mods, kernel_size=5, example_length=300,
+                 tcn_channel=ref_configs.config["tcn"]["channels"], modal_dim=32, num_heads=2,
+                 root_dir=tmp, device="cpu")
+    model.init()
+    hsd = synthetic.lfan_state_dict(seed=0, modalities=mods)
+    model.load_state_dict(hsd, strict=True)
+    model.eval()
+    X = synthetic.feature_windows(2, 300, seed=1234, modalities=mods)
+    logits = model({k: v.clone() for k, v in X.items()})
+    torch.save({"x_seed": 1234, "batch": 2, "weights_seed": 0, "modalities": mods, "logits": logits},
+               os.path.join(OUT, "head_b2.pt"))
+    print("head", logits.shape, float(logits.abs().mean()))
+
+    # ---- full LFAN from pixels -------------------------------------------------------------
+    mods3 = ["video", "vggish", "bert"]
+    full = LFAN(backbone_settings=ref_configs.config["backbone_settings"], output_dim=7,
+                task="CLASSIFICATION", modality=mods3, kernel_size=5, example_length=300,
+                tcn_channel=ref_configs.config["tcn"]["channels"], modal_dim=32, num_heads=2,
+                root_dir=tmp, device="cpu")
+    full.init()
+    fsd = synthetic.lfan_state_dict(seed=0, modalities=mods3)
+    full.load_state_dict(fsd, strict=True)
+    full.eval()
+    keys = {k: list(v.shape) for k, v in full.state_dict().items()}
+    assert list(keys) == list(fsd), "synthetic key order differs from the reference's"
+    json.dump(keys, open(os.path.join(OUT, "state_keys.json"), "w"), indent=0)
+    feats = synthetic.feature_windows(1, 300, seed=77, modalities=["vggish", "bert"])
+    vid = synthetic.frames(300, seed=78).view(1, 300, 3, 40, 40)
+    Xf = {"video": vid, "vggish": feats["vggish"], "bert": feats["bert"]}
+    lg = full({k: v.clone() for k, v in Xf.items()})
+    torch.save({"feat_seed": 77, "frame_seed": 78, "weights_seed": 0, "modalities": mods3, "logits": lg},
+               os.path.join(OUT, "lfan_b1.pt"))
+    print("lfan", lg.shape, float(lg.abs().mean()), len(keys), "keys")
+
+    # ---- windowing (trainer.py imports pynvml/munch, absent here: exec the one function) ----
+    src = open(os.path.join(REF, "trainer.py")).read()
+    start = src.index("    def windowing(x, window_length, hop_length)")
+    body = src[start:]
+    ns = {"np": np, "List": list}
+    exec("import numpy as np\nfrom typing import List\n" + "\n".join(l[4:] for l in body.splitlines()), ns)
+    cases = {}
+    for L in (1, 150, 299, 300, 301, 499, 500, 501, 700, 701, 1234, 3000):
+        cases[str(L)] = [[int(w[0]), int(w[-1]), len(w)] for w in ns["windowing"](np.arange(L), 300, 200)]
+    json.dump(cases, open(os.path.join(OUT, "windowing.json"), "w"))
+    print("windowing", {k: len(v) for k, v in cases.items()})
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,233 @@
+"""CPU oracle for the LFAN hot path -- TEST INFRASTRUCTURE ONLY.
+
+This file is a plain-PyTorch fp32, *functional* restatement of the reference
+arithmetic for the path named in BASELINE.json (IR-50 -> TCN -> cross-modal
+attention -> classifier).  It works directly on a reference-layout
+``state_dict`` (dict[str, Tensor]); it holds no nn.Module and no parameters.
+
+Who may use it: ``tests/``, ``__graft_entry__.smoke()`` and the
+``cpu_baseline`` / ``--impl reference`` legs of ``bench.py``.  The product
+package (``feature_vs_text_compound_emotion_b200``) never imports it.
+
+Parity pin: the reference ships no golden vectors, so the
+oracle is pinned against the reference modules themselves, imported from
+/root/reference in the build container by ``oracle/gen_golden.py``; the
+resulting fixtures live in ``tests/golden/`` and ``tests/test_oracle.py``
+re-checks the oracle against them on every run (no /root/reference needed).
+
+Every function cites the reference lines it restates (paths relative to
+/root/reference).
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Sequence
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+Tensor = torch.Tensor
+SD = Dict[str, Tensor]
+
+BN_EPS = 1e-5          # torch.nn.BatchNorm{1,2}d default, used everywhere in the reference
+LN_EPS = 1e-5          # torch.nn.LayerNorm default (models/transformer.py:189)
+LEAKY_SLOPE = 0.01     # torch.nn.LeakyReLU default (models/temporal_convolutional_model.py:27,33,39)
+
+# get_blocks(50): models/arcface_model.py:95-102 -> (in_channel, depth, stride) per unit
+IR50_UNITS = ([(64, 64, 1)] * 3
+              + [(64, 128, 2)] + [(128, 128, 1)] * 3
+              + [(128, 256, 2)] + [(256, 256, 1)] * 13
+              + [(256, 512, 2)] + [(512, 512, 1)] * 2)
+
+
+def _bn_eval(sd: SD, p: str, x: Tensor) -> Tensor:
+    """Eval-mode BatchNorm as an affine map over dim 1 (nn.BatchNorm1d/2d, running stats)."""
+    scale = sd[p + ".weight"] / torch.sqrt(sd[p + ".running_var"] + BN_EPS)
+    shift = sd[p + ".bias"] - sd[p + ".running_mean"] * scale
+    shape = [1, -1] + [1] * (x.dim() - 2)
+    return x * scale.view(shape) + shift.view(shape)
+
+
+def _prelu(x: Tensor, alpha: Tensor) -> Tensor:
+    """Per-channel PReLU (models/arcface_model.py:54, :132)."""
+    a = alpha.view(1, -1, 1, 1)
+    return torch.where(x >= 0, x, a * x)
+
+
+# --------------------------------------------------------------------------------------
+# IR-50 (models/arcface_model.py:120-151, models/backbone.py:69-130)
+# --------------------------------------------------------------------------------------
+def ir_unit(sd: SD, p: str, x: Tensor, cin: int, depth: int, stride: int) -> Tensor:
+    """bottleneck_IR.forward, models/arcface_model.py:44-60."""
+    if cin == depth:
+        # MaxPool2d(1, stride) == strided subsampling (:48)
+        shortcut = x[:, :, ::stride, ::stride]
+    else:
+        shortcut = F.conv2d(x, sd[p + ".shortcut_layer.0.weight"], None, stride)          # :50
+        shortcut = _bn_eval(sd, p + ".shortcut_layer.1", shortcut)                          # :51
+    r = _bn_eval(sd, p + ".res_layer.0", x)                                                 # :53
+    r = F.conv2d(r, sd[p + ".res_layer.1.weight"], None, 1, 1)                              # :54
+    r = _prelu(r, sd[p + ".res_layer.2.weight"])                                            # :54
+    r = F.conv2d(r, sd[p + ".res_layer.3.weight"], None, stride, 1)                         # :55
+    r = _bn_eval(sd, p + ".res_layer.4", r)                                                 # :55
+    return r + shortcut                                                                     # :60
+
+
+def ir50_forward(sd: SD, x: Tensor, prefix: str = "", units=IR50_UNITS) -> Tensor:
+    """Backbone.forward (arcface_model.py:147-151) with the 5x5 head of VisualBackbone
+    (backbone.py:99-103).  ``x`` is [N,3,40,40] fp32; returns unit-norm [N,512].
+    ``prefix`` selects the sub-dict, e.g. 'backbone.' for a VisualBackbone state_dict or
+    'spatial.visual.backbone.' for an LFAN one."""
+    p = prefix
+    h = F.conv2d(x, sd[p + "input_layer.0.weight"], None, 1, 1)                             # :130
+    h = _bn_eval(sd, p + "input_layer.1", h)                                                # :131
+    h = _prelu(h, sd[p + "input_layer.2.weight"])                                           # :132
+    for i, (cin, depth, stride) in enumerate(units):
+        h = ir_unit(sd, f"{p}body.{i}", h, cin, depth, stride)
+    h = _bn_eval(sd, p + "output_layer.0", h)            # BN2d; Dropout is identity in eval
+    h = h.reshape(h.shape[0], -1)                         # Flatten in NCHW order (arcface_model.py:12-14)
+    h = F.linear(h, sd[p + "output_layer.3.weight"], sd[p + "output_layer.3.bias"])
+    h = _bn_eval(sd, p + "output_layer.4", h)             # BN1d
+    return h / torch.norm(h, 2, 1, True)                  # l2_norm, arcface_model.py:17-20
+
+
+# --------------------------------------------------------------------------------------
+# TCN (models/temporal_convolutional_model.py:12-75)
+# --------------------------------------------------------------------------------------
+def weight_norm_effective(g: Tensor, v: Tensor) -> Tensor:
+    """Old-style torch.nn.utils.weight_norm (dim=0): w = g * v / ||v|| with the norm taken
+    over every dim but 0 (temporal_convolutional_model.py:24, :30)."""
+    norm = v.reshape(v.shape[0], -1).norm(dim=1).view(-1, 1, 1)
+    return g * v / norm
+
+
+def causal_dilated_conv(x: Tensor, w: Tensor, b: Tensor, dilation: int) -> Tensor:
+    """Conv1d(padding=(k-1)*d, dilation=d) followed by Chomp1d(padding)
+    (temporal_convolutional_model.py:12-18, :24-26): symmetric padding, then drop the
+    right-hand ``padding`` samples => causal."""
+    pad = (w.shape[-1] - 1) * dilation
+    y = F.conv1d(x, w, b, stride=1, padding=pad, dilation=dilation)
+    return y[:, :, :-pad] if pad > 0 else y
+
+
+def temporal_block(sd: SD, p: str, x: Tensor, dilation: int) -> Tensor:
+    """TemporalBlock.forward (:51-54); Dropout is identity in eval."""
+    w1 = weight_norm_effective(sd[p + ".conv1.weight_g"], sd[p + ".conv1.weight_v"])
+    w2 = weight_norm_effective(sd[p + ".conv2.weight_g"], sd[p + ".conv2.weight_v"])
+    h = F.leaky_relu(causal_dilated_conv(x, w1, sd[p + ".conv1.bias"], dilation), LEAKY_SLOPE)
+    h = F.leaky_relu(causal_dilated_conv(h, w2, sd[p + ".conv2.bias"], dilation), LEAKY_SLOPE)
+    if (p + ".downsample.weight") in sd:
+        res = F.conv1d(x, sd[p + ".downsample.weight"], sd[p + ".downsample.bias"])
+    else:
+        res = x
+    return F.leaky_relu(h + res, LEAKY_SLOPE)
+
+
+def tcn_forward(sd: SD, prefix: str, x: Tensor, num_levels: int = 4) -> Tensor:
+    """TemporalConvNet.forward (:57-75): level i has dilation 2**i.  x: [B, C_in, T]."""
+    for i in range(num_levels):
+        x = temporal_block(sd, f"{prefix}network.{i}", x, 2 ** i)
+    return x
+
+
+# --------------------------------------------------------------------------------------
+# Cross-modal attention fusion (models/transformer.py:11-19, :102-215)
+# --------------------------------------------------------------------------------------
+def fusion_forward(sd: SD, prefix: str, feats: Dict[str, Tensor], modalities: Sequence[str],
+                   modal_dim: int = 32, num_heads: int = 2) -> Tensor:
+    """MultimodalTransformerEncoder.forward -> MultiModalEncoderBlock.forward ->
+    MultimodalMultiheadAttention.forward.  feats[m]: [B, T, D_m].  Returns [B, T, modal_dim*M].
+
+    The reference reshapes each qkv projection [B,T,3*modal_dim] as [B,T,H,1,3*hd] and chunks
+    the last axis (:142-144), so inside one head the 3*hd outputs are laid out q|k|v.  Tokens
+    are the modalities (M of them); softmax(QK^T/sqrt(hd))V + V (:156-157); heads/modalities
+    are flattened as (head, modal, dim) (:158-159); o_proj; LayerNorm without residual
+    (:192-197, dropout is identity in eval)."""
+    hd = modal_dim // num_heads
+    a = prefix + "layers.self_attn."
+    qs, ks, vs = [], [], []
+    for m in modalities:
+        qkv = F.linear(feats[m], sd[f"{a}qkv_proj.{m}.weight"], sd[f"{a}qkv_proj.{m}.bias"])
+        B, T, _ = qkv.shape
+        qkv = qkv.view(B, T, num_heads, 3, hd)
+        qs.append(qkv[:, :, :, 0])
+        ks.append(qkv[:, :, :, 1])
+        vs.append(qkv[:, :, :, 2])
+    Q = torch.stack(qs, dim=3)          # [B, T, H, M, hd]
+    K = torch.stack(ks, dim=3)
+    V = torch.stack(vs, dim=3)
+    logits = torch.einsum("bthmd,bthnd->bthmn", Q, K) / math.sqrt(hd)
+    att = torch.softmax(logits, dim=-1)
+    vals = torch.einsum("bthmn,bthnd->bthmd", att, V) + V
+    vals = vals.reshape(B, T, num_heads * len(modalities) * hd)
+    o = F.linear(vals, sd[a + "o_proj.weight"], sd[a + "o_proj.bias"])
+    n = prefix + "layers.norm1."
+    return F.layer_norm(o, (o.shape[-1],), sd[n + "weight"], sd[n + "bias"], LN_EPS)
+
+
+# --------------------------------------------------------------------------------------
+# LFAN (models/model.py:375-526)
+# --------------------------------------------------------------------------------------
+def head_forward(sd: SD, feats: Dict[str, Tensor], modalities: Sequence[str],
+                 modal_dim: int = 32, num_heads: int = 2) -> Tensor:
+    """Everything in LFAN.forward after the backbones (model.py:511-526).
+    feats[m]: [B, T, D_m] (the reference receives [B,1,T,D_m] and squeezes, :513).
+    Returns logits [B, T, n_cls]."""
+    enc = {}
+    for m in modalities:
+        x = feats[m].transpose(1, 2)                                  # :513  [B, D, T]
+        x = tcn_forward(sd, f"temporal.{m}.", x)                      # :514
+        enc[m] = _bn_eval(sd, f"bn.{m}", x).transpose(1, 2)           # :515  [B, T, C]
+    follower = fusion_forward(sd, "fusion.", enc, modalities, modal_dim, num_heads)   # :517
+    cat = torch.cat((enc[modalities[0]], follower), dim=-1)           # :519
+    return F.linear(cat, sd["regressor.weight"], sd["regressor.bias"])   # :520
+
+
+def lfan_forward(sd: SD, X: Dict[str, Tensor], modalities: Sequence[str],
+                 modal_dim: int = 32, num_heads: int = 2) -> Tensor:
+    """LFAN.forward (model.py:487-526), classification task (no tanh, :523).
+    X['video']: [B,T,3,40,40]; other modalities [B,1,T,D]."""
+    feats = {}
+    for m in modalities:
+        if m == "video":
+            B, T = X[m].shape[:2]
+            emb = ir50_forward(sd, X[m].reshape(B * T, *X[m].shape[2:]), "spatial.visual.backbone.")
+            feats[m] = emb.view(B, T, -1)                             # :490-497
+        else:
+            feats[m] = X[m].squeeze(1)
+    return head_forward(sd, feats, modalities, modal_dim, num_heads)
+
+
+# --------------------------------------------------------------------------------------
+# Long-video windowing (trainer.py:788-913)
+# --------------------------------------------------------------------------------------
+def windowing(length: int, window_length: int = 300, hop_length: int = 200) -> List[np.ndarray]:
+    """Trainer.windowing (trainer.py:894-913) on arange(length): full windows every hop, plus
+    a tail window covering the last ``window_length`` frames when the regular grid misses the
+    end; a single short window when length < window_length."""
+    idx = np.arange(length)
+    if length < window_length:
+        return [idx]
+    n = (length - window_length) // hop_length + 1
+    out = [idx[i * hop_length: i * hop_length + window_length] for i in range(n)]
+    if out[-1][-1] < length - 1:
+        out.append(idx[-window_length:])
+    return out
+
+
+def windowed_inference(forward_fn, X: Dict[str, Tensor], window_length: int = 300,
+                       hop_length: int = 200) -> Tensor:
+    """Trainer.inference_forward_windows (trainer.py:832-892): run ``forward_fn`` on each
+    window, sum into place, divide by the per-frame overlap count."""
+    any_key = next(iter(X))
+    length = X[any_key].shape[1] if any_key == "video" else X[any_key].shape[2]
+    out, cnt = None, torch.zeros(length)
+    for wd in windowing(length, window_length, hop_length):
+        chunk = {m: (v[:, wd] if m == "video" else v[:, :, wd]) for m, v in X.items()}
+        y = forward_fn(chunk)
+        if out is None:
+            out = torch.zeros(y.shape[0], length, y.shape[2], dtype=y.dtype)
+        out[:, wd] += y
+        cnt[wd] += 1
+    return out / cnt.view(1, -1, 1)

@@ -1,0 +1,84 @@
+"""The oracle (oracle/lfan_oracle.py) against fixtures produced by the unmodified reference
+modules (oracle/gen_golden.py).  CPU only; no /root/reference needed at run time."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from feature_vs_text_compound_emotion_b200 import synthetic
+from oracle import lfan_oracle as O
+
+torch.set_grad_enabled(False)
+
+
+def test_ir50_matches_reference(golden_dir):
+    g = torch.load(os.path.join(golden_dir, "ir50_n4.pt"))
+    sd = synthetic.visual_backbone_state_dict(g["weights_seed"])
+    x = synthetic.frames(g["n"], seed=g["x_seed"])
+    emb = O.ir50_forward(sd, x, "backbone.")
+    assert emb.shape == (4, 512)
+    # same fp32 ops as the reference => tight tolerance (only op-order noise)
+    assert (emb - g["emb"]).abs().max().item() < 2e-6
+    assert torch.allclose(emb.norm(dim=1), torch.ones(4), atol=1e-5)
+
+
+def test_head_matches_reference(golden_dir):
+    g = torch.load(os.path.join(golden_dir, "head_b2.pt"))
+    mods = g["modalities"]
+    sd = synthetic.lfan_state_dict(g["weights_seed"], mods)
+    X = synthetic.feature_windows(g["batch"], 300, seed=g["x_seed"], modalities=mods)
+    logits = O.lfan_forward(sd, X, mods)
+    assert logits.shape == (2, 300, 7)
+    assert (logits - g["logits"]).abs().max().item() < 2e-5
+
+
+def test_lfan_from_pixels_matches_reference(golden_dir):
+    g = torch.load(os.path.join(golden_dir, "lfan_b1.pt"))
+    mods = g["modalities"]
+    sd = synthetic.lfan_state_dict(g["weights_seed"], mods)
+    feats = synthetic.feature_windows(1, 300, seed=g["feat_seed"], modalities=["vggish", "bert"])
+    X = {"video": synthetic.frames(300, seed=g["frame_seed"]).view(1, 300, 3, 40, 40),
+         "vggish": feats["vggish"], "bert": feats["bert"]}
+    logits = O.lfan_forward(sd, X, mods)
+    assert (logits - g["logits"]).abs().max().item() < 5e-5
+    assert (logits.argmax(-1) == g["logits"].argmax(-1)).float().mean().item() == 1.0
+
+
+def test_state_dict_layout_matches_reference(golden_dir):
+    keys = json.load(open(os.path.join(golden_dir, "state_keys.json")))
+    sd = synthetic.lfan_state_dict(0, ["video", "vggish", "bert"])
+    assert list(sd) == list(keys)
+    assert len(keys) == 534
+    for k, v in sd.items():
+        assert list(v.shape) == keys[k], k
+
+
+def test_windowing_matches_reference(golden_dir):
+    cases = json.load(open(os.path.join(golden_dir, "windowing.json")))
+    for L, wins in cases.items():
+        mine = [[int(w[0]), int(w[-1]), len(w)] for w in O.windowing(int(L), 300, 200)]
+        assert mine == wins, L
+
+
+def test_tcn_is_causal():
+    sd = synthetic.head_state_dict(3, ["vggish"])
+    x = torch.randn(1, 128, 300)
+    y0 = O.tcn_forward(sd, "temporal.vggish.", x)
+    x2 = x.clone()
+    x2[:, :, 200:] += 1.0
+    y1 = O.tcn_forward(sd, "temporal.vggish.", x2)
+    assert torch.equal(y0[:, :, :200], y1[:, :, :200])
+    assert not torch.equal(y0[:, :, 200:], y1[:, :, 200:])
+
+
+def test_windowed_inference_overlap_average():
+    # a forward that returns the frame index itself must survive stitch+average unchanged
+    def fwd(chunk):
+        v = chunk["vggish"]            # [B,1,T,1]
+        return v[:, 0].expand(-1, -1, 7).clone()
+    L = 701
+    X = {"vggish": torch.arange(L, dtype=torch.float32).view(1, 1, L, 1)}
+    out = O.windowed_inference(fwd, X)
+    assert torch.allclose(out[0, :, 0], torch.arange(L, dtype=torch.float32))
