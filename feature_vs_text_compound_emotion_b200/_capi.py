@@ -1,0 +1,105 @@
+"""ctypes binding of libcer_b200.so (include/cer_b200.h).
+
+The library is the only compute path: there is no CPU or eager-PyTorch fallback.  ``lib()``
+raises if the shared object is missing; every wrapper raises ``CerError`` on a non-zero status.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libcer_b200.so")
+CER_MAX_MODALS = 4
+
+
+class CerError(RuntimeError):
+    pass
+
+
+class IrUnit(C.Structure):
+    _fields_ = [("cin", C.c_int32), ("depth", C.c_int32), ("stride", C.c_int32), ("has_proj", C.c_int32),
+                ("w1", C.c_void_p), ("bias1", C.c_void_p), ("alpha", C.c_void_p),
+                ("w2", C.c_void_p), ("bias2", C.c_void_p)]
+
+
+class Ir50Weights(C.Structure):
+    _fields_ = [("in_h", C.c_int32), ("in_w", C.c_int32),
+                ("stem_w", C.c_void_p), ("stem_bias", C.c_void_p), ("stem_alpha", C.c_void_p),
+                ("n_units", C.c_int32), ("units", C.POINTER(IrUnit)),
+                ("fc_in", C.c_int32), ("emb_dim", C.c_int32),
+                ("fc_w", C.c_void_p), ("fc_bias", C.c_void_p)]
+
+
+class TcnBlock(C.Structure):
+    _fields_ = [("c_in", C.c_int32), ("c_out", C.c_int32), ("kernel_size", C.c_int32), ("dilation", C.c_int32),
+                ("w1", C.c_void_p), ("b1", C.c_void_p), ("w2", C.c_void_p), ("b2", C.c_void_p),
+                ("wd", C.c_void_p), ("bd", C.c_void_p), ("post_scale", C.c_void_p), ("post_shift", C.c_void_p)]
+
+
+class FusionWeights(C.Structure):
+    _fields_ = [("n_modals", C.c_int32), ("dim", C.c_int32 * CER_MAX_MODALS),
+                ("modal_dim", C.c_int32), ("num_heads", C.c_int32), ("n_out", C.c_int32),
+                ("wqkv", C.c_void_p * CER_MAX_MODALS), ("bqkv", C.c_void_p * CER_MAX_MODALS),
+                ("wo", C.c_void_p), ("bo", C.c_void_p), ("ln_g", C.c_void_p), ("ln_b", C.c_void_p),
+                ("wr", C.c_void_p), ("br", C.c_void_p)]
+
+
+# name -> (restype, argtypes); mirrors include/cer_b200.h one to one
+SIGNATURES = {
+    "cer_last_error": (C.c_char_p, []),
+    "cer_version": (C.c_int, []),
+    "cer_check_device": (C.c_int, []),
+    "cer_ir50_workspace_bytes": (C.c_size_t, [C.POINTER(Ir50Weights), C.c_int64]),
+    "cer_ir50_create": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(Ir50Weights), C.c_int64, C.c_void_p, C.c_size_t]),
+    "cer_ir50_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    "cer_ir50_debug_activation": (C.c_int64, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]),
+    "cer_ir50_launches": (C.c_int64, [C.c_void_p, C.c_int64]),
+    "cer_ir50_destroy": (None, [C.c_void_p]),
+    "cer_tcn_block_workspace_bytes": (C.c_size_t, [C.POINTER(TcnBlock), C.c_int64, C.c_int64]),
+    "cer_tcn_block_forward": (C.c_int, [C.POINTER(TcnBlock), C.c_void_p, C.c_void_p, C.c_int64, C.c_int64,
+                                        C.c_void_p, C.c_size_t, C.c_void_p]),
+    "cer_fusion_head_forward": (C.c_int, [C.POINTER(FusionWeights), C.POINTER(C.c_void_p), C.c_int64, C.c_void_p,
+                                          C.c_void_p, C.c_void_p]),
+    "cer_stitch_windows": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int64,
+                                     C.c_void_p, C.c_void_p]),
+}
+
+_lib: Optional[C.CDLL] = None
+
+
+def lib() -> C.CDLL:
+    """Load libcer_b200.so (built by feature_vs_text_compound_emotion_b200.build)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise CerError(f"{LIB_PATH} is missing: run `python -m feature_vs_text_compound_emotion_b200.build` "
+                           "(there is no fallback path)")
+        handle = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = handle
+    return _lib
+
+
+def check(status: int, what: str = "") -> int:
+    if status < 0:
+        msg = lib().cer_last_error()
+        raise CerError(f"{what} failed with status {status}: {msg.decode() if msg else ''}")
+    return status
+
+
+def require_gpu() -> None:
+    """Fail loudly when the kernels cannot run (no CUDA device / not sm_100)."""
+    import torch
+    if not torch.cuda.is_available():
+        raise CerError("no CUDA device: the B200 kernels have no CPU fallback")
+    check(lib().cer_check_device(), "cer_check_device")
+
+
+def current_stream_ptr() -> int:
+    import torch
+    return torch.cuda.current_stream().cuda_stream

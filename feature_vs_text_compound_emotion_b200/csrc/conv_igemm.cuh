@@ -1,0 +1,265 @@
+// Implicit-GEMM convolution for the IR-50 residual units on sm_100a.
+//
+//   D[m, co] = sum_{tap, ci} X[pixel(m) + tap, ci] * W[co, tap, ci]   (+ fused 1x1/s2 shortcut K-steps)
+//
+// GEMM view: M = frames*Hout*Wout output pixels, N = Cout, K = taps*Cin (+ Cin2).
+//   A tile (128 pixels x 64 channels, bf16) : TMA *im2col* load from the NHWC activation; the halo
+//                                             (zero padding) and frame boundaries are resolved by
+//                                             the TMA unit, so a tile may start at any pixel.
+//   B tile (BN couts x 64 k, bf16)          : TMA tiled load from the packed weight matrix [Cout][K].
+//   D (128 x BN fp32)                       : TMEM accumulator, double buffered (2*BN columns).
+// Warp roles (192 threads): warps 0-3 epilogue (one TMEM lane = one output pixel per thread),
+// warp 4 TMA producer, warp 5 TMEM allocator + single-thread tcgen05.mma issuer.
+// Persistent: grid = min(#tiles, #SMs); tiles are walked n-tile-fastest so neighbouring CTAs
+// share the same activation rows in L2.
+//
+// Epilogue (fused): + bias[class(pixel)][co]  -> PReLU(alpha[co]) -> + residual[m][co] -> bf16|fp32.
+// `class(pixel)` is the 9-way border class (corner/edge/interior) that makes the pre-conv
+// BatchNorm exact under zero padding (reference: models/arcface_model.py:52-55).
+#pragma once
+#include "ptx.cuh"
+
+namespace cer {
+
+struct alignas(64) ConvKernelParams {
+  CUtensorMap tmap_a;    // im2col, main operand  [N,H,W,Cin]
+  CUtensorMap tmap_a2;   // im2col, fused 1x1 shortcut operand [N,H2,W2,Cin2] (unused if ksteps2==0)
+  CUtensorMap tmap_b;    // tiled, weights [Cout][Ktot]
+  int M;                 // valid output pixels
+  int Hout, Wout, Cout;
+  int cin_chunks;        // Cin/64
+  int ksize;             // 1 or 3
+  int ksteps_main;       // ksize*ksize*cin_chunks
+  int ksteps2;           // Cin2/64 or 0
+  int stride, pad;       // main conv geometry (base coord = o*stride - pad)
+  int stride2;           // shortcut stride
+  int num_m_tiles, num_n_tiles;
+  int bias_classes;      // 1 or 9
+  int out_fp32;          // 0: bf16 output, 1: fp32 output
+  const float* bias;     // [bias_classes][Cout]
+  const float* alpha;    // [Cout] PReLU slopes or nullptr
+  const __nv_bfloat16* res;  // [M][Cout] residual or nullptr
+  void* out;             // [M][Cout]
+};
+
+constexpr int kConvThreads = 192;
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;           // 64 bf16 = 128 B = one swizzle row
+constexpr int kABytes = kBlockM * 128;
+
+template <int BN, int STAGES>
+struct ConvSmem {
+  static constexpr int kBBytes = BN * 128;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kBarOffset = STAGES * kStageBytes;
+  static constexpr int kTotal = kBarOffset + (2 * STAGES + 4) * 8 + 16 + 1024 /*alignment slack*/;
+};
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
+  using L = ConvSmem<BN, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOffset);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int total_tiles = p.num_m_tiles * p.num_n_tiles;
+  const int ksteps = p.ksteps_main + p.ksteps2;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull_bar[a], 1);
+      mbar_init(&tempty_bar[a], 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 4 && lane == 0) {
+    tma_prefetch_desc(&p.tmap_a);
+    tma_prefetch_desc(&p.tmap_b);
+    if (p.ksteps2 > 0) tma_prefetch_desc(&p.tmap_a2);
+  }
+  if (warp == 5) {
+    tmem_alloc(tmem_slot, 2 * BN);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 4) {
+    // ===================== TMA producer (one lane) =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const int hw = p.Hout * p.Wout;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int m_tile = tile / p.num_n_tiles;
+        const int n_tile = tile - m_tile * p.num_n_tiles;
+        const int m0 = m_tile * kBlockM;
+        const int n_img = m0 / hw;
+        const int rem = m0 - n_img * hw;
+        const int oh = rem / p.Wout;
+        const int ow = rem - oh * p.Wout;
+        for (int ks = 0; ks < ksteps; ++ks) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * L::kStageBytes;
+          uint8_t* sb = sa + kABytes;
+          mbar_expect_tx(&full_bar[stage], L::kStageBytes);
+          if (ks < p.ksteps_main) {
+            const int tap = ks / p.cin_chunks;
+            const int chunk = ks - tap * p.cin_chunks;
+            const int r = tap / p.ksize;
+            const int s = tap - r * p.ksize;
+            tma_load_im2col_4d(&p.tmap_a, &full_bar[stage], sa, chunk * kBlockK, ow * p.stride - p.pad,
+                               oh * p.stride - p.pad, n_img, (uint16_t)s, (uint16_t)r);
+          } else {
+            const int chunk = ks - p.ksteps_main;
+            tma_load_im2col_4d(&p.tmap_a2, &full_bar[stage], sa, chunk * kBlockK, ow * p.stride2, oh * p.stride2,
+                               n_img, 0, 0);
+          }
+          tma_load_2d(&p.tmap_b, &full_bar[stage], sb, ks * kBlockK, n_tile * BN);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 5) {
+    // ===================== MMA issuer (one lane) =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc(kBlockM, BN, /*bf16*/ 1);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * BN;
+        for (int ks = 0; ks < ksteps; ++ks) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + stage * L::kStageBytes);
+          const uint32_t b_addr = a_addr + kABytes;
+#pragma unroll
+          for (int k = 0; k < kBlockK / 16; ++k) {
+            umma_f16(tmem_d, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc,
+                     (ks | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);       // frees the smem slot once these MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tfull_bar[acc]);           // accumulator complete -> epilogue
+      }
+    }
+  } else {
+    // ===================== Epilogue (warps 0-3, 128 threads) =====================
+    const int row = warp * 32 + lane;           // TMEM lane == row of the M tile
+    const uint32_t lane_addr = (static_cast<uint32_t>(warp * 32) << 16);
+    const int hw = p.Hout * p.Wout;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      const int m_tile = tile / p.num_n_tiles;
+      const int n_tile = tile - m_tile * p.num_n_tiles;
+      const int m = m_tile * kBlockM + row;
+      const bool valid = m < p.M;
+      const int n0 = n_tile * BN;
+      int cls = 0;
+      if (p.bias_classes == 9) {
+        const int rem = m % hw;
+        const int oh = rem / p.Wout;
+        const int ow = rem - oh * p.Wout;
+        cls = (oh == 0 ? 0 : (oh == p.Hout - 1 ? 2 : 1)) * 3 + (ow == 0 ? 0 : (ow == p.Wout - 1 ? 2 : 1));
+      }
+      const float* bias = p.bias + static_cast<size_t>(cls) * p.Cout + n0;
+      const size_t out_off = static_cast<size_t>(m) * p.Cout + n0;
+
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint4 rres[4];
+        if (p.res != nullptr && valid) {
+          const uint4* rp = reinterpret_cast<const uint4*>(p.res + out_off + c0);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) rres[j] = __ldg(rp + j);
+        }
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_base + lane_addr + acc * BN + c0, v);
+        tmem_ld_wait();
+        float f[32];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 b = __ldg(reinterpret_cast<const float4*>(bias + c0) + j);
+          f[4 * j + 0] = __uint_as_float(v[4 * j + 0]) + b.x;
+          f[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + b.y;
+          f[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + b.z;
+          f[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + b.w;
+        }
+        if (p.alpha != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(p.alpha + n0 + c0) + j);
+            f[4 * j + 0] = f[4 * j + 0] >= 0.f ? f[4 * j + 0] : f[4 * j + 0] * a.x;
+            f[4 * j + 1] = f[4 * j + 1] >= 0.f ? f[4 * j + 1] : f[4 * j + 1] * a.y;
+            f[4 * j + 2] = f[4 * j + 2] >= 0.f ? f[4 * j + 2] : f[4 * j + 2] * a.z;
+            f[4 * j + 3] = f[4 * j + 3] >= 0.f ? f[4 * j + 3] : f[4 * j + 3] * a.w;
+          }
+        }
+        if (p.res != nullptr && valid) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t w[4] = {rres[j].x, rres[j].y, rres[j].z, rres[j].w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&w[q]);
+              f[8 * j + 2 * q + 0] += __bfloat162float(h.x);
+              f[8 * j + 2 * q + 1] += __bfloat162float(h.y);
+            }
+          }
+        }
+        if (valid) {
+          if (p.out_fp32) {
+            float4* op = reinterpret_cast<float4*>(static_cast<float*>(p.out) + out_off + c0);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) op[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+          } else {
+            uint4* op = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + out_off + c0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              op[j] = make_uint4(pack_bf16x2(f[8 * j + 0], f[8 * j + 1]), pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
+                                 pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), pack_bf16x2(f[8 * j + 6], f[8 * j + 7]));
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tempty_bar[acc]);            // 128 arrivals release the accumulator stage
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 2 * BN);
+  }
+}
+
+}  // namespace cer

@@ -1,0 +1,426 @@
+// IR-50 frame encoder plan: stem kernel, tcgen05 implicit-GEMM residual units, FC head, L2 norm.
+// C-ABI: cer_ir50_* in include/cer_b200.h.  Reference semantics: models/arcface_model.py:44-60,
+// :120-151 and models/backbone.py:99-103 (see DESIGN.md for the BN folding algebra).
+#include <cuda_runtime.h>
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <algorithm>
+
+#include "../../include/cer_b200.h"
+#include "common.h"
+#include "conv_igemm.cuh"
+
+namespace cer {
+
+// ------------------------------------------------------------------------------------------
+// Stem: conv3x3(3->64, pad 1) + BN + PReLU, fp32 NCHW in -> bf16 NHWC out.  K = 27 is not a
+// tensor-core shape; this kernel is bound by its 128 B/pixel output stream (HBM roofline).
+// One thread = one output pixel, all 64 channels; weights [27][64] broadcast from smem.
+// Reference: Backbone.input_layer, models/arcface_model.py:130-132.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) stem_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                   const float* __restrict__ bias, const float* __restrict__ alpha,
+                                                   __nv_bfloat16* __restrict__ out, int n_frames, int H, int W) {
+  __shared__ __align__(16) float ws[27 * 64];
+  __shared__ __align__(16) float bs[64];
+  __shared__ __align__(16) float as[64];
+  for (int i = threadIdx.x; i < 27 * 64; i += blockDim.x) ws[i] = w[i];
+  if (threadIdx.x < 64) {
+    bs[threadIdx.x] = bias[threadIdx.x];
+    as[threadIdx.x] = alpha[threadIdx.x];
+  }
+  __syncthreads();
+  const int hw = H * W;
+  const long long total = static_cast<long long>(n_frames) * hw;
+  for (long long pix = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; pix < total;
+       pix += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int n = static_cast<int>(pix / hw);
+    const int rem = static_cast<int>(pix - static_cast<long long>(n) * hw);
+    const int oh = rem / W, ow = rem - oh * W;
+    float in[27];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+#pragma unroll
+      for (int s = 0; s < 3; ++s) {
+        const int ih = oh + r - 1, iw = ow + s - 1;
+        const bool ok = ih >= 0 && ih < H && iw >= 0 && iw < W;
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+          in[(r * 3 + s) * 3 + c] = ok ? __ldg(x + (static_cast<size_t>(n) * 3 + c) * hw + ih * W + iw) : 0.f;
+      }
+    }
+    uint4* op = reinterpret_cast<uint4*>(out + static_cast<size_t>(pix) * 64);
+#pragma unroll
+    for (int cg = 0; cg < 8; ++cg) {
+      float acc[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = bs[cg * 8 + j];
+#pragma unroll
+      for (int t = 0; t < 27; ++t) {
+        const float4 w0 = *reinterpret_cast<const float4*>(&ws[t * 64 + cg * 8]);
+        const float4 w1 = *reinterpret_cast<const float4*>(&ws[t * 64 + cg * 8 + 4]);
+        acc[0] = fmaf(in[t], w0.x, acc[0]); acc[1] = fmaf(in[t], w0.y, acc[1]);
+        acc[2] = fmaf(in[t], w0.z, acc[2]); acc[3] = fmaf(in[t], w0.w, acc[3]);
+        acc[4] = fmaf(in[t], w1.x, acc[4]); acc[5] = fmaf(in[t], w1.y, acc[5]);
+        acc[6] = fmaf(in[t], w1.z, acc[6]); acc[7] = fmaf(in[t], w1.w, acc[7]);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = acc[j] >= 0.f ? acc[j] : acc[j] * as[cg * 8 + j];
+      op[cg] = make_uint4(pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]), pack_bf16x2(acc[4], acc[5]),
+                          pack_bf16x2(acc[6], acc[7]));
+    }
+  }
+}
+
+// Row-wise L2 normalisation, one warp per row (l2_norm, models/arcface_model.py:17-20; no eps).
+__global__ void l2norm_kernel(const float* __restrict__ in, float* __restrict__ out, int rows, int dim) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float4* ip = reinterpret_cast<const float4*>(in + static_cast<size_t>(row) * dim);
+  float4* op = reinterpret_cast<float4*>(out + static_cast<size_t>(row) * dim);
+  float ss = 0.f;
+  for (int i = lane; i < dim / 4; i += 32) {
+    const float4 v = ip[i];
+    ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  const float inv = 1.0f / sqrtf(ss);
+  for (int i = lane; i < dim / 4; i += 32) {
+    float4 v = ip[i];
+    v.x *= inv; v.y *= inv; v.z *= inv; v.w *= inv;
+    op[i] = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Host side: tensor maps + launch descriptors
+// ------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+typedef CUresult (*PFN_encodeIm2col)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                     const cuuint64_t*, const int*, const int*, cuuint32_t, cuuint32_t,
+                                     const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled g_encode_tiled = nullptr;
+static PFN_encodeIm2col g_encode_im2col = nullptr;
+static int g_driver_version = 0;
+
+static int load_driver_entry_points() {
+  if (g_encode_tiled && g_encode_im2col) return CER_OK;
+  cudaDriverEntryPointQueryResult q;
+  void* fn = nullptr;
+  CER_CUDA(cudaGetDriverEntryPointByVersion("cuTensorMapEncodeTiled", &fn, 12000, cudaEnableDefault, &q));
+  if (q != cudaDriverEntryPointSuccess || !fn) return set_error(CER_ERR_CUDA, "cuTensorMapEncodeTiled not found");
+  g_encode_tiled = reinterpret_cast<PFN_encodeTiled>(fn);
+  CER_CUDA(cudaGetDriverEntryPointByVersion("cuTensorMapEncodeIm2col", &fn, 12000, cudaEnableDefault, &q));
+  if (q != cudaDriverEntryPointSuccess || !fn) return set_error(CER_ERR_CUDA, "cuTensorMapEncodeIm2col not found");
+  g_encode_im2col = reinterpret_cast<PFN_encodeIm2col>(fn);
+  CER_CUDA(cudaDriverGetVersion(&g_driver_version));
+  return CER_OK;
+}
+
+// NHWC bf16 activation [N][H][W][C], im2col traversal of a k x k / stride / pad convolution.
+static int make_im2col_map(CUtensorMap* map, const void* base, int N, int H, int W, int C, int ksize, int stride,
+                           int pad) {
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  int lower[2] = {-pad, -pad};
+  int upper[2] = {pad - (ksize - 1), pad - (ksize - 1)};
+  cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
+  CUresult r = g_encode_im2col(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides,
+                               lower, upper, /*channelsPerPixel*/ kBlockK, /*pixelsPerColumn*/ kBlockM, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                               CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char buf[160];
+    snprintf(buf, sizeof buf, "cuTensorMapEncodeIm2col failed (%d) N=%d H=%d W=%d C=%d k=%d s=%d", (int)r, N, H, W, C,
+             ksize, stride);
+    return set_error(CER_ERR_CUDA, buf);
+  }
+  // Driver quirk (same guard as CUTLASS' im2col descriptor builder): small tensors need bit 21 of
+  // descriptor word 1 cleared on drivers <= 13.1.
+  if (g_driver_version <= 13010 && (size_t)N * H * W * C * 2 < 131072)
+    reinterpret_cast<uint64_t*>(map)[1] &= ~(1ull << 21);
+  return CER_OK;
+}
+
+// Packed weights [Cout][K] bf16, box = 64 (k) x BN (cout), 128B swizzle.
+static int make_weight_map(CUtensorMap* map, const void* base, int Cout, int K, int BN) {
+  cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)Cout};
+  cuuint64_t strides[1] = {(cuuint64_t)K * 2};
+  cuuint32_t box[2] = {(cuuint32_t)kBlockK, (cuuint32_t)BN};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode_tiled(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box,
+                              estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char buf[128];
+    snprintf(buf, sizeof buf, "cuTensorMapEncodeTiled failed (%d) Cout=%d K=%d BN=%d", (int)r, Cout, K, BN);
+    return set_error(CER_ERR_CUDA, buf);
+  }
+  return CER_OK;
+}
+
+struct ConvOp {
+  ConvKernelParams kp;
+  int bn;          // 64 / 128 / 256
+  int hw_out;      // output pixels per frame
+};
+
+struct ConvGeom {
+  const void* src; int H, W, Cin, ksize, stride, pad;
+  const void* src2; int H2, W2, Cin2, stride2;       // fused shortcut operand (Cin2 = 0: none)
+  const void* weight; const float* bias; int bias_classes; const float* alpha;
+  const __nv_bfloat16* res; void* dst; int Cout; int out_fp32;
+};
+
+static int pick_bn(int cout) { return cout % 256 == 0 ? 256 : (cout % 128 == 0 ? 128 : 64); }
+
+static int build_conv_op(ConvOp* op, const ConvGeom& g, int n_cap) {
+  if (g.Cin % kBlockK || g.Cin2 % kBlockK || g.Cout % 64) return set_error(CER_ERR_INVALID, "channels must be multiples of 64");
+  memset(op, 0, sizeof *op);
+  const int Hout = (g.H + 2 * g.pad - g.ksize) / g.stride + 1;
+  const int Wout = (g.W + 2 * g.pad - g.ksize) / g.stride + 1;
+  op->bn = pick_bn(g.Cout);
+  op->hw_out = Hout * Wout;
+  ConvKernelParams& p = op->kp;
+  int rc = make_im2col_map(&p.tmap_a, g.src, n_cap, g.H, g.W, g.Cin, g.ksize, g.stride, g.pad);
+  if (rc) return rc;
+  if (g.Cin2 > 0) {
+    rc = make_im2col_map(&p.tmap_a2, g.src2, n_cap, g.H2, g.W2, g.Cin2, 1, g.stride2, 0);
+    if (rc) return rc;
+    if ((g.H2 - 1) / g.stride2 + 1 != Hout || (g.W2 - 1) / g.stride2 + 1 != Wout)
+      return set_error(CER_ERR_INVALID, "shortcut geometry mismatch");
+  } else {
+    p.tmap_a2 = p.tmap_a;
+  }
+  const int ktot = g.ksize * g.ksize * g.Cin + g.Cin2;
+  rc = make_weight_map(&p.tmap_b, g.weight, g.Cout, ktot, op->bn);
+  if (rc) return rc;
+  p.Hout = Hout; p.Wout = Wout; p.Cout = g.Cout;
+  p.cin_chunks = g.Cin / kBlockK;
+  p.ksize = g.ksize;
+  p.ksteps_main = g.ksize * g.ksize * p.cin_chunks;
+  p.ksteps2 = g.Cin2 / kBlockK;
+  p.stride = g.stride; p.pad = g.pad; p.stride2 = g.stride2 > 0 ? g.stride2 : 1;
+  p.num_n_tiles = g.Cout / op->bn;
+  p.bias_classes = g.bias_classes;
+  p.out_fp32 = g.out_fp32;
+  p.bias = g.bias; p.alpha = g.alpha; p.res = g.res; p.out = g.dst;
+  return CER_OK;
+}
+
+template <int BN, int STAGES>
+static int launch_conv_inst(const ConvKernelParams& p, int grid, cudaStream_t st) {
+  using L = ConvSmem<BN, STAGES>;
+  static bool configured = false;
+  if (!configured) {
+    CER_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
+    configured = true;
+  }
+  conv_igemm_kernel<BN, STAGES><<<grid, kConvThreads, L::kTotal, st>>>(p);
+  CER_CUDA(cudaGetLastError());
+  return CER_OK;
+}
+
+static int launch_conv(const ConvOp& op, int frames, int num_sms, cudaStream_t st) {
+  ConvKernelParams p = op.kp;
+  p.M = frames * op.hw_out;
+  p.num_m_tiles = (p.M + kBlockM - 1) / kBlockM;
+  const int tiles = p.num_m_tiles * p.num_n_tiles;
+  if (tiles == 0) return CER_OK;
+  const int grid = std::min(tiles, num_sms);
+  switch (op.bn) {
+    case 256: return launch_conv_inst<256, 4>(p, grid, st);
+    case 128: return launch_conv_inst<128, 6>(p, grid, st);
+    default:  return launch_conv_inst<64, 8>(p, grid, st);
+  }
+}
+
+}  // namespace cer
+
+using namespace cer;
+
+struct cer_ir50 {
+  cer_ir50_weights w;
+  std::vector<cer_ir_unit> units;
+  int64_t cap;            // frames per pass
+  int n_cap;              // cap + padding frames (tensor-map N extent)
+  int num_sms;
+  uint8_t* buf[3];
+  float* fc_out;          // [cap][emb_dim] pre-norm
+  size_t act_bytes;       // per activation buffer
+  std::vector<ConvOp> ops;          // 2 per unit, then FC
+  struct ActInfo { const void* ptr; int H, W, C; };
+  std::vector<ActInfo> unit_out;    // where each unit's output lives
+  ActInfo stem_out;
+};
+
+static const int kPadFrames = 8;   // a 128-pixel tile may run at most 127 pixels (<= 6 frames of 5x5) past the end
+
+static size_t max_act_bytes_per_frame(const cer_ir50_weights* w) {
+  int H = w->in_h, W = w->in_w;
+  size_t mx = (size_t)H * W * 64 * 2;
+  for (int i = 0; i < w->n_units; ++i) {
+    const cer_ir_unit& u = w->units[i];
+    mx = std::max(mx, (size_t)H * W * u.depth * 2);
+    H = (H - 1) / u.stride + 1;
+    W = (W - 1) / u.stride + 1;
+    mx = std::max(mx, (size_t)H * W * u.depth * 2);
+  }
+  return mx;
+}
+
+extern "C" size_t cer_ir50_workspace_bytes(const cer_ir50_weights* w, int64_t frames_per_pass) {
+  if (!w || frames_per_pass <= 0) return 0;
+  const size_t act = ((max_act_bytes_per_frame(w) * (frames_per_pass + kPadFrames)) + 1023) & ~size_t(1023);
+  const size_t fc = (((size_t)frames_per_pass + kPadFrames) * w->emb_dim * 4 + 1023) & ~size_t(1023);
+  return 3 * act + fc + 1024;
+}
+
+extern "C" int cer_ir50_create(cer_ir50** out, const cer_ir50_weights* w, int64_t frames_per_pass,
+                               void* workspace_dev, size_t workspace_bytes) {
+  if (!out || !w || !workspace_dev || frames_per_pass <= 0 || w->n_units <= 0 || !w->units)
+    return set_error(CER_ERR_INVALID, "cer_ir50_create: null/invalid argument");
+  if (frames_per_pass + kPadFrames > (1 << 24)) return set_error(CER_ERR_INVALID, "frames_per_pass too large");
+  int rc = cer_check_device();
+  if (rc) return rc;
+  rc = load_driver_entry_points();
+  if (rc) return rc;
+  if (workspace_bytes < cer_ir50_workspace_bytes(w, frames_per_pass))
+    return set_error(CER_ERR_WORKSPACE, "cer_ir50_create: workspace too small");
+  if (reinterpret_cast<uintptr_t>(workspace_dev) % 256) return set_error(CER_ERR_INVALID, "workspace must be 256B aligned");
+
+  cer_ir50* p = new cer_ir50();
+  p->w = *w;
+  p->units.assign(w->units, w->units + w->n_units);
+  p->w.units = p->units.data();
+  p->cap = frames_per_pass;
+  p->n_cap = (int)frames_per_pass + kPadFrames;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&p->num_sms, cudaDevAttrMultiProcessorCount, dev);
+  p->act_bytes = ((max_act_bytes_per_frame(w) * p->n_cap) + 1023) & ~size_t(1023);
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(workspace_dev) + 1023) & ~uintptr_t(1023));
+  for (int i = 0; i < 3; ++i) p->buf[i] = base + i * p->act_bytes;
+  p->fc_out = reinterpret_cast<float*>(base + 3 * p->act_bytes);
+
+  int H = w->in_h, W = w->in_w;
+  int cur = 0, tb = 1, nxt = 2;
+  p->stem_out = {p->buf[cur], H, W, 64};
+  int C = 64;
+  for (int i = 0; i < w->n_units; ++i) {
+    const cer_ir_unit& u = p->units[i];
+    if (u.cin != C) { delete p; return set_error(CER_ERR_INVALID, "unit cin does not match previous depth"); }
+    if (!u.has_proj && (u.stride != 1 || u.cin != u.depth)) {
+      delete p;
+      return set_error(CER_ERR_INVALID, "identity shortcut needs stride 1 and cin == depth (MaxPool(1,2) shortcut unsupported)");
+    }
+    ConvGeom g1{};
+    g1.src = p->buf[cur]; g1.H = H; g1.W = W; g1.Cin = u.cin; g1.ksize = 3; g1.stride = 1; g1.pad = 1;
+    g1.weight = u.w1; g1.bias = u.bias1; g1.bias_classes = 9; g1.alpha = u.alpha; g1.res = nullptr;
+    g1.dst = p->buf[tb]; g1.Cout = u.depth; g1.out_fp32 = 0;
+    ConvOp op1;
+    rc = build_conv_op(&op1, g1, p->n_cap);
+    if (rc) { delete p; return rc; }
+    p->ops.push_back(op1);
+
+    ConvGeom g2{};
+    g2.src = p->buf[tb]; g2.H = H; g2.W = W; g2.Cin = u.depth; g2.ksize = 3; g2.stride = u.stride; g2.pad = 1;
+    if (u.has_proj) {
+      g2.src2 = p->buf[cur]; g2.H2 = H; g2.W2 = W; g2.Cin2 = u.cin; g2.stride2 = u.stride;
+    } else {
+      g2.res = reinterpret_cast<const __nv_bfloat16*>(p->buf[cur]);
+    }
+    g2.weight = u.w2; g2.bias = u.bias2; g2.bias_classes = 1; g2.alpha = nullptr;
+    g2.dst = p->buf[nxt]; g2.Cout = u.depth; g2.out_fp32 = 0;
+    ConvOp op2;
+    rc = build_conv_op(&op2, g2, p->n_cap);
+    if (rc) { delete p; return rc; }
+    p->ops.push_back(op2);
+
+    H = (H - 1) / u.stride + 1;
+    W = (W - 1) / u.stride + 1;
+    C = u.depth;
+    p->unit_out.push_back({p->buf[nxt], H, W, C});
+    std::swap(cur, nxt);
+  }
+  if (H * W * C != w->fc_in || w->emb_dim % 64) { delete p; return set_error(CER_ERR_INVALID, "fc_in / emb_dim mismatch"); }
+  ConvGeom gf{};
+  gf.src = p->buf[cur]; gf.H = 1; gf.W = 1; gf.Cin = w->fc_in; gf.ksize = 1; gf.stride = 1; gf.pad = 0;
+  gf.weight = w->fc_w; gf.bias = w->fc_bias; gf.bias_classes = 1; gf.dst = p->fc_out; gf.Cout = w->emb_dim;
+  gf.out_fp32 = 1;
+  ConvOp opf;
+  rc = build_conv_op(&opf, gf, p->n_cap);
+  if (rc) { delete p; return rc; }
+  p->ops.push_back(opf);
+  *out = p;
+  return CER_OK;
+}
+
+static int run_pass(cer_ir50* p, const float* x, int frames, int last_unit, float* emb_out, cudaStream_t st) {
+  const int H = p->w.in_h, W = p->w.in_w;
+  const long long pix = (long long)frames * H * W;
+  const int blocks = (int)std::min<long long>((pix + 127) / 128, (long long)p->num_sms * 16);
+  stem_kernel<<<blocks, 128, 0, st>>>(x, p->w.stem_w, p->w.stem_bias, p->w.stem_alpha,
+                                      reinterpret_cast<__nv_bfloat16*>(p->buf[0]), frames, H, W);
+  CER_CUDA(cudaGetLastError());
+  const int n_units = (int)p->units.size();
+  for (int i = 0; i < n_units && i <= last_unit; ++i) {
+    int rc = launch_conv(p->ops[2 * i], frames, p->num_sms, st);
+    if (rc) return rc;
+    rc = launch_conv(p->ops[2 * i + 1], frames, p->num_sms, st);
+    if (rc) return rc;
+  }
+  if (last_unit >= n_units) {
+    int rc = launch_conv(p->ops[2 * n_units], frames, p->num_sms, st);
+    if (rc) return rc;
+    const int wpb = 8;
+    l2norm_kernel<<<(frames + wpb - 1) / wpb, wpb * 32, 0, st>>>(p->fc_out, emb_out, frames, p->w.emb_dim);
+    CER_CUDA(cudaGetLastError());
+  }
+  return CER_OK;
+}
+
+extern "C" int cer_ir50_forward(cer_ir50* p, const float* x, int64_t n_frames, float* emb_out, void* stream) {
+  if (!p || n_frames < 0 || (n_frames > 0 && (!x || !emb_out))) return set_error(CER_ERR_INVALID, "cer_ir50_forward: bad argument");
+  if (reinterpret_cast<uintptr_t>(x) % 4 || reinterpret_cast<uintptr_t>(emb_out) % 16)
+    return set_error(CER_ERR_INVALID, "cer_ir50_forward: emb_out must be 16B aligned");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t frame_elems = (size_t)3 * p->w.in_h * p->w.in_w;
+  for (int64_t f0 = 0; f0 < n_frames; f0 += p->cap) {
+    const int frames = (int)std::min<int64_t>(p->cap, n_frames - f0);
+    int rc = run_pass(p, x + f0 * frame_elems, frames, (int)p->units.size(), emb_out + f0 * p->w.emb_dim, st);
+    if (rc) return rc;
+  }
+  return CER_OK;
+}
+
+extern "C" int64_t cer_ir50_debug_activation(cer_ir50* p, const float* x, int64_t frames, int32_t unit_index,
+                                             void* dst_dev, void* stream) {
+  if (!p || !x || !dst_dev || frames <= 0 || frames > p->cap || unit_index < -1 || unit_index >= (int)p->units.size())
+    return set_error(CER_ERR_INVALID, "cer_ir50_debug_activation: bad argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int rc = run_pass(p, x, (int)frames, unit_index, nullptr, st);
+  if (rc) return rc;
+  const cer_ir50::ActInfo& a = unit_index < 0 ? p->stem_out : p->unit_out[unit_index];
+  const int64_t elems = frames * a.H * a.W * a.C;
+  CER_CUDA(cudaMemcpyAsync(dst_dev, a.ptr, (size_t)elems * 2, cudaMemcpyDeviceToDevice, st));
+  return elems;
+}
+
+extern "C" int64_t cer_ir50_launches(const cer_ir50* p, int64_t n_frames) {
+  if (!p || n_frames <= 0) return 0;
+  const int64_t passes = (n_frames + p->cap - 1) / p->cap;
+  return passes * (1 + 2 * (int64_t)p->units.size() + 2);
+}
+
+extern "C" void cer_ir50_destroy(cer_ir50* p) { delete p; }

@@ -1,0 +1,204 @@
+"""Device-side engines: packed weights resident in HBM + ctypes calls into libcer_b200.so.
+
+PyTorch is used for device memory (torch.empty), the current stream and nothing else; every
+FLOP of the path runs in the hand-written kernels behind the C-ABI.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Sequence
+
+import torch
+
+from . import _capi
+from ._capi import FusionWeights, Ir50Weights, IrUnit, TcnBlock, check, lib
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+class Ir50Engine:
+    """IR-50 frame encoder plan (cer_ir50_*).  ``frames_per_pass`` bounds the workspace: inputs
+    longer than that are processed in passes inside one C call."""
+
+    def __init__(self, packed: dict, device: torch.device, frames_per_pass: int = 512):
+        _capi.require_gpu()
+        self.device = torch.device(device)
+        self.frames_per_pass = int(frames_per_pass)
+        dev = lambda t: t.to(self.device).contiguous()
+        self._keep: List[torch.Tensor] = []
+
+        def put(t):
+            d = dev(t)
+            self._keep.append(d)
+            return d.data_ptr()
+
+        units = packed["units"]
+        self._units = (IrUnit * len(units))()
+        for i, u in enumerate(units):
+            self._units[i] = IrUnit(u["cin"], u["depth"], u["stride"], u["has_proj"], put(u["w1"]), put(u["bias1"]),
+                                    put(u["alpha"]), put(u["w2"]), put(u["bias2"]))
+        self._w = Ir50Weights(packed["in_hw"], packed["in_hw"], put(packed["stem_w"]), put(packed["stem_bias"]),
+                              put(packed["stem_alpha"]), len(units), self._units, packed["fc_in"], packed["emb_dim"],
+                              put(packed["fc_w"]), put(packed["fc_bias"]))
+        self.emb_dim = packed["emb_dim"]
+        self.in_hw = packed["in_hw"]
+        self.unit_shapes = []
+        hw = self.in_hw
+        for u in units:
+            hw = (hw - 1) // u["stride"] + 1
+            self.unit_shapes.append((hw, hw, u["depth"]))
+        with torch.cuda.device(self.device):
+            nbytes = lib().cer_ir50_workspace_bytes(C.byref(self._w), self.frames_per_pass)
+            self._ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+            h = C.c_void_p()
+            check(lib().cer_ir50_create(C.byref(h), C.byref(self._w), self.frames_per_pass, self._ws.data_ptr(), nbytes),
+                  "cer_ir50_create")
+        self._h = h
+
+    def forward(self, x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """x: [N,3,H,W] fp32 on the engine's device -> [N, emb_dim] fp32, unit norm."""
+        if x.dim() != 4 or x.shape[1] != 3 or x.shape[2] != self.in_hw or x.shape[3] != self.in_hw:
+            raise ValueError(f"expected [N,3,{self.in_hw},{self.in_hw}], got {tuple(x.shape)}")
+        if x.device != self.device or x.dtype != torch.float32:
+            raise ValueError("input must be fp32 on the engine's CUDA device")
+        x = x.contiguous()
+        n = x.shape[0]
+        if out is None:
+            out = torch.empty(n, self.emb_dim, dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            check(lib().cer_ir50_forward(self._h, x.data_ptr(), n, out.data_ptr(), _capi.current_stream_ptr()),
+                  "cer_ir50_forward")
+        return out
+
+    def debug_activation(self, x: torch.Tensor, unit_index: int) -> torch.Tensor:
+        """bf16 NHWC output of unit ``unit_index`` (-1: stem) for the first frames_per_pass frames."""
+        x = x.contiguous()
+        n = x.shape[0]
+        H, W, Cc = (self.in_hw, self.in_hw, 64) if unit_index < 0 else self.unit_shapes[unit_index]
+        dst = torch.empty(n, H, W, Cc, dtype=torch.bfloat16, device=self.device)
+        with torch.cuda.device(self.device):
+            r = lib().cer_ir50_debug_activation(self._h, x.data_ptr(), n, unit_index, dst.data_ptr(),
+                                                _capi.current_stream_ptr())
+        check(int(r), "cer_ir50_debug_activation")
+        return dst
+
+    def launches(self, n_frames: int) -> int:
+        return int(lib().cer_ir50_launches(self._h, n_frames))
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            try:
+                lib().cer_ir50_destroy(h)
+            except Exception:
+                pass
+            self._h = None
+
+
+class TcnEngine:
+    """A stack of fused TemporalBlocks (cer_tcn_block_forward), time-major [B,T,C] fp32."""
+
+    def __init__(self, blocks: Sequence[dict], device: torch.device):
+        _capi.require_gpu()
+        self.device = torch.device(device)
+        self._keep: List[torch.Tensor] = []
+        self.blocks: List[TcnBlock] = []
+        self.c_in = blocks[0]["c_in"]
+        self.c_out = blocks[-1]["c_out"]
+
+        def put(t):
+            if t is None:
+                return None
+            d = t.to(self.device).contiguous()
+            self._keep.append(d)
+            return d.data_ptr()
+
+        for b in blocks:
+            self.blocks.append(TcnBlock(b["c_in"], b["c_out"], b["kernel_size"], b["dilation"], put(b["w1"]), put(b["b1"]),
+                                        put(b["w2"]), put(b["b2"]), put(b["wd"]), put(b["bd"]), put(b["post_scale"]),
+                                        put(b["post_shift"])))
+        self._bufs: Dict[tuple, List[torch.Tensor]] = {}
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        if x.dim() != 3 or x.shape[2] != self.c_in:
+            raise ValueError(f"expected [B,T,{self.c_in}], got {tuple(x.shape)}")
+        if x.device != self.device or x.dtype != torch.float32:
+            raise ValueError("input must be fp32 on the engine's CUDA device")
+        x = x.contiguous()
+        B, T, _ = x.shape
+        stream = _capi.current_stream_ptr()
+        cur = x
+        with torch.cuda.device(self.device):
+            for blk in self.blocks:
+                y = torch.empty(B, T, blk.c_out, dtype=torch.float32, device=self.device)
+                check(lib().cer_tcn_block_forward(C.byref(blk), cur.data_ptr(), y.data_ptr(), B, T, None, 0, stream),
+                      "cer_tcn_block_forward")
+                cur = y
+        return cur
+
+    @property
+    def launches(self) -> int:
+        return len(self.blocks)
+
+
+class FusionEngine:
+    """Cross-modal attention + LayerNorm (+ classifier) (cer_fusion_head_forward)."""
+
+    def __init__(self, fw: dict, device: torch.device):
+        _capi.require_gpu()
+        self.device = torch.device(device)
+        self._keep: List[torch.Tensor] = []
+
+        def put(t):
+            d = t.to(self.device).contiguous()
+            self._keep.append(d)
+            return d.data_ptr()
+
+        w = FusionWeights()
+        w.n_modals = fw["n_modals"]
+        for i, d in enumerate(fw["dim"]):
+            w.dim[i] = d
+            w.wqkv[i] = put(fw["wqkv"][i])
+            w.bqkv[i] = put(fw["bqkv"][i])
+        w.modal_dim, w.num_heads, w.n_out = fw["modal_dim"], fw["num_heads"], fw["n_out"]
+        w.wo, w.bo, w.ln_g, w.ln_b = put(fw["wo"]), put(fw["bo"]), put(fw["ln_g"]), put(fw["ln_b"])
+        w.wr, w.br = put(fw["wr"]), put(fw["br"])
+        self._w = w
+        self.dims = list(fw["dim"])
+        self.n_out = fw["n_out"]
+        self.E = fw["modal_dim"] * fw["n_modals"]
+
+    def forward(self, feats: Sequence[torch.Tensor], want_fused: bool = False):
+        """feats[m]: [rows, D_m] fp32 -> logits [rows, n_out] (and fused [rows, E])."""
+        rows = feats[0].shape[0]
+        keep = []
+        ptrs = (C.c_void_p * len(feats))()
+        for i, f in enumerate(feats):
+            if f.dim() != 2 or f.shape[0] != rows or f.shape[1] != self.dims[i]:
+                raise ValueError(f"modality {i}: expected [{rows},{self.dims[i]}], got {tuple(f.shape)}")
+            if f.device != self.device or f.dtype != torch.float32:
+                raise ValueError("inputs must be fp32 on the engine's CUDA device")
+            f = f.contiguous()
+            keep.append(f)
+            ptrs[i] = f.data_ptr()
+        logits = torch.empty(rows, self.n_out, dtype=torch.float32, device=self.device)
+        fused = torch.empty(rows, self.E, dtype=torch.float32, device=self.device) if want_fused else None
+        with torch.cuda.device(self.device):
+            check(lib().cer_fusion_head_forward(C.byref(self._w), ptrs, rows, logits.data_ptr(), _ptr(fused),
+                                                _capi.current_stream_ptr()), "cer_fusion_head_forward")
+        return (logits, fused) if want_fused else logits
+
+
+def stitch_windows(win_logits: torch.Tensor, win_start: torch.Tensor, length: int) -> torch.Tensor:
+    """win_logits [n_win, win_len, n_out] fp32, win_start int32 [n_win] -> [length, n_out] mean over
+    the windows covering each frame (trainer.py:864-890)."""
+    _capi.require_gpu()
+    n_win, win_len, n_out = win_logits.shape
+    out = torch.empty(length, n_out, dtype=torch.float32, device=win_logits.device)
+    with torch.cuda.device(win_logits.device):
+        check(lib().cer_stitch_windows(win_logits.contiguous().data_ptr(), win_start.contiguous().data_ptr(), n_win,
+                                       win_len, n_out, length, out.data_ptr(), _capi.current_stream_ptr()),
+              "cer_stitch_windows")
+    return out

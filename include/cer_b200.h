@@ -1,0 +1,151 @@
+/* cer_b200.h -- C-ABI of libcer_b200.so: the B200 (sm_100a) LFAN inference hot path.
+ *
+ * The reference (sbelharbi/feature-vs-text-compound-emotion) has no FFI layer: its boundary for
+ * this path is the torch.nn.Module surface.  The entry points below are
+ * what the host-side mirrors of those modules bind (feature_vs_text_compound_emotion_b200/
+ * modules.py via ctypes); each cites the reference code it replaces (paths relative to the
+ * reference root).
+ *
+ * Conventions
+ *   - every pointer named *_dev / inside a *_weights struct is a DEVICE pointer owned by the caller;
+ *   - no entry point allocates device memory (workspaces are caller-provided, sized by the
+ *     *_workspace_bytes functions), none synchronises the device; all work is enqueued on
+ *     `stream` (a cudaStream_t passed as void*);
+ *   - return value: 0 on success, a negative cer_status otherwise (cer_last_error() gives the text);
+ *   - handles are not thread-safe; distinct handles may be used from distinct threads.
+ *   - activations inside the library are NHWC bf16, accumulation fp32; the TCN/fusion head
+ *     computes in fp32.
+ */
+#ifndef CER_B200_H_
+#define CER_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum cer_status {
+  CER_OK = 0,
+  CER_ERR_INVALID = -1,   /* bad shape / null pointer / misaligned pointer            */
+  CER_ERR_ARCH = -2,      /* device is not compute capability 10.x                     */
+  CER_ERR_CUDA = -3,      /* a CUDA runtime/driver call failed                         */
+  CER_ERR_WORKSPACE = -4  /* workspace too small                                       */
+} cer_status;
+
+const char* cer_last_error(void);
+int cer_version(void);
+/* 0 if the current device can run the kernels (sm_100), CER_ERR_ARCH otherwise. */
+int cer_check_device(void);
+
+/* ------------------------------------------------------------------------------------------
+ * IR-50 frame encoder.   Replaces VisualBackbone.forward / Backbone.forward
+ * (models/backbone.py:124-126, models/arcface_model.py:147-151) incl. bottleneck_IR
+ * (arcface_model.py:44-60), the 5x5 output_layer (backbone.py:99-103) and l2_norm (:17-20).
+ * Weights arrive pre-packed by feature_vs_text_compound_emotion_b200/packing.py:
+ * ------------------------------------------------------------------------------------------ */
+typedef struct cer_ir_unit {
+  int32_t cin, depth, stride;   /* bottleneck_IR(in_channel, depth, stride)                        */
+  int32_t has_proj;             /* 1: 1x1/stride conv+BN shortcut fused as extra K columns of w2   */
+  const void* w1;               /* bf16 [depth][9*cin]   res_layer.1 with res_layer.0 (BN) scale folded; K = (r,s,ci) */
+  const float* bias1;           /* fp32 [9][depth]       BN shift pushed through conv1, per border class           */
+  const float* alpha;           /* fp32 [depth]          res_layer.2 PReLU slopes                                   */
+  const void* w2;               /* bf16 [depth][9*depth (+cin)]  res_layer.3 * BN scale (+ shortcut conv * its BN scale) */
+  const float* bias2;           /* fp32 [depth]          res_layer.4 BN shift (+ shortcut BN shift)                 */
+} cer_ir_unit;
+
+typedef struct cer_ir50_weights {
+  int32_t in_h, in_w;           /* 40, 40                                                          */
+  const float* stem_w;          /* fp32 [27][64]  input_layer.0 * input_layer.1 scale; row = (r*3+s)*3+ci */
+  const float* stem_bias;       /* fp32 [64]                                                       */
+  const float* stem_alpha;      /* fp32 [64]      input_layer.2                                    */
+  int32_t n_units;
+  const cer_ir_unit* units;     /* HOST array of n_units entries (device pointers inside)          */
+  int32_t fc_in;                /* H*W*C of the last unit's output (5*5*512)                       */
+  int32_t emb_dim;              /* 512                                                             */
+  const void* fc_w;             /* bf16 [emb_dim][fc_in], K in NHWC (h,w,c) order; output_layer.{0,3,4} folded */
+  const float* fc_bias;         /* fp32 [emb_dim]                                                  */
+} cer_ir50_weights;
+
+typedef struct cer_ir50 cer_ir50;
+
+/* Bytes of device workspace for a plan that processes up to `frames_per_pass` frames per pass. */
+size_t cer_ir50_workspace_bytes(const cer_ir50_weights* w, int64_t frames_per_pass);
+/* Builds TMA descriptors and launch configs over `workspace_dev`.  The weight pointers and the
+ * workspace must stay valid and unmoved for the life of the plan. */
+int cer_ir50_create(cer_ir50** out, const cer_ir50_weights* w, int64_t frames_per_pass, void* workspace_dev,
+                    size_t workspace_bytes);
+/* x_nchw_dev: fp32 [n_frames][3][in_h][in_w] in [-1,1]; emb_out_dev: fp32 [n_frames][emb_dim],
+ * unit L2 norm per row.  Any n_frames >= 0 (processed in passes). */
+int cer_ir50_forward(cer_ir50* plan, const float* x_nchw_dev, int64_t n_frames, float* emb_out_dev, void* stream);
+/* Debug/inspection: run the stem and units 0..unit_index (-1 = stem only) on `frames`
+ * (<= frames_per_pass) frames and copy that unit's bf16 NHWC output to dst_dev
+ * (frames*H*W*C bf16).  Returns the element count or a negative cer_status. */
+int64_t cer_ir50_debug_activation(cer_ir50* plan, const float* x_nchw_dev, int64_t frames, int32_t unit_index,
+                                  void* dst_dev, void* stream);
+/* Number of kernel launches one forward of n_frames enqueues (for bench accounting). */
+int64_t cer_ir50_launches(const cer_ir50* plan, int64_t n_frames);
+void cer_ir50_destroy(cer_ir50* plan);
+
+/* ------------------------------------------------------------------------------------------
+ * One TemporalBlock, fused.   Replaces TemporalBlock.forward
+ * (models/temporal_convolutional_model.py:21-54): weight-normed dilated Conv1d + Chomp1d +
+ * LeakyReLU, twice, plus identity / 1x1 residual and the final LeakyReLU.  Optionally applies a
+ * trailing per-channel affine (the eval BatchNorm1d of models/model.py:475,515) to the output.
+ * Layout: x [B][T][c_in] fp32 (time-major rows, channels contiguous), y [B][T][c_out] fp32.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct cer_tcn_block {
+  int32_t c_in, c_out, kernel_size, dilation;
+  const float* w1;      /* fp32 [k][c_in][c_out]   effective (g*v/||v||) conv1 weight, tap-major        */
+  const float* b1;      /* fp32 [c_out]                                                                  */
+  const float* w2;      /* fp32 [k][c_out][c_out]  effective conv2 weight                                */
+  const float* b2;      /* fp32 [c_out]                                                                  */
+  const float* wd;      /* fp32 [c_in][c_out]      1x1 downsample or NULL (identity residual)            */
+  const float* bd;      /* fp32 [c_out] or NULL                                                          */
+  const float* post_scale; /* fp32 [c_out] or NULL: y = y*post_scale + post_shift after the last LeakyReLU */
+  const float* post_shift;
+} cer_tcn_block;
+
+size_t cer_tcn_block_workspace_bytes(const cer_tcn_block* blk, int64_t batch, int64_t length);
+int cer_tcn_block_forward(const cer_tcn_block* blk, const float* x_dev, float* y_dev, int64_t batch, int64_t length,
+                          void* workspace_dev, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Cross-modal attention fusion + classifier, fused.   Replaces
+ * MultimodalTransformerEncoder.forward (models/transformer.py:200-209, :168-197, :102-165,
+ * :11-19) followed by cat + regressor of LFAN.forward (models/model.py:517-521).
+ * feats[m]: fp32 [rows][dim[m]] (rows = B*T frames); logits: fp32 [rows][n_out].
+ * ------------------------------------------------------------------------------------------ */
+#define CER_MAX_MODALS 4
+typedef struct cer_fusion_weights {
+  int32_t n_modals;                 /* 1..CER_MAX_MODALS; modality 0 is the leader              */
+  int32_t dim[CER_MAX_MODALS];      /* encoder_dim per modality (128, 32, 128)                   */
+  int32_t modal_dim, num_heads;     /* 32, 2                                                     */
+  int32_t n_out;                    /* classifier outputs (7)                                    */
+  const float* wqkv[CER_MAX_MODALS];/* fp32 [dim[m]][3*modal_dim]  qkv_proj.<m>.weight transposed */
+  const float* bqkv[CER_MAX_MODALS];/* fp32 [3*modal_dim]                                         */
+  const float* wo;                  /* fp32 [E][E] o_proj.weight transposed (in-major), E = modal_dim*n_modals */
+  const float* bo;                  /* fp32 [E]                                                   */
+  const float* ln_g;                /* fp32 [E] norm1.weight                                      */
+  const float* ln_b;                /* fp32 [E] norm1.bias                                        */
+  const float* wr;                  /* fp32 [dim[0]+E][n_out] regressor.weight transposed         */
+  const float* br;                  /* fp32 [n_out]                                               */
+} cer_fusion_weights;
+
+int cer_fusion_head_forward(const cer_fusion_weights* w, const float* const* feats_dev, int64_t rows,
+                            float* logits_dev, float* fused_out_dev /* [rows][E] or NULL */, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Window stitching.   Replaces the sum / overlap-count / divide of
+ * Trainer.inference_forward_windows (trainer.py:864-890) on device.
+ * win_logits: fp32 [n_windows][win_len][n_out]; win_start: int32 [n_windows] first frame of each
+ * window; out: fp32 [length][n_out] = mean over the windows covering each frame.
+ * ------------------------------------------------------------------------------------------ */
+int cer_stitch_windows(const float* win_logits_dev, const int32_t* win_start_dev, int32_t n_windows,
+                       int32_t win_len, int32_t n_out, int64_t length, float* out_dev, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CER_B200_H_ */

@@ -1,0 +1,88 @@
+"""Drop-in boundary on the CPU: constructors, state_dict layout, strict loading, C-ABI symbols.
+No compute calls (those need a GPU and live in test_gpu_*.py)."""
+import ctypes
+import json
+import os
+import re
+import warnings
+
+import pytest
+import torch
+
+from feature_vs_text_compound_emotion_b200 import _capi, synthetic
+
+warnings.filterwarnings("ignore")
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BS = {"visual_state_dict": "res50_ir_0.887", "audio_state_dict": "vggish"}
+
+
+def _lfan(mods):
+    from feature_vs_text_compound_emotion_b200.models.model import LFAN
+    m = LFAN(backbone_settings=BS, output_dim=7, task="CLASSIFICATION", modality=mods, kernel_size=5,
+             example_length=300, tcn_channel=synthetic.TCN_CHANNELS, modal_dim=32, num_heads=2, root_dir="",
+             device="cpu")
+    m.init(visual_state_dict=synthetic.visual_backbone_state_dict(0) if "video" in mods else None)
+    return m
+
+
+def test_lfan_state_dict_layout_equals_reference(golden_dir):
+    keys = json.load(open(os.path.join(golden_dir, "state_keys.json")))
+    m = _lfan(["video", "vggish", "bert"])
+    sd = m.state_dict()
+    assert list(sd) == list(keys)
+    for k, v in sd.items():
+        assert list(v.shape) == keys[k], k
+    m.load_state_dict(synthetic.lfan_state_dict(0, ["video", "vggish", "bert"]), strict=True)
+    trainable = sum(p.numel() for p in m.parameters() if p.requires_grad)
+    assert trainable == 5002503
+    assert sum(p.numel() for p in m.parameters()) == 42290127
+
+
+def test_feature_only_modalities():
+    m = _lfan(["cnn_res50", "vggish", "bert"])
+    assert "spatial.visual.backbone.input_layer.0.weight" not in m.state_dict()
+    m.load_state_dict(synthetic.lfan_state_dict(0, ["cnn_res50", "vggish", "bert"]), strict=True)
+    assert m.final_dim == 224
+
+
+def test_visual_backbone_loads_checkpoint_layout(tmp_path):
+    from feature_vs_text_compound_emotion_b200.models.backbone import VisualBackbone
+    p = tmp_path / "res50_ir_0.887.pth"
+    torch.save(synthetic.visual_backbone_state_dict(0), p)
+    vb = VisualBackbone(use_pretrained=True, state_dict_path=str(p))
+    assert len(vb.state_dict()) == 351
+    assert vb.backbone.output_layer[3].in_features == 12800
+
+
+def test_forward_fails_loudly_without_gpu():
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    m = _lfan(["cnn_res50", "vggish", "bert"]).eval()
+    X = synthetic.feature_windows(1, 300)
+    with pytest.raises(_capi.CerError):
+        with torch.no_grad():
+            m(X)
+
+
+def test_training_mode_is_rejected_not_silently_wrong():
+    m = _lfan(["cnn_res50", "vggish", "bert"]).train()
+    with pytest.raises(NotImplementedError):
+        m(synthetic.feature_windows(1, 300))
+
+
+def test_capi_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "cer_b200.h")).read()
+    declared = set(re.findall(r"\b(cer_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    assert declared == set(_capi.SIGNATURES), declared ^ set(_capi.SIGNATURES)
+    lib = _capi.lib()
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.cer_version() >= 100
+
+
+def test_struct_sizes_match_header_layout():
+    # 64-bit: int32 x4 + 5 pointers; guards against silent ctypes/header drift
+    assert ctypes.sizeof(_capi.IrUnit) == 16 + 5 * 8
+    assert ctypes.sizeof(_capi.TcnBlock) == 16 + 8 * 8
+    assert ctypes.sizeof(_capi.Ir50Weights) == 8 + 3 * 8 + 8 + 8 + 8 + 2 * 8
