@@ -57,6 +57,9 @@ SIGNATURES = {
     "cer_ir50_debug_activation": (C.c_int64, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]),
     "cer_ir50_launches": (C.c_int64, [C.c_void_p, C.c_int64]),
     "cer_ir50_destroy": (None, [C.c_void_p]),
+    "cer_conv_forward": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
+                                   C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p,
+                                   C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     "cer_tcn_block_workspace_bytes": (C.c_size_t, [C.POINTER(TcnBlock), C.c_int64, C.c_int64]),
     "cer_tcn_block_forward": (C.c_int, [C.POINTER(TcnBlock), C.c_void_p, C.c_void_p, C.c_int64, C.c_int64,
                                         C.c_void_p, C.c_size_t, C.c_void_p]),

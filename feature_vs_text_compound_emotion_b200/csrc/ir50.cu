@@ -424,3 +424,29 @@ extern "C" int64_t cer_ir50_launches(const cer_ir50* p, int64_t n_frames) {
 }
 
 extern "C" void cer_ir50_destroy(cer_ir50* p) { delete p; }
+
+// Single convolution through the same kernel (tests and per-layer-class roofline measurements;
+// the plan above is the production path).  Builds its tensor maps per call.
+extern "C" int cer_conv_forward(const void* src_nhwc, int32_t n_frames, int32_t n_alloc, int32_t h, int32_t w,
+                                int32_t cin, const void* weight, int32_t cout, int32_t ksize, int32_t stride,
+                                int32_t pad, const float* bias, int32_t bias_classes, const float* alpha,
+                                const void* res, void* dst, int32_t out_fp32, void* stream) {
+  if (!src_nhwc || !weight || !bias || !dst || n_frames <= 0 || n_alloc < n_frames || (ksize != 1 && ksize != 3) ||
+      (bias_classes != 1 && bias_classes != 9))
+    return set_error(CER_ERR_INVALID, "cer_conv_forward: bad argument");
+  int rc = cer_check_device();
+  if (rc) return rc;
+  rc = load_driver_entry_points();
+  if (rc) return rc;
+  ConvGeom g{};
+  g.src = src_nhwc; g.H = h; g.W = w; g.Cin = cin; g.ksize = ksize; g.stride = stride; g.pad = pad;
+  g.weight = weight; g.bias = bias; g.bias_classes = bias_classes; g.alpha = alpha;
+  g.res = static_cast<const __nv_bfloat16*>(res); g.dst = dst; g.Cout = cout; g.out_fp32 = out_fp32;
+  ConvOp op;
+  rc = build_conv_op(&op, g, n_alloc);
+  if (rc) return rc;
+  int dev = 0, sms = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  return launch_conv(op, n_frames, sms, static_cast<cudaStream_t>(stream));
+}

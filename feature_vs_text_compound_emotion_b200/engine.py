@@ -202,3 +202,22 @@ def stitch_windows(win_logits: torch.Tensor, win_start: torch.Tensor, length: in
                                        win_len, n_out, length, out.data_ptr(), _capi.current_stream_ptr()),
               "cer_stitch_windows")
     return out
+
+
+def conv_forward(src: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, ksize: int, stride: int, pad: int,
+                 alpha: Optional[torch.Tensor] = None, res: Optional[torch.Tensor] = None, out_fp32: bool = False,
+                 n_frames: Optional[int] = None) -> torch.Tensor:
+    """One convolution through the tcgen05 implicit-GEMM kernel (cer_conv_forward).
+    src bf16 [N,H,W,Cin]; weight bf16 [Cout, k*k*Cin]; bias fp32 [1|9, Cout] -> [n,Ho,Wo,Cout]."""
+    _capi.require_gpu()
+    n_alloc, H, W, cin = src.shape
+    n = n_alloc if n_frames is None else n_frames
+    cout = weight.shape[0]
+    ho, wo = (H + 2 * pad - ksize) // stride + 1, (W + 2 * pad - ksize) // stride + 1
+    dst = torch.empty(n, ho, wo, cout, dtype=torch.float32 if out_fp32 else torch.bfloat16, device=src.device)
+    bias = bias.reshape(-1, cout).contiguous()
+    with torch.cuda.device(src.device):
+        check(lib().cer_conv_forward(src.contiguous().data_ptr(), n, n_alloc, H, W, cin, weight.contiguous().data_ptr(),
+                                     cout, ksize, stride, pad, bias.data_ptr(), bias.shape[0], _ptr(alpha), _ptr(res),
+                                     dst.data_ptr(), int(out_fp32), _capi.current_stream_ptr()), "cer_conv_forward")
+    return dst

@@ -88,6 +88,17 @@ int64_t cer_ir50_debug_activation(cer_ir50* plan, const float* x_nchw_dev, int64
 int64_t cer_ir50_launches(const cer_ir50* plan, int64_t n_frames);
 void cer_ir50_destroy(cer_ir50* plan);
 
+/* One convolution through the same tcgen05 implicit-GEMM kernel (tests, per-layer roofline runs).
+ * src: bf16 NHWC [n_alloc][h][w][cin] (n_alloc >= n_frames is the allocated / tensor-map extent);
+ * weight: bf16 [cout][ksize*ksize*cin] with K = (r,s,ci); bias: fp32 [bias_classes][cout]
+ * (bias_classes 9 = border-class table, stride-1 pad-1 3x3 only); alpha: PReLU slopes or NULL;
+ * res: bf16 [M][cout] residual or NULL; dst: bf16 (or fp32 if out_fp32) [M][cout],
+ * M = n_frames*hout*wout.  cin, cout multiples of 64. */
+int cer_conv_forward(const void* src_nhwc_dev, int32_t n_frames, int32_t n_alloc, int32_t h, int32_t w, int32_t cin,
+                     const void* weight_dev, int32_t cout, int32_t ksize, int32_t stride, int32_t pad,
+                     const float* bias_dev, int32_t bias_classes, const float* alpha_dev, const void* res_dev,
+                     void* dst_dev, int32_t out_fp32, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * One TemporalBlock, fused.   Replaces TemporalBlock.forward
  * (models/temporal_convolutional_model.py:21-54): weight-normed dilated Conv1d + Chomp1d +

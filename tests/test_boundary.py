@@ -66,7 +66,7 @@ def test_forward_fails_loudly_without_gpu():
 
 def test_training_mode_is_rejected_not_silently_wrong():
     m = _lfan(["cnn_res50", "vggish", "bert"]).train()
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(NotImplementedError), torch.enable_grad():
         m(synthetic.feature_windows(1, 300))
 
 

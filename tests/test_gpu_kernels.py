@@ -1,0 +1,184 @@
+"""GPU parity tests, kernel by kernel, through the C-ABI (libcer_b200.so).
+
+Each CUDA kernel is compared with a plain fp32 PyTorch computation of the same op on the CPU
+(F.conv2d etc. on the bf16-rounded operands the kernel sees), so a failure points at one kernel.
+Tolerances: bf16 outputs -> error relative to the tensor's max <= 1e-2 (one bf16 ulp is 2^-8 of
+the value); fp32 head kernels -> 1e-4 absolute.
+"""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from feature_vs_text_compound_emotion_b200 import packing, synthetic
+from oracle import lfan_oracle as O
+from tests import emulate
+
+pytestmark = pytest.mark.gpu
+torch.set_grad_enabled(False)
+
+
+def _dev():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    return torch.device("cuda:0")
+
+
+def _rel_err(a, b):
+    a, b = a.float().cpu(), b.float().cpu()
+    return ((a - b).abs().max() / b.abs().max().clamp_min(1e-6)).item()
+
+
+def _conv_case(dev, n, H, cin, cout, ksize, stride, classes, prelu, residual, fp32, seed, n_alloc=None):
+    from feature_vs_text_compound_emotion_b200.engine import conv_forward
+    g = torch.Generator().manual_seed(seed)
+    pad = 1 if ksize == 3 else 0
+    n_alloc = n_alloc or n
+    x = torch.randn(n_alloc, H, H, cin, generator=g).to(torch.bfloat16)
+    w = (torch.randn(cout, ksize, ksize, cin, generator=g) * (ksize * ksize * cin) ** -0.5).to(torch.bfloat16)
+    bias = 0.5 * torch.randn(classes, cout, generator=g)
+    alpha = (0.25 + 0.1 * torch.randn(cout, generator=g)) if prelu else None
+    Ho = (H + 2 * pad - ksize) // stride + 1
+    res = torch.randn(n, Ho, Ho, cout, generator=g).to(torch.bfloat16) if residual else None
+    # fp32 reference on the same bf16-rounded operands
+    y = F.conv2d(x[:n].float().permute(0, 3, 1, 2), w.float().permute(0, 3, 1, 2), None, stride, pad)
+    if classes == 9:
+        y = y + bias[emulate.border_class_map(Ho, Ho)].permute(2, 0, 1).unsqueeze(0)
+    else:
+        y = y + bias.view(1, -1, 1, 1)
+    if prelu:
+        y = torch.where(y >= 0, y, y * alpha.view(1, -1, 1, 1))
+    y = y.permute(0, 2, 3, 1)
+    if residual:
+        y = y + res.float()
+    out = conv_forward(x.to(dev), w.reshape(cout, -1).to(dev), bias.to(dev), ksize, stride, pad,
+                       alpha=None if alpha is None else alpha.to(dev), res=None if res is None else res.to(dev),
+                       out_fp32=fp32, n_frames=n)
+    torch.cuda.synchronize()
+    return _rel_err(out, y), out, y
+
+
+# (n, H, cin, cout, ksize, stride, classes, prelu, residual, fp32)
+CONV_CASES = [
+    (3, 10, 256, 256, 3, 1, 9, True, False, False),     # stage-3 conv1 (the 50.7% class), ragged M = 300
+    (3, 10, 256, 256, 3, 1, 1, False, True, False),     # stage-3 conv2 + residual
+    (2, 40, 64, 64, 3, 1, 9, True, False, False),       # stage-1 conv1, BN = 64
+    (2, 40, 64, 128, 3, 1, 9, True, False, False),      # widening conv1
+    (2, 40, 128, 128, 3, 2, 1, False, False, False),    # stride-2 conv2
+    (5, 20, 128, 128, 3, 1, 1, False, True, False),     # stage 2
+    (7, 5, 512, 512, 3, 1, 9, True, False, False),      # stage 4: 25 px/frame, tiles span frames, 2 n-tiles
+    (4, 10, 256, 512, 3, 1, 9, True, False, False),     # widening to 512
+    (4, 10, 512, 512, 3, 2, 1, False, False, False),    # stride-2 at 10x10 -> 5x5
+    (3, 40, 64, 128, 1, 2, 1, False, False, False),     # 1x1 stride-2 projection alone
+    (130, 1, 12800, 512, 1, 1, 1, False, False, True),  # the FC head as a 1x1 conv, fp32 out, 2 m-tiles
+    (1, 5, 512, 512, 3, 1, 9, True, True, False),       # a single frame (tiny tensor: driver-quirk path)
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES, ids=lambda c: "n%d_h%d_%dto%d_k%ds%d_c%d%s%s%s" % (
+    c[0], c[1], c[2], c[3], c[4], c[5], c[6], "_prelu" if c[7] else "", "_res" if c[8] else "", "_f32" if c[9] else ""))
+def test_conv_igemm_matches_conv2d(case):
+    dev = _dev()
+    err, out, ref = _conv_case(dev, *case, seed=11)
+    assert err < 1e-2, f"relative error {err}"
+
+
+def test_conv_igemm_padded_allocation_matches():
+    """Same layer with the tensor-map extent larger than the valid frames (the plan's layout)."""
+    dev = _dev()
+    err, _, _ = _conv_case(dev, 3, 10, 256, 256, 3, 1, 9, True, False, False, seed=12, n_alloc=11)
+    assert err < 1e-2
+
+
+def test_stem_and_units_progressively():
+    """Stem, then the output of selected residual units, against the packed-weight emulation
+    (which tests/test_packing.py ties to the oracle)."""
+    dev = _dev()
+    from feature_vs_text_compound_emotion_b200.engine import Ir50Engine
+    sd = synthetic.visual_backbone_state_dict(0)
+    pk = packing.pack_ir50(sd, "backbone.")
+    x = synthetic.frames(5, seed=21)
+    _, taps = emulate.ir50_packed(pk, x, round_act=True)
+    eng = Ir50Engine(pk, dev, frames_per_pass=16)
+    for unit in (-1, 0, 2, 3, 6, 7, 8, 20, 21, 23):
+        got = eng.debug_activation(x.to(dev), unit)
+        torch.cuda.synchronize()
+        err = _rel_err(got, taps[unit])
+        assert err < 3e-2, f"unit {unit}: relative error {err}"
+
+
+def test_ir50_embedding_vs_golden(golden_dir):
+    import os
+    dev = _dev()
+    from feature_vs_text_compound_emotion_b200.engine import Ir50Engine
+    g = torch.load(os.path.join(golden_dir, "ir50_n4.pt"))
+    sd = synthetic.visual_backbone_state_dict(g["weights_seed"])
+    eng = Ir50Engine(packing.pack_ir50(sd, "backbone."), dev, frames_per_pass=8)
+    emb = eng.forward(synthetic.frames(g["n"], seed=g["x_seed"]).to(dev)).cpu()
+    cos = F.cosine_similarity(emb, g["emb"], dim=1)
+    assert cos.min().item() >= 0.999, cos          # BASELINE.json tolerance
+    assert torch.allclose(emb.norm(dim=1), torch.ones(4), atol=1e-4)
+
+
+@pytest.mark.parametrize("n,fpp", [(1, 8), (13, 8), (37, 16), (64, 64)])
+def test_ir50_passes_and_ragged_counts(n, fpp):
+    """n not a multiple of the pass size / tile size gives the same rows as one big pass."""
+    dev = _dev()
+    from feature_vs_text_compound_emotion_b200.engine import Ir50Engine
+    sd = synthetic.visual_backbone_state_dict(0)
+    pk = packing.pack_ir50(sd, "backbone.")
+    x = synthetic.frames(n, seed=31).to(dev)
+    a = Ir50Engine(pk, dev, frames_per_pass=fpp).forward(x)
+    b = Ir50Engine(pk, dev, frames_per_pass=128).forward(x)
+    torch.cuda.synchronize()
+    # frames are independent: identical arithmetic per frame regardless of batching
+    assert torch.equal(a, b)
+    ref = O.ir50_forward(sd, x[: min(n, 4)].cpu(), "backbone.")
+    assert F.cosine_similarity(a[: min(n, 4)].cpu(), ref, dim=1).min().item() >= 0.999
+
+
+@pytest.mark.parametrize("modal,B,T", [("vggish", 2, 300), ("cnn_res50", 1, 300), ("bert", 3, 77), ("vggish", 1, 5)])
+def test_tcn_stack_vs_oracle(modal, B, T):
+    dev = _dev()
+    from feature_vs_text_compound_emotion_b200.engine import TcnEngine
+    sd = synthetic.head_state_dict(2, [modal])
+    x = torch.randn(B, T, synthetic.EMBEDDING_DIM[modal], generator=torch.Generator().manual_seed(5))
+    want = O._bn_eval(sd, f"bn.{modal}", O.tcn_forward(sd, f"temporal.{modal}.", x.transpose(1, 2))).transpose(1, 2)
+    eng = TcnEngine(packing.pack_tcn(sd, f"temporal.{modal}.", f"bn.{modal}"), dev)
+    got = eng.forward(x.to(dev)).cpu()
+    assert (got - want).abs().max().item() < 1e-4
+
+
+def test_fusion_head_vs_oracle():
+    dev = _dev()
+    from feature_vs_text_compound_emotion_b200.engine import FusionEngine
+    mods = ["cnn_res50", "vggish", "bert"]
+    sd = synthetic.lfan_state_dict(4, mods)
+    g = torch.Generator().manual_seed(9)
+    rows = 603                                  # not a multiple of the 4-frame warp group
+    feats = [torch.randn(rows, d, generator=g) for d in (128, 32, 128)]
+    enc = {m: f.view(1, rows, -1) for m, f in zip(mods, feats)}
+    fused = O.fusion_forward(sd, "fusion.", enc, mods)
+    want = F.linear(torch.cat((enc[mods[0]], fused), -1), sd["regressor.weight"], sd["regressor.bias"])[0]
+    eng = FusionEngine(packing.pack_fusion(sd, mods, 32, 2), dev)
+    logits, fz = eng.forward([f.to(dev) for f in feats], want_fused=True)
+    assert (fz.cpu() - fused[0]).abs().max().item() < 1e-4
+    assert (logits.cpu() - want).abs().max().item() < 1e-4
+
+
+def test_stitch_windows_vs_oracle():
+    dev = _dev()
+    from feature_vs_text_compound_emotion_b200.engine import stitch_windows
+    L = 701
+    wins = O.windowing(L, 300, 200)
+    g = torch.Generator().manual_seed(3)
+    wl = torch.randn(len(wins), 300, 7, generator=g)
+    out = torch.zeros(L, 7)
+    cnt = torch.zeros(L)
+    for i, w in enumerate(wins):
+        out[w] += wl[i]
+        cnt[w] += 1
+    want = out / cnt.view(-1, 1)
+    starts = torch.tensor([int(w[0]) for w in wins], dtype=torch.int32)
+    got = stitch_windows(wl.to(dev), starts.to(dev), L).cpu()
+    assert (got - want).abs().max().item() < 1e-6

@@ -1,0 +1,107 @@
+"""End-to-end GPU parity of the drop-in modules against the reference-generated goldens.
+Tolerances are BASELINE.json's: embedding cosine >= 0.999, logit max-abs <= 2e-2, argmax
+agreement >= 99.5 %."""
+import os
+import warnings
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from feature_vs_text_compound_emotion_b200 import synthetic
+from oracle import lfan_oracle as O
+
+pytestmark = pytest.mark.gpu
+torch.set_grad_enabled(False)
+warnings.filterwarnings("ignore")
+BS = {"visual_state_dict": "res50_ir_0.887", "audio_state_dict": "vggish"}
+
+
+def _dev():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    return torch.device("cuda:0")
+
+
+def _lfan(mods, dev, seed=0):
+    from feature_vs_text_compound_emotion_b200.models.model import LFAN
+    m = LFAN(backbone_settings=BS, output_dim=7, task="CLASSIFICATION", modality=mods, kernel_size=5,
+             example_length=300, tcn_channel=synthetic.TCN_CHANNELS, modal_dim=32, num_heads=2, root_dir="",
+             device=dev)
+    m.init(visual_state_dict=synthetic.visual_backbone_state_dict(seed) if "video" in mods else None)
+    m.load_state_dict(synthetic.lfan_state_dict(seed, mods), strict=True)
+    return m.to(dev).eval()
+
+
+def test_head_only_vs_golden(golden_dir):
+    """BASELINE config 1 shape: B=2 x T=300 pre-extracted features."""
+    dev = _dev()
+    g = torch.load(os.path.join(golden_dir, "head_b2.pt"))
+    mods = g["modalities"]
+    m = _lfan(mods, dev, g["weights_seed"])
+    X = {k: v.to(dev) for k, v in synthetic.feature_windows(g["batch"], 300, seed=g["x_seed"], modalities=mods).items()}
+    out = m(X).cpu()
+    assert out.shape == (2, 300, 7)
+    assert (out - g["logits"]).abs().max().item() <= 2e-2
+    assert (out - g["logits"]).abs().max().item() <= 1e-3      # the head is fp32: much tighter in practice
+    assert (out.argmax(-1) == g["logits"].argmax(-1)).float().mean().item() >= 0.995
+
+
+def test_full_lfan_from_pixels_vs_golden(golden_dir):
+    dev = _dev()
+    g = torch.load(os.path.join(golden_dir, "lfan_b1.pt"))
+    mods = g["modalities"]
+    m = _lfan(mods, dev, g["weights_seed"])
+    feats = synthetic.feature_windows(1, 300, seed=g["feat_seed"], modalities=["vggish", "bert"])
+    X = {"video": synthetic.frames(300, seed=g["frame_seed"]).view(1, 300, 3, 40, 40).to(dev),
+         "vggish": feats["vggish"].to(dev), "bert": feats["bert"].to(dev)}
+    out = m(X).cpu()
+    err = (out - g["logits"]).abs().max().item()
+    agree = (out.argmax(-1) == g["logits"].argmax(-1)).float().mean().item()
+    assert err <= 2e-2, err
+    assert agree >= 0.995, agree
+
+
+def test_visual_backbone_module_cosine():
+    dev = _dev()
+    from feature_vs_text_compound_emotion_b200.models.backbone import VisualBackbone
+    sd = synthetic.visual_backbone_state_dict(3)
+    vb = VisualBackbone(use_pretrained=False)
+    vb.load_state_dict(sd, strict=True)
+    vb = vb.to(dev).eval()
+    x = synthetic.frames(24, seed=8)
+    emb = vb(x.to(dev)).cpu()
+    ref = O.ir50_forward(sd, x, "backbone.")
+    assert F.cosine_similarity(emb, ref, dim=1).min().item() >= 0.999
+    assert torch.equal(vb.extract(x.to(dev)).cpu(), emb)
+
+
+def test_submodules_keep_reference_layouts():
+    """TemporalConvNet takes [B,C,T]; MultimodalTransformerEncoder takes a dict of [B,T,D]."""
+    dev = _dev()
+    mods = ["cnn_res50", "vggish", "bert"]
+    m = _lfan(mods, dev)
+    sd = synthetic.lfan_state_dict(0, mods)
+    x = torch.randn(2, 128, 300, generator=torch.Generator().manual_seed(1))
+    got = m.temporal["vggish"](x.to(dev)).cpu()
+    want = O.tcn_forward(sd, "temporal.vggish.", x)
+    assert got.shape == (2, 32, 300) and (got - want).abs().max().item() < 1e-4
+    enc = {k: torch.randn(2, 300, d, generator=torch.Generator().manual_seed(2)) for k, d in
+           zip(mods, (128, 32, 128))}
+    fused = m.fusion({k: v.to(dev) for k, v in enc.items()}).cpu()
+    assert (fused - O.fusion_forward(sd, "fusion.", enc, mods)).abs().max().item() < 1e-4
+
+
+def test_argmax_agreement_over_many_frames():
+    """600 frames from pixels, different weights seed: the 99.5 % argmax bar with margin."""
+    dev = _dev()
+    mods = ["video", "vggish", "bert"]
+    m = _lfan(mods, dev, seed=5)
+    sd = synthetic.lfan_state_dict(5, mods)
+    feats = synthetic.feature_windows(2, 300, seed=41, modalities=["vggish", "bert"])
+    vid = synthetic.frames(600, seed=42).view(2, 300, 3, 40, 40)
+    X = {"video": vid, "vggish": feats["vggish"], "bert": feats["bert"]}
+    ref = O.lfan_forward(sd, {k: v.clone() for k, v in X.items()}, mods)
+    out = m({k: v.to(dev) for k, v in X.items()}).cpu()
+    assert (out - ref).abs().max().item() <= 2e-2
+    assert (out.argmax(-1) == ref.argmax(-1)).float().mean().item() >= 0.995
