@@ -307,8 +307,8 @@ def main():
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": burst, "unit": "TFLOP/s", "frac": achieved / burst,
                      "traffic": traffic, "kernel": "conv_igemm_kernel<256,4> 256->256 3x3 @10x10",
                      "frames_per_launch": dom_frames, "ms_per_launch": dom_ms, "peak_source": f"{src} burst"},
-        "ir50": {"ms": ir50_ms, "tflops": IR50_GFLOP_PER_FRAME * frames / ir50_ms / 1e6,
-                 "frac_of_sustained_peak": IR50_GFLOP_PER_FRAME * frames / ir50_ms / 1e6 / sustained,
+        "ir50": {"ms": ir50_ms, "tflops": IR50_GFLOP_PER_FRAME * frames / ir50_ms,
+                 "frac_of_sustained_peak": IR50_GFLOP_PER_FRAME * frames / ir50_ms / sustained,
                  "share_of_step": ir50_ms / ms_per_step},
     }
     if world == 1 and not args.no_cpu_baseline:

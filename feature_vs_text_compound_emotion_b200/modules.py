@@ -100,7 +100,7 @@ class Backbone(_PackedModule):
     The CUDA plan is built for the spatial size the output_layer expects (H = 8*sqrt(fc_in/512));
     as in the reference, a mismatching input size is an error."""
 
-    frames_per_pass = 512
+    frames_per_pass = 2400      # frames per pass of the plan (workspace ~1.25 MB per frame)
 
     def __init__(self, num_layers, drop_ratio, input_channels=3, mode='ir'):
         super().__init__()
