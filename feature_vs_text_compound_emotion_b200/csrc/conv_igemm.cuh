@@ -8,8 +8,11 @@
 //                                             the TMA unit, so a tile may start at any pixel.
 //   B tile (BN couts x 64 k, bf16)          : TMA tiled load from the packed weight matrix [Cout][K].
 //   D (128 x BN fp32)                       : TMEM accumulator, double buffered (2*BN columns).
-// Warp roles (192 threads): warps 0-3 epilogue (one TMEM lane = one output pixel per thread),
-// warp 4 TMA producer, warp 5 TMEM allocator + single-thread tcgen05.mma issuer.
+// Warp roles (416 threads): warps 0-7 epilogue (warp w reads TMEM lanes 32*(w%4).., i.e. one output
+// pixel per thread, and the column half w/4), warp 8 TMEM allocator + single-thread tcgen05.mma
+// issuer, warps 9-10 TMA producers for A (even / odd k-steps), warps 11-12 TMA producers for B.  Four producer threads because one
+// thread sustains only one TMA issue per ~410 cycles (mbarrier wait + expect_tx + issue; measured
+// with tools/tma_probe.cu), while the TMA path itself delivers a 16 KB tile every ~200 cycles.
 // Persistent: grid = min(#tiles, #SMs); tiles are walked n-tile-fastest so neighbouring CTAs
 // share the same activation rows in L2.
 //
@@ -28,6 +31,7 @@ struct alignas(64) ConvKernelParams {
   int M;                 // valid output pixels
   int Hout, Wout, Cout;
   int cin_chunks;        // Cin/64
+  int cin_shift;         // log2(cin_chunks) when ksize == 3 (power of two there); unused for ksize == 1
   int ksize;             // 1 or 3
   int ksteps_main;       // ksize*ksize*cin_chunks
   int ksteps2;           // Cin2/64 or 0
@@ -42,7 +46,11 @@ struct alignas(64) ConvKernelParams {
   void* out;             // [M][Cout]
 };
 
-constexpr int kConvThreads = 192;
+constexpr int kConvThreads = 416;
+constexpr int kEpiWarps = 8;
+constexpr int kMmaWarp = 8;
+constexpr int kProdWarp0 = 9;
+constexpr int kProducersPerOperand = 2;
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;           // 64 bf16 = 128 B = one swizzle row
 constexpr int kABytes = kBlockM * 128;
@@ -52,7 +60,9 @@ struct ConvSmem {
   static constexpr int kBBytes = BN * 128;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kBarOffset = STAGES * kStageBytes;
-  static constexpr int kTotal = kBarOffset + (2 * STAGES + 4) * 8 + 16 + 1024 /*alignment slack*/;
+  static constexpr int kTableOffset = kBarOffset + (2 * STAGES + 4) * 8 + 16;      // bias table + PReLU slopes
+  static constexpr int kTableBytes = (9 * 512 + 512) * 4;                          // worst case: 9 classes x 512 couts
+  static constexpr int kTotal = kTableOffset + kTableBytes + 1024 /*alignment slack*/;
 };
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
@@ -70,77 +80,110 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
   uint64_t* tfull_bar = empty_bar + STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  float* s_bias = reinterpret_cast<float*>(smem + L::kTableOffset);     // [bias_classes][Cout]
+  float* s_alpha = s_bias + p.bias_classes * p.Cout;                    // [Cout]
 
-  const int warp = threadIdx.x >> 5;
+  // warp index broadcast from lane 0 so the compiler treats role dispatch and the role loops as
+  // warp-uniform (descriptors and addresses then live in uniform registers)
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
   const int total_tiles = p.num_m_tiles * p.num_n_tiles;
   const int ksteps = p.ksteps_main + p.ksteps2;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full_bar[s], 1);
+      mbar_init(&full_bar[s], 2);          // one arrive.expect_tx from the A producer, one from the B producer
       mbar_init(&empty_bar[s], 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull_bar[a], 1);
-      mbar_init(&tempty_bar[a], 128);
+      mbar_init(&tempty_bar[a], kEpiWarps * 32);
     }
     fence_barrier_init();
   }
-  if (warp == 4 && lane == 0) {
+  if (warp == kProdWarp0 && lane == 0) {
     tma_prefetch_desc(&p.tmap_a);
-    tma_prefetch_desc(&p.tmap_b);
     if (p.ksteps2 > 0) tma_prefetch_desc(&p.tmap_a2);
   }
-  if (warp == 5) {
+  if (warp == kProdWarp0 + kProducersPerOperand && lane == 0) tma_prefetch_desc(&p.tmap_b);
+  if (warp == kMmaWarp) {
     tmem_alloc(tmem_slot, 2 * BN);
     tmem_relinquish();
+  }
+  if (warp < kEpiWarps) {     // stage the epilogue constants once per CTA
+    for (int i = threadIdx.x; i < p.bias_classes * p.Cout; i += kEpiWarps * 32) s_bias[i] = __ldg(p.bias + i);
+    if (p.alpha != nullptr)
+      for (int i = threadIdx.x; i < p.Cout; i += kEpiWarps * 32) s_alpha[i] = __ldg(p.alpha + i);
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 4) {
-    // ===================== TMA producer (one lane) =====================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
+  if (warp >= kProdWarp0) {
+    // ===================== TMA producers (one lane each) =====================
+    // first two: A operand of k-steps g = 0,1 (mod 2); next two: B operand likewise.  g counts
+    // k-steps across all tiles of this CTA, so stage = g % STAGES and the phase flips per wrap.
+    // Control flow is warp-uniform (all 32 lanes walk the loop and wait on the barrier); one
+    // elected lane issues expect_tx + the TMA.
+    {
+      const bool is_a = warp < kProdWarp0 + kProducersPerOperand;
+      const int q = (warp - kProdWarp0) % kProducersPerOperand;
       const int hw = p.Hout * p.Wout;
+      int stage = q % STAGES;
+      uint32_t phase = (q / STAGES) & 1;
+      int ks_carry = q;                       // first k-step of this producer inside the current tile
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int m_tile = tile / p.num_n_tiles;
         const int n_tile = tile - m_tile * p.num_n_tiles;
-        const int m0 = m_tile * kBlockM;
-        const int n_img = m0 / hw;
-        const int rem = m0 - n_img * hw;
-        const int oh = rem / p.Wout;
-        const int ow = rem - oh * p.Wout;
-        for (int ks = 0; ks < ksteps; ++ks) {
+        int cw = 0, ch = 0, n_img = 0, cw2 = 0, ch2 = 0;
+        if (is_a) {
+          const int m0 = m_tile * kBlockM;
+          n_img = m0 / hw;
+          const int rem = m0 - n_img * hw;
+          const int oh = rem / p.Wout;
+          const int ow = rem - oh * p.Wout;
+          cw = ow * p.stride - p.pad; ch = oh * p.stride - p.pad;
+          cw2 = ow * p.stride2; ch2 = oh * p.stride2;
+        }
+        int ks = ks_carry;
+        for (; ks < ksteps; ks += kProducersPerOperand) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * L::kStageBytes;
-          uint8_t* sb = sa + kABytes;
-          mbar_expect_tx(&full_bar[stage], L::kStageBytes);
-          if (ks < p.ksteps_main) {
-            const int tap = ks / p.cin_chunks;
-            const int chunk = ks - tap * p.cin_chunks;
-            const int r = tap / p.ksize;
-            const int s = tap - r * p.ksize;
-            tma_load_im2col_4d(&p.tmap_a, &full_bar[stage], sa, chunk * kBlockK, ow * p.stride - p.pad,
-                               oh * p.stride - p.pad, n_img, (uint16_t)s, (uint16_t)r);
+          if (is_a) {
+            int tap = 0, chunk = ks;
+            if (p.ksize == 3) { tap = ks >> p.cin_shift; chunk = ks & (p.cin_chunks - 1); }
+            const int r = (tap * 11) >> 5;          // tap / 3 for tap in [0, 9)
+            const int s = tap - r * 3;
+            const bool main_op = ks < p.ksteps_main;
+            if (elect_one()) {
+              mbar_expect_tx(&full_bar[stage], kABytes);
+              if (main_op) {
+                tma_load_im2col_4d(&p.tmap_a, &full_bar[stage], sa, chunk * kBlockK, cw, ch, n_img, (uint16_t)s,
+                                   (uint16_t)r);
+              } else {
+                tma_load_im2col_4d(&p.tmap_a2, &full_bar[stage], sa, (ks - p.ksteps_main) * kBlockK, cw2, ch2, n_img,
+                                   0, 0);
+              }
+            }
           } else {
-            const int chunk = ks - p.ksteps_main;
-            tma_load_im2col_4d(&p.tmap_a2, &full_bar[stage], sa, chunk * kBlockK, ow * p.stride2, oh * p.stride2,
-                               n_img, 0, 0);
+            if (elect_one()) {
+              mbar_expect_tx(&full_bar[stage], L::kBBytes);
+              tma_load_2d(&p.tmap_b, &full_bar[stage], sa + kABytes, ks * kBlockK, n_tile * BN);
+            }
           }
-          tma_load_2d(&p.tmap_b, &full_bar[stage], sb, ks * kBlockK, n_tile * BN);
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          __syncwarp();
+          stage += kProducersPerOperand;
+          if (stage >= STAGES) { stage -= STAGES; phase ^= 1; }
         }
+        ks_carry = ks - ksteps;                 // keeps the global even/odd split across tiles
       }
     }
-  } else if (warp == 5) {
-    // ===================== MMA issuer (one lane) =====================
-    if (lane == 0) {
+  } else if (warp == kMmaWarp) {
+    // ===================== MMA issuer (warp-uniform loop, one elected lane issues) =====================
+    {
       constexpr uint32_t idesc = umma_idesc(kBlockM, BN, /*bf16*/ 1);
+      const uint32_t smem_base = smem_u32(smem);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -153,24 +196,33 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
         for (int ks = 0; ks < ksteps; ++ks) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem + stage * L::kStageBytes);
-          const uint32_t b_addr = a_addr + kABytes;
+          const uint32_t a_addr = smem_base + stage * L::kStageBytes;
+          const uint64_t adesc = umma_desc_sw128(a_addr);
+          const uint64_t bdesc = umma_desc_sw128(a_addr + kABytes);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < kBlockK / 16; ++k) {
-            umma_f16(tmem_d, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc,
-                     (ks | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < kBlockK / 16; ++k) {
+              // +32 bytes along K inside the 128 B swizzle row == +2 in the (addr >> 4) field
+              umma_f16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (ks | k) != 0 ? 1u : 0u);
+            }
+            umma_commit(&empty_bar[stage]);       // frees the smem slot once these MMAs retire
+            if (ks == ksteps - 1) umma_commit(&tfull_bar[acc]);   // accumulator complete -> epilogue
           }
-          umma_commit(&empty_bar[stage]);       // frees the smem slot once these MMAs retire
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tfull_bar[acc]);           // accumulator complete -> epilogue
       }
     }
   } else {
-    // ===================== Epilogue (warps 0-3, 128 threads) =====================
-    const int row = warp * 32 + lane;           // TMEM lane == row of the M tile
-    const uint32_t lane_addr = (static_cast<uint32_t>(warp * 32) << 16);
+    // ===================== Epilogue (warps 0-7, 256 threads) =====================
+    constexpr int kHalf = BN / 2;                // columns per thread per tile
+    const int quarter = warp & 3;                // TMEM lane quarter this warp may read
+    const int half = warp >> 2;                  // column half
+    const int row = quarter * 32 + lane;         // TMEM lane == row of the M tile
+    const uint32_t lane_addr = (static_cast<uint32_t>(quarter * 32) << 16);
     const int hw = p.Hout * p.Wout;
+    const bool has_res = p.res != nullptr;
+    const bool has_alpha = p.alpha != nullptr;
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
@@ -179,7 +231,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
       const int n_tile = tile - m_tile * p.num_n_tiles;
       const int m = m_tile * kBlockM + row;
       const bool valid = m < p.M;
-      const int n0 = n_tile * BN;
+      const int n0 = n_tile * BN + half * kHalf;
       int cls = 0;
       if (p.bias_classes == 9) {
         const int rem = m % hw;
@@ -187,42 +239,54 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
         const int ow = rem - oh * p.Wout;
         cls = (oh == 0 ? 0 : (oh == p.Hout - 1 ? 2 : 1)) * 3 + (ow == 0 ? 0 : (ow == p.Wout - 1 ? 2 : 1));
       }
-      const float* bias = p.bias + static_cast<size_t>(cls) * p.Cout + n0;
+      const float* sb = s_bias + cls * p.Cout + n0;
+      const float* sal = s_alpha + n0;
       const size_t out_off = static_cast<size_t>(m) * p.Cout + n0;
+      const bool ld_res = has_res && valid;
 
+      // residual of the first chunk is requested before the accumulator wait: its latency hides
+      // behind the MMA of this tile
+      uint4 rnext[4];
+      if (ld_res) {
+        const uint4* rp = reinterpret_cast<const uint4*>(p.res + out_off);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) rnext[j] = __ldg(rp + j);
+      }
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
-#pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        uint4 rres[4];
-        if (p.res != nullptr && valid) {
-          const uint4* rp = reinterpret_cast<const uint4*>(p.res + out_off + c0);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) rres[j] = __ldg(rp + j);
-        }
+      for (int c0 = 0; c0 < kHalf; c0 += 32) {
         uint32_t v[32];
-        tmem_ld_32x32(tmem_base + lane_addr + acc * BN + c0, v);
+        tmem_ld_32x32(tmem_base + lane_addr + acc * BN + half * kHalf + c0, v);
+        uint4 rres[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) rres[j] = rnext[j];
+        if (c0 + 32 < kHalf && ld_res) {
+          const uint4* rp = reinterpret_cast<const uint4*>(p.res + out_off + c0 + 32);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) rnext[j] = __ldg(rp + j);
+        }
         tmem_ld_wait();
         float f[32];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const float4 b = __ldg(reinterpret_cast<const float4*>(bias + c0) + j);
+          const float4 b = *reinterpret_cast<const float4*>(sb + c0 + 4 * j);
           f[4 * j + 0] = __uint_as_float(v[4 * j + 0]) + b.x;
           f[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + b.y;
           f[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + b.z;
           f[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + b.w;
         }
-        if (p.alpha != nullptr) {
+        if (has_alpha) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            const float4 a = __ldg(reinterpret_cast<const float4*>(p.alpha + n0 + c0) + j);
+            const float4 a = *reinterpret_cast<const float4*>(sal + c0 + 4 * j);
             f[4 * j + 0] = f[4 * j + 0] >= 0.f ? f[4 * j + 0] : f[4 * j + 0] * a.x;
             f[4 * j + 1] = f[4 * j + 1] >= 0.f ? f[4 * j + 1] : f[4 * j + 1] * a.y;
             f[4 * j + 2] = f[4 * j + 2] >= 0.f ? f[4 * j + 2] : f[4 * j + 2] * a.z;
             f[4 * j + 3] = f[4 * j + 3] >= 0.f ? f[4 * j + 3] : f[4 * j + 3] * a.w;
           }
         }
-        if (p.res != nullptr && valid) {
+        if (ld_res) {
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const uint32_t w[4] = {rres[j].x, rres[j].y, rres[j].z, rres[j].w};
@@ -250,13 +314,13 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
         }
       }
       tc_fence_before();
-      mbar_arrive(&tempty_bar[acc]);            // 128 arrivals release the accumulator stage
+      mbar_arrive(&tempty_bar[acc]);            // 256 arrivals release the accumulator stage
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) {
+  if (warp == kMmaWarp) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 2 * BN);
   }

@@ -207,6 +207,10 @@ static int build_conv_op(ConvOp* op, const ConvGeom& g, int n_cap) {
   if (rc) return rc;
   p.Hout = Hout; p.Wout = Wout; p.Cout = g.Cout;
   p.cin_chunks = g.Cin / kBlockK;
+  p.cin_shift = 0;
+  while ((1 << p.cin_shift) < p.cin_chunks) ++p.cin_shift;
+  if (g.ksize == 3 && (1 << p.cin_shift) != p.cin_chunks)
+    return set_error(CER_ERR_INVALID, "3x3 conv needs Cin/64 to be a power of two");
   p.ksize = g.ksize;
   p.ksteps_main = g.ksize * g.ksize * p.cin_chunks;
   p.ksteps2 = g.Cin2 / kBlockK;
