@@ -16,9 +16,9 @@ CSRC = os.path.join(HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 LIB = os.path.join(HERE, "libcer_b200.so")
 STAMP = os.path.join(HERE, ".libcer_b200.stamp")
-SOURCES = ["common.cu", "ir50.cu", "tcn.cu", "fusion.cu"]
+SOURCES = ["common.cu", "ir50.cu", "tcn.cu", "tcn_tc.cu", "fusion.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "--use_fast_math" if False else "-DCER_NO_FAST_MATH", "-Xcompiler", "-fPIC,-O2"]
+              "-Xcompiler", "-fPIC,-O2"]
 
 
 def _nvcc() -> str:

@@ -169,6 +169,46 @@ static int make_weight_map(CUtensorMap* map, const void* base, int Cout, int K, 
   return CER_OK;
 }
 
+// Generic helpers shared with the TCN tensor-core path (tcn_tc.cu).
+int make_im2col_map_generic(CUtensorMap* map, CUtensorMapDataType dt, int elem_bytes, const void* base, int N, int H,
+                            int W, int C, const int lower[2], const int upper[2], int stride, int channels_per_pixel) {
+  int rc = load_driver_entry_points();
+  if (rc) return rc;
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)C * elem_bytes, (cuuint64_t)W * C * elem_bytes, (cuuint64_t)H * W * C * elem_bytes};
+  cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
+  CUresult r = g_encode_im2col(map, dt, 4, const_cast<void*>(base), dims, strides, lower, upper, channels_per_pixel,
+                               kBlockM, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                               CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char buf[160];
+    snprintf(buf, sizeof buf, "cuTensorMapEncodeIm2col failed (%d) N=%d H=%d W=%d C=%d elem=%d", (int)r, N, H, W, C, elem_bytes);
+    return set_error(CER_ERR_CUDA, buf);
+  }
+  if (g_driver_version <= 13010 && (size_t)N * H * W * C * elem_bytes < 131072)
+    reinterpret_cast<uint64_t*>(map)[1] &= ~(1ull << 21);
+  return CER_OK;
+}
+
+int make_tiled2d_map_generic(CUtensorMap* map, CUtensorMapDataType dt, int elem_bytes, const void* base, int rows,
+                             int cols, int box_rows, int box_cols) {
+  int rc = load_driver_entry_points();
+  if (rc) return rc;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)cols * elem_bytes};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode_tiled(map, dt, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char buf[128];
+    snprintf(buf, sizeof buf, "cuTensorMapEncodeTiled failed (%d) rows=%d cols=%d", (int)r, rows, cols);
+    return set_error(CER_ERR_CUDA, buf);
+  }
+  return CER_OK;
+}
+
 struct ConvOp {
   ConvKernelParams kp;
   int bn;          // 64 / 128 / 256

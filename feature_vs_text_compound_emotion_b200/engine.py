@@ -98,11 +98,18 @@ class Ir50Engine:
 
 
 class TcnEngine:
-    """A stack of fused TemporalBlocks (cer_tcn_block_forward), time-major [B,T,C] fp32."""
+    """A stack of TemporalBlocks, time-major [B,T,C] fp32.
 
-    def __init__(self, blocks: Sequence[dict], device: torch.device):
+    precision="tf32" (default): tcgen05 kind::tf32 tensor-core kernel, two launches per block
+    (cer_tcn_block_tc_forward).  precision="fp32": the CUDA-core fused kernel, one launch per
+    block (cer_tcn_block_forward) -- exact fp32 FMA, ~10x slower, kept for numerics work."""
+
+    def __init__(self, blocks: Sequence[dict], device: torch.device, precision: str = "tf32"):
         _capi.require_gpu()
+        if precision not in ("tf32", "fp32"):
+            raise ValueError(precision)
         self.device = torch.device(device)
+        self.precision = precision
         self._keep: List[torch.Tensor] = []
         self.blocks: List[TcnBlock] = []
         self.c_in = blocks[0]["c_in"]
@@ -115,11 +122,14 @@ class TcnEngine:
             self._keep.append(d)
             return d.data_ptr()
 
+        if precision == "tf32":
+            from .packing import tcn_block_to_kmajor
+            blocks = [tcn_block_to_kmajor(b) for b in blocks]
         for b in blocks:
             self.blocks.append(TcnBlock(b["c_in"], b["c_out"], b["kernel_size"], b["dilation"], put(b["w1"]), put(b["b1"]),
                                         put(b["w2"]), put(b["b2"]), put(b["wd"]), put(b["bd"]), put(b["post_scale"]),
                                         put(b["post_shift"])))
-        self._bufs: Dict[tuple, List[torch.Tensor]] = {}
+        self._ws: Optional[torch.Tensor] = None
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         if x.dim() != 3 or x.shape[2] != self.c_in:
@@ -131,16 +141,25 @@ class TcnEngine:
         stream = _capi.current_stream_ptr()
         cur = x
         with torch.cuda.device(self.device):
+            if self.precision == "tf32":
+                need = max(B * T * blk.c_out * 4 for blk in self.blocks)
+                if self._ws is None or self._ws.numel() < need:
+                    self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
             for blk in self.blocks:
                 y = torch.empty(B, T, blk.c_out, dtype=torch.float32, device=self.device)
-                check(lib().cer_tcn_block_forward(C.byref(blk), cur.data_ptr(), y.data_ptr(), B, T, None, 0, stream),
-                      "cer_tcn_block_forward")
+                if self.precision == "tf32":
+                    check(lib().cer_tcn_block_tc_forward(C.byref(blk), cur.data_ptr(), y.data_ptr(), B, T,
+                                                         self._ws.data_ptr(), self._ws.numel(), stream),
+                          "cer_tcn_block_tc_forward")
+                else:
+                    check(lib().cer_tcn_block_forward(C.byref(blk), cur.data_ptr(), y.data_ptr(), B, T, None, 0, stream),
+                          "cer_tcn_block_forward")
                 cur = y
         return cur
 
     @property
     def launches(self) -> int:
-        return len(self.blocks)
+        return len(self.blocks) * (2 if self.precision == "tf32" else 1)
 
 
 class FusionEngine:

@@ -120,9 +120,24 @@ def weight_norm_effective(g: torch.Tensor, v: torch.Tensor) -> torch.Tensor:
     return g.double() * v / v.reshape(v.shape[0], -1).norm(dim=1).view(-1, 1, 1)
 
 
+def tcn_block_to_kmajor(blk: dict) -> dict:
+    """Tap-major fp32-kernel layout -> the K-major layout of the tensor-core kernel:
+    w1 [cout][k*cin] with K = (tap, ci); w2 [cout][k*cout (+ cin)] with the downsample appended."""
+    out = dict(blk)
+    k, cin, cout = blk["w1"].shape
+    out["w1"] = blk["w1"].permute(2, 0, 1).reshape(cout, k * cin).contiguous()
+    w2 = blk["w2"].permute(2, 0, 1).reshape(cout, k * cout)
+    if blk["wd"] is not None:
+        w2 = torch.cat([w2, blk["wd"].t()], dim=1)
+    out["w2"] = w2.contiguous()
+    out["layout"] = "k_major"
+    return out
+
+
 def pack_tcn(sd: Dict[str, torch.Tensor], prefix: str, bn_prefix: str = None) -> List[dict]:
     """prefix = 'temporal.<m>.'; bn_prefix = 'bn.<m>' folds the trailing BatchNorm1d
-    (models/model.py:515) into the last block's output affine."""
+    (models/model.py:515) into the last block's output affine.  Returns the tap-major layout
+    ([k][cin][cout]); engine.TcnEngine converts to K-major for the tensor-core kernel."""
     blocks = []
     i = 0
     while f"{prefix}network.{i}.conv1.weight_v" in sd:

@@ -122,6 +122,15 @@ size_t cer_tcn_block_workspace_bytes(const cer_tcn_block* blk, int64_t batch, in
 int cer_tcn_block_forward(const cer_tcn_block* blk, const float* x_dev, float* y_dev, int64_t batch, int64_t length,
                           void* workspace_dev, size_t workspace_bytes, void* stream);
 
+/* Tensor-core variant (tcgen05 kind::tf32: fp32 operands, 10-bit-mantissa multiply, fp32
+ * accumulate) -- the production path.  Same struct, different weight layout:
+ *   w1: fp32 [c_out][k*c_in], K = (tap, ci);   w2: fp32 [c_out][k*c_out (+ c_in)] with the 1x1
+ *   downsample weights appended as the last c_in columns (wd != NULL only flags their presence,
+ *   bd is its bias).  Channels must be multiples of 32.  workspace holds conv1's output. */
+size_t cer_tcn_block_tc_workspace_bytes(const cer_tcn_block* blk, int64_t batch, int64_t length);
+int cer_tcn_block_tc_forward(const cer_tcn_block* blk, const float* x_dev, float* y_dev, int64_t batch, int64_t length,
+                             void* workspace_dev, size_t workspace_bytes, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Cross-modal attention fusion + classifier, fused.   Replaces
  * MultimodalTransformerEncoder.forward (models/transformer.py:200-209, :168-197, :102-165,
