@@ -1,0 +1,58 @@
+"""Long-video inference: windows of 300 frames every 200, overlap averaging -- on the device.
+
+Restates the semantics of Trainer.windowing / window_input / inference_forward_windows
+(trainer.py:788-913) around the CUDA path, with two exact savings the reference leaves on the
+table:
+  * IR-50 is per-frame in eval mode, so every *unique* frame is encoded once and the 512-d
+    embeddings are windowed, instead of re-encoding the 100-frame overlaps (33-50 % less conv work);
+  * all windows of a video go through the head as one batch (the reference loops with bsz 1).
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Sequence
+
+import torch
+
+
+def window_starts(length: int, window_length: int = 300, hop_length: int = 200) -> List[int]:
+    """First frame of every window: a regular grid while a full window fits, plus one tail window
+    flush with the end when the grid does not reach the last frame (trainer.py:894-913)."""
+    if length < window_length:
+        return [0]
+    starts = list(range(0, length - window_length + 1, hop_length))
+    if starts[-1] + window_length < length:
+        starts.append(length - window_length)
+    return starts
+
+
+def gather_windows(feat: torch.Tensor, starts: Sequence[int], window_length: int) -> torch.Tensor:
+    """feat [T, D] -> [n_windows, window_length, D].  A video shorter than the window is padded by
+    repeating its last frame (the reference's training-time rule, base/dataset.py:570-582)."""
+    T = feat.shape[0]
+    if T < window_length:
+        pad = feat[-1:].expand(window_length - T, *feat.shape[1:])
+        feat = torch.cat([feat, pad], dim=0)
+    idx = torch.as_tensor(starts, device=feat.device).view(-1, 1) + torch.arange(window_length, device=feat.device)
+    return feat[idx]
+
+
+@torch.no_grad()
+def infer_video(model, video: torch.Tensor, feats: Dict[str, torch.Tensor], window_length: int = 300,
+                hop_length: int = 200) -> torch.Tensor:
+    """One whole video through the LFAN mirror.
+
+    video: [T,3,40,40] fp32 on the GPU (post eval-transform), feats[m]: [T, D_m] for the
+    non-visual modalities.  Returns per-frame logits [T, n_out] = the reference's stitched output.
+    """
+    from .engine import stitch_windows
+    T = video.shape[0]
+    emb = model.spatial["visual"](video)                       # every unique frame once
+    starts = window_starts(T, window_length, hop_length)
+    batch = {}
+    for m in model.modality:
+        src = emb if m == "video" else feats[m]
+        batch[m] = gather_windows(src, starts, window_length).contiguous()
+    logits = model.forward_features(batch)                     # [n_windows, window_length, n_out]
+    start_t = torch.as_tensor(starts, dtype=torch.int32, device=video.device)
+    out = stitch_windows(logits, start_t, max(T, window_length))
+    return out[:T]

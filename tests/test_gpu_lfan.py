@@ -105,3 +105,31 @@ def test_argmax_agreement_over_many_frames():
     out = m({k: v.to(dev) for k, v in X.items()}).cpu()
     assert (out - ref).abs().max().item() <= 2e-2
     assert (out.argmax(-1) == ref.argmax(-1)).float().mean().item() >= 0.995
+
+
+def test_long_video_windowing_dedup_and_stitch():
+    """501-frame video: unique frames encoded once, 3 windows batched through the head, stitched on
+    device -- equals the reference procedure (every window from scratch, overlap-averaged)."""
+    dev = _dev()
+    from feature_vs_text_compound_emotion_b200 import windowing
+    mods = ["video", "vggish", "bert"]
+    m = _lfan(mods, dev, seed=2)
+    sd = synthetic.lfan_state_dict(2, mods)
+    L = 501
+    vid = synthetic.frames(L, seed=51)
+    g = torch.Generator().manual_seed(52)
+    feats = {"vggish": torch.randn(L, 128, generator=g), "bert": torch.randn(L, 768, generator=g)}
+    out = windowing.infer_video(m, vid.to(dev), {k: v.to(dev) for k, v in feats.items()}).cpu()
+    assert out.shape == (L, 7)
+    # oracle: frames are independent in eval mode, so embeddings may be computed once for the check
+    emb = O.ir50_forward(sd, vid, "spatial.visual.backbone.")
+    X = {"video": emb.view(1, 1, L, 512), "vggish": feats["vggish"].view(1, 1, L, 128), "bert": feats["bert"].view(1, 1, L, 768)}
+
+    def fwd(chunk):
+        return O.head_forward(sd, {k: v.squeeze(1) for k, v in chunk.items()}, mods)
+    Xo = {"video": X["video"], "vggish": X["vggish"], "bert": X["bert"]}
+    # oracle.windowed_inference indexes [:, :, wd] for non-'video' keys and [:, wd] for 'video'
+    Xo["video"] = X["video"].squeeze(1)
+    want = O.windowed_inference(lambda c: fwd({"video": c["video"].unsqueeze(1), "vggish": c["vggish"], "bert": c["bert"]}), Xo)[0]
+    assert (out - want).abs().max().item() <= 2e-2
+    assert (out.argmax(-1) == want.argmax(-1)).float().mean().item() >= 0.995
