@@ -55,14 +55,22 @@ constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;           // 64 bf16 = 128 B = one swizzle row
 constexpr int kABytes = kBlockM * 128;
 
-template <int BN, int STAGES>
+constexpr int kBresSteps = 9;          // weights-resident variant: all 9 taps of a Cin=64 layer stay in smem
+
+// BRES = true: the whole weight matrix of the layer (9 k-steps x BN x 128 B) is loaded once per CTA
+// and stays in shared memory; the ring stages then carry only the A operand.  Used for the
+// Cin = 64 layers, where the TMA path (~80 B/cycle/SM) rather than the tensor pipe is the limit
+// and B would otherwise be a third of the traffic.
+template <int BN, int STAGES, bool BRES>
 struct ConvSmem {
   static constexpr int kBBytes = BN * 128;
-  static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kBarOffset = STAGES * kStageBytes;
-  static constexpr int kTableOffset = kBarOffset + (2 * STAGES + 4) * 8 + 16;      // bias table + PReLU slopes
-  static constexpr int kTableBytes = (9 * 512 + 512) * 4;                          // worst case: 9 classes x 512 couts
-  static constexpr int kTotal = kTableOffset + kTableBytes + 1024 /*alignment slack*/;
+  static constexpr int kStageBytes = kABytes + (BRES ? 0 : kBBytes);
+  static constexpr int kBresOffset = STAGES * kStageBytes;
+  static constexpr int kBarOffset = kBresOffset + (BRES ? kBresSteps * kBBytes : 0);
+  static constexpr int kNumBars = 2 * STAGES + 5;                                   // full, empty, tfull[2], tempty[2], bres
+  static constexpr int kTableOffset = (kBarOffset + kNumBars * 8 + 16 + 15) & ~15;  // bias table + PReLU slopes (float4 reads)
+  static constexpr int kTableFloats = 10 * (BN == 256 ? 512 : BN);                 // [<=9][Cout] + [Cout]
+  static constexpr int kTotal = kTableOffset + kTableFloats * 4 + 1024 /*alignment slack*/;
 };
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
@@ -70,16 +78,17 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool BRES>
 __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
-  using L = ConvSmem<BN, STAGES>;
+  using L = ConvSmem<BN, STAGES, BRES>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOffset);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tfull_bar = empty_bar + STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* bres_bar = tempty_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bres_bar + 1);
   float* s_bias = reinterpret_cast<float*>(smem + L::kTableOffset);     // [bias_classes][Cout]
   float* s_alpha = s_bias + p.bias_classes * p.Cout;                    // [Cout]
 
@@ -92,13 +101,14 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full_bar[s], 2);          // one arrive.expect_tx from the A producer, one from the B producer
+      mbar_init(&full_bar[s], BRES ? 1 : 2);   // one arrive.expect_tx per operand that travels through the ring
       mbar_init(&empty_bar[s], 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull_bar[a], 1);
       mbar_init(&tempty_bar[a], kEpiWarps * 32);
     }
+    mbar_init(bres_bar, 1);
     fence_barrier_init();
   }
   if (warp == kProdWarp0 && lane == 0) {
@@ -125,12 +135,24 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
     // first two: A operand of k-steps g = 0,1 (mod 2); next two: B operand likewise.  g counts
     // k-steps across all tiles of this CTA, so stage = g % STAGES and the phase flips per wrap.
     // Control flow is warp-uniform (all 32 lanes walk the loop and wait on the barrier); one
-    // elected lane issues expect_tx + the TMA.
-    {
-      const bool is_a = warp < kProdWarp0 + kProducersPerOperand;
-      const int q = (warp - kProdWarp0) % kProducersPerOperand;
+    // elected lane issues expect_tx + the TMA.  Barrier / stage addresses are running 32-bit
+    // shared-memory addresses.
+    const bool is_a = warp < kProdWarp0 + kProducersPerOperand;
+    const int q = (warp - kProdWarp0) % kProducersPerOperand;
+    const uint32_t smem_base = smem_u32(smem);
+    const uint32_t full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar);
+    if (BRES && !is_a) {
+      // resident weights: one producer warp loads every k-step's B tile once, then retires
+      if (q == 0 && elect_one()) {
+        const uint32_t bar = smem_u32(bres_bar);
+        mbar_expect_tx_a(bar, ksteps * L::kBBytes);
+        for (int ks = 0; ks < ksteps; ++ks)
+          tma_load_2d_a(&p.tmap_b, bar, smem_base + L::kBresOffset + ks * L::kBBytes, ks * kBlockK, 0);
+      }
+      __syncwarp();
+    } else {
       const int hw = p.Hout * p.Wout;
-      int stage = q % STAGES;
+      uint32_t stage = q % STAGES;
       uint32_t phase = (q / STAGES) & 1;
       int ks_carry = q;                       // first k-step of this producer inside the current tile
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -146,10 +168,12 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
           cw = ow * p.stride - p.pad; ch = oh * p.stride - p.pad;
           cw2 = ow * p.stride2; ch2 = oh * p.stride2;
         }
+        const int n0 = n_tile * BN;
         int ks = ks_carry;
         for (; ks < ksteps; ks += kProducersPerOperand) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* sa = smem + stage * L::kStageBytes;
+          mbar_wait_a(empty0 + stage * 8, phase ^ 1);
+          const uint32_t sa = smem_base + stage * L::kStageBytes;
+          const uint32_t fb = full0 + stage * 8;
           if (is_a) {
             int tap = 0, chunk = ks;
             if (p.ksize == 3) { tap = ks >> p.cin_shift; chunk = ks & (p.cin_chunks - 1); }
@@ -157,19 +181,17 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
             const int s = tap - r * 3;
             const bool main_op = ks < p.ksteps_main;
             if (elect_one()) {
-              mbar_expect_tx(&full_bar[stage], kABytes);
+              mbar_expect_tx_a(fb, kABytes);
               if (main_op) {
-                tma_load_im2col_4d(&p.tmap_a, &full_bar[stage], sa, chunk * kBlockK, cw, ch, n_img, (uint16_t)s,
-                                   (uint16_t)r);
+                tma_load_im2col_4d_a(&p.tmap_a, fb, sa, chunk * kBlockK, cw, ch, n_img, (uint16_t)s, (uint16_t)r);
               } else {
-                tma_load_im2col_4d(&p.tmap_a2, &full_bar[stage], sa, (ks - p.ksteps_main) * kBlockK, cw2, ch2, n_img,
-                                   0, 0);
+                tma_load_im2col_4d_a(&p.tmap_a2, fb, sa, (ks - p.ksteps_main) * kBlockK, cw2, ch2, n_img, 0, 0);
               }
             }
           } else {
             if (elect_one()) {
-              mbar_expect_tx(&full_bar[stage], L::kBBytes);
-              tma_load_2d(&p.tmap_b, &full_bar[stage], sa + kABytes, ks * kBlockK, n_tile * BN);
+              mbar_expect_tx_a(fb, L::kBBytes);
+              tma_load_2d_a(&p.tmap_b, fb, sa + kABytes, ks * kBlockK, n0);
             }
           }
           __syncwarp();
@@ -183,30 +205,34 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
     // ===================== MMA issuer (warp-uniform loop, one elected lane issues) =====================
     {
       constexpr uint32_t idesc = umma_idesc(kBlockM, BN, /*bf16*/ 1);
+      constexpr uint32_t kStageLo = L::kStageBytes >> 4;     // descriptor address field counts 16 B units
       const uint32_t smem_base = smem_u32(smem);
-      int stage = 0;
-      uint32_t phase = 0;
+      const uint32_t full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar);
+      const uint32_t tfull0 = smem_u32(tfull_bar), tempty0 = smem_u32(tempty_bar);
+      const uint32_t a_lo0 = umma_desc_lo(smem_base);
+      const uint32_t bres_lo0 = umma_desc_lo(smem_base + L::kBresOffset);
+      if (BRES) mbar_wait_a(smem_u32(bres_bar), 0);
+      uint32_t stage = 0, phase = 0;
       int it = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-        const int acc = it & 1;
+        const uint32_t acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
-        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        mbar_wait_a(tempty0 + acc * 8, acc_phase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * BN;
         for (int ks = 0; ks < ksteps; ++ks) {
-          mbar_wait(&full_bar[stage], phase);
+          mbar_wait_a(full0 + stage * 8, phase);
           tc_fence_after();
-          const uint32_t a_addr = smem_base + stage * L::kStageBytes;
-          const uint64_t adesc = umma_desc_sw128(a_addr);
-          const uint64_t bdesc = umma_desc_sw128(a_addr + kABytes);
+          const uint32_t a_lo = a_lo0 + stage * kStageLo;
+          const uint32_t b_lo = BRES ? bres_lo0 + ks * (L::kBBytes >> 4) : a_lo + (kABytes >> 4);
           if (elect_one()) {
-#pragma unroll
-            for (int k = 0; k < kBlockK / 16; ++k) {
-              // +32 bytes along K inside the 128 B swizzle row == +2 in the (addr >> 4) field
-              umma_f16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (ks | k) != 0 ? 1u : 0u);
-            }
-            umma_commit(&empty_bar[stage]);       // frees the smem slot once these MMAs retire
-            if (ks == ksteps - 1) umma_commit(&tfull_bar[acc]);   // accumulator complete -> epilogue
+            // +32 bytes along K inside the 128 B swizzle row == +2 in the descriptor address field
+            umma_f16(tmem_d, umma_desc_from_lo(a_lo), umma_desc_from_lo(b_lo), idesc, ks != 0 ? 1u : 0u);
+            umma_f16(tmem_d, umma_desc_from_lo(a_lo + 2), umma_desc_from_lo(b_lo + 2), idesc, 1u);
+            umma_f16(tmem_d, umma_desc_from_lo(a_lo + 4), umma_desc_from_lo(b_lo + 4), idesc, 1u);
+            umma_f16(tmem_d, umma_desc_from_lo(a_lo + 6), umma_desc_from_lo(b_lo + 6), idesc, 1u);
+            umma_commit_a(empty0 + stage * 8);                      // frees the smem slot once these MMAs retire
+            if (ks == ksteps - 1) umma_commit_a(tfull0 + acc * 8);  // accumulator complete -> epilogue
           }
           __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }

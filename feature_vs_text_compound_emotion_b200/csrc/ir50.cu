@@ -262,15 +262,17 @@ static int build_conv_op(ConvOp* op, const ConvGeom& g, int n_cap) {
   return CER_OK;
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool BRES>
 static int launch_conv_inst(const ConvKernelParams& p, int grid, cudaStream_t st) {
-  using L = ConvSmem<BN, STAGES>;
+  using L = ConvSmem<BN, STAGES, BRES>;
+  static_assert(L::kTotal <= 232448, "conv kernel shared memory exceeds 227 KB");
   static bool configured = false;
   if (!configured) {
-    CER_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
+    CER_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<BN, STAGES, BRES>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
     configured = true;
   }
-  conv_igemm_kernel<BN, STAGES><<<grid, kConvThreads, L::kTotal, st>>>(p);
+  if ((p.bias_classes + 1) * p.Cout > L::kTableFloats) return set_error(CER_ERR_INVALID, "conv: Cout too large for the epilogue table");
+  conv_igemm_kernel<BN, STAGES, BRES><<<grid, kConvThreads, L::kTotal, st>>>(p);
   CER_CUDA(cudaGetLastError());
   return CER_OK;
 }
@@ -282,10 +284,12 @@ static int launch_conv(const ConvOp& op, int frames, int num_sms, cudaStream_t s
   const int tiles = p.num_m_tiles * p.num_n_tiles;
   if (tiles == 0) return CER_OK;
   const int grid = std::min(tiles, num_sms);
+  // weights-resident variant when the whole layer's B fits (Cin = 64 layers: 9 k-steps, one n-tile)
+  const bool bres = p.num_n_tiles == 1 && (p.ksteps_main + p.ksteps2) <= kBresSteps && tiles >= 4 * grid;
   switch (op.bn) {
-    case 256: return launch_conv_inst<256, 4>(p, grid, st);
-    case 128: return launch_conv_inst<128, 6>(p, grid, st);
-    default:  return launch_conv_inst<64, 8>(p, grid, st);
+    case 256: return launch_conv_inst<256, 4, false>(p, grid, st);
+    case 128: return bres ? launch_conv_inst<128, 4, true>(p, grid, st) : launch_conv_inst<128, 6, false>(p, grid, st);
+    default:  return bres ? launch_conv_inst<64, 8, true>(p, grid, st) : launch_conv_inst<64, 8, false>(p, grid, st);
   }
 }
 

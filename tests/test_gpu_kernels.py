@@ -72,6 +72,9 @@ CONV_CASES = [
     (3, 40, 64, 128, 1, 2, 1, False, False, False),     # 1x1 stride-2 projection alone
     (130, 1, 12800, 512, 1, 1, 1, False, False, True),  # the FC head as a 1x1 conv, fp32 out, 2 m-tiles
     (1, 5, 512, 512, 3, 1, 9, True, True, False),       # a single frame (tiny tensor: driver-quirk path)
+    (48, 40, 64, 64, 3, 1, 9, True, False, False),      # 600 tiles >= 4 waves: weights-resident variant, BN = 64
+    (48, 40, 64, 64, 3, 1, 1, False, True, False),      # same with residual epilogue
+    (48, 40, 64, 128, 3, 1, 9, True, False, False),     # weights-resident variant, BN = 128
 ]
 
 
