@@ -55,6 +55,7 @@ constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;           // 64 bf16 = 128 B = one swizzle row
 constexpr int kABytes = kBlockM * 128;
 
+constexpr int kPrefetchTiles = 2;      // L2 prefetch distance of the A producer, in tiles of this CTA
 constexpr int kBresSteps = 9;          // weights-resident variant: all 9 taps of a Cin=64 layer stay in smem
 
 // BRES = true: the whole weight matrix of the layer (9 k-steps x BN x 128 B) is loaded once per CTA
@@ -78,7 +79,12 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
-template <int BN, int STAGES, bool BRES>
+// ALIGNED = true: the host guarantees ksteps % STAGES == 0, so every tile walks the ring a whole
+// number of times.  Stage indices are then compile-time inside the unrolled role loops: barrier,
+// smem and descriptor addresses are base + immediate, which shrinks the MMA-issue loop from ~70 to
+// ~20 instructions per k-step (at N = 64 a k-step is only 128 cycles of tensor work, so the
+// issuing warp -- not memory -- was the limiter; profiles/r01_conv_v6_*).
+template <int BN, int STAGES, bool BRES, bool ALIGNED>
 __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
   using L = ConvSmem<BN, STAGES, BRES>;
   extern __shared__ uint8_t smem_raw[];
@@ -141,9 +147,83 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
     const int q = (warp - kProdWarp0) % kProducersPerOperand;
     const uint32_t smem_base = smem_u32(smem);
     const uint32_t full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar);
-    if (BRES && !is_a) {
+    constexpr int kNPA = BRES ? 3 : 2;          // A producer warps in the aligned variant
+    const int pw = warp - kProdWarp0;          // 0..3
+    if (ALIGNED && !(BRES && pw == 3)) {
+      // ---- stage-aligned producers: warp `pa` of kNP owns stages pa, pa+kNP, ... of every round ----
+      const bool a_role = BRES ? true : pw < 2;
+      const int kNP = a_role ? kNPA : 2;
+      const int pa = a_role ? pw : pw - 2;
+      const int hw = p.Hout * p.Wout;
+      const int rounds = ksteps / STAGES;
+      uint32_t phase = 0;
+      const uint32_t sa0 = smem_base + pa * L::kStageBytes + (a_role ? 0 : kABytes);
+      const uint32_t fb0 = full0 + pa * 8, eb0 = empty0 + pa * 8;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int m_tile = tile / p.num_n_tiles;
+        const int n_tile = tile - m_tile * p.num_n_tiles;
+        const int n0 = n_tile * BN;
+        int cw = 0, ch = 0, n_img = 0, cw2 = 0, ch2 = 0;
+        if (a_role) {
+          const int m0 = m_tile * kBlockM;
+          n_img = m0 / hw;
+          const int rem = m0 - n_img * hw;
+          const int oh = rem / p.Wout;
+          const int ow = rem - oh * p.Wout;
+          cw = ow * p.stride - p.pad; ch = oh * p.stride - p.pad;
+          cw2 = ow * p.stride2; ch2 = oh * p.stride2;
+          if (pa == 0 && n_tile == 0) {          // L2 prefetch of the tile this CTA reaches kPrefetchTiles from now
+            const int step = gridDim.x / p.num_n_tiles > 0 ? gridDim.x / p.num_n_tiles : 1;
+            const int ptile_m = m_tile + kPrefetchTiles * step;
+            if (ptile_m < p.num_m_tiles && elect_one()) {
+              const int pm0 = ptile_m * kBlockM;
+              const int pn = pm0 / hw;
+              const int prem = pm0 - pn * hw;
+              const int poh = prem / p.Wout;
+              const int pow_ = prem - poh * p.Wout;
+              const uint16_t mid = p.ksize == 3 ? 1 : 0;
+              for (int c = 0; c < p.cin_chunks; ++c)
+                tma_prefetch_im2col_4d(&p.tmap_a, c * kBlockK, pow_ * p.stride - p.pad, poh * p.stride - p.pad, pn, mid, mid);
+            }
+            __syncwarp();
+          }
+        }
+        for (int r = 0; r < rounds; ++r) {
+#pragma unroll
+          for (int j = 0; j < STAGES; ++j) {
+            if (j % (BRES ? 3 : 2) != 0) continue;            // j walks this warp's stages: pa + j (j multiple of kNP)
+            if (j + pa >= STAGES) continue;
+            const int ks = r * STAGES + pa + j;
+            mbar_wait_a(eb0 + j * 8, phase ^ 1);
+            if (a_role) {
+              int tap = 0, chunk = ks;
+              if (p.ksize == 3) { tap = ks >> p.cin_shift; chunk = ks & (p.cin_chunks - 1); }
+              const int rr = (tap * 11) >> 5;
+              const int ss = tap - rr * 3;
+              if (elect_one()) {
+                mbar_expect_tx_a(fb0 + j * 8, kABytes);
+                if (ks < p.ksteps_main)
+                  tma_load_im2col_4d_a(&p.tmap_a, fb0 + j * 8, sa0 + j * L::kStageBytes, chunk * kBlockK, cw, ch, n_img,
+                                       (uint16_t)ss, (uint16_t)rr);
+                else
+                  tma_load_im2col_4d_a(&p.tmap_a2, fb0 + j * 8, sa0 + j * L::kStageBytes, (ks - p.ksteps_main) * kBlockK,
+                                       cw2, ch2, n_img, 0, 0);
+              }
+            } else {
+              if (elect_one()) {
+                mbar_expect_tx_a(fb0 + j * 8, L::kBBytes);
+                tma_load_2d_a(&p.tmap_b, fb0 + j * 8, sa0 + j * L::kStageBytes, ks * kBlockK, n0);
+              }
+            }
+            __syncwarp();
+          }
+          phase ^= 1;
+        }
+      }
+      (void)kNP;
+    } else if (BRES && !is_a) {
       // resident weights: one producer warp loads every k-step's B tile once, then retires
-      if (q == 0 && elect_one()) {
+      if ((ALIGNED ? pw == 3 : q == 0) && elect_one()) {
         const uint32_t bar = smem_u32(bres_bar);
         mbar_expect_tx_a(bar, ksteps * L::kBBytes);
         for (int ks = 0; ks < ksteps; ++ks)
@@ -169,6 +249,25 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
           cw2 = ow * p.stride2; ch2 = oh * p.stride2;
         }
         const int n0 = n_tile * BN;
+        // The first tap of a tile misses L2 (every later tap re-reads almost the same pixels), and
+        // the ring is too shallow to cover HBM latency, so the tile this CTA will process
+        // kPrefetchTiles iterations from now is prefetched into L2 here (centre tap, all chunks).
+        if (is_a && q == 0 && n_tile == 0) {
+          const int ptile_m = m_tile + kPrefetchTiles * (gridDim.x / p.num_n_tiles > 0 ? gridDim.x / p.num_n_tiles : 1);
+          if (ptile_m < p.num_m_tiles && elect_one()) {
+            const int pm0 = ptile_m * kBlockM;
+            const int pn = pm0 / hw;
+            const int prem = pm0 - pn * hw;
+            const int poh = prem / p.Wout;
+            const int pow_ = prem - poh * p.Wout;
+            const uint16_t mid = p.ksize == 3 ? 1 : 0;
+            for (int c = 0; c < p.cin_chunks; ++c)
+              tma_prefetch_im2col_4d(&p.tmap_a, c * kBlockK, pow_ * p.stride - p.pad, poh * p.stride - p.pad, pn, mid, mid);
+            for (int c = 0; c < p.ksteps2; ++c)
+              tma_prefetch_im2col_4d(&p.tmap_a2, c * kBlockK, pow_ * p.stride2, poh * p.stride2, pn, 0, 0);
+          }
+          __syncwarp();
+        }
         int ks = ks_carry;
         for (; ks < ksteps; ks += kProducersPerOperand) {
           mbar_wait_a(empty0 + stage * 8, phase ^ 1);
@@ -214,6 +313,36 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
       if (BRES) mbar_wait_a(smem_u32(bres_bar), 0);
       uint32_t stage = 0, phase = 0;
       int it = 0;
+      if (ALIGNED) {
+        const int rounds = ksteps / STAGES;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+          const uint32_t acc = it & 1;
+          const uint32_t acc_phase = (it >> 1) & 1;
+          mbar_wait_a(tempty0 + acc * 8, acc_phase ^ 1);
+          tc_fence_after();
+          const uint32_t tmem_d = tmem_base + acc * BN;
+          for (int r = 0; r < rounds; ++r) {
+            const uint32_t b_round = bres_lo0 + r * STAGES * (L::kBBytes >> 4);
+#pragma unroll
+            for (int sidx = 0; sidx < STAGES; ++sidx) {
+              mbar_wait_a(full0 + sidx * 8, phase);
+              tc_fence_after();
+              if (elect_one()) {
+                const uint32_t a_lo = a_lo0 + sidx * kStageLo;
+                const uint32_t b_lo = BRES ? b_round + sidx * (L::kBBytes >> 4) : a_lo + (kABytes >> 4);
+                umma_f16(tmem_d, umma_desc_from_lo(a_lo), umma_desc_from_lo(b_lo), idesc, (r | sidx) != 0 ? 1u : 0u);
+                umma_f16(tmem_d, umma_desc_from_lo(a_lo + 2), umma_desc_from_lo(b_lo + 2), idesc, 1u);
+                umma_f16(tmem_d, umma_desc_from_lo(a_lo + 4), umma_desc_from_lo(b_lo + 4), idesc, 1u);
+                umma_f16(tmem_d, umma_desc_from_lo(a_lo + 6), umma_desc_from_lo(b_lo + 6), idesc, 1u);
+                umma_commit_a(empty0 + sidx * 8);
+                if (sidx == STAGES - 1 && r == rounds - 1) umma_commit_a(tfull0 + acc * 8);
+              }
+              __syncwarp();
+            }
+            phase ^= 1;
+          }
+        }
+      } else
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
         const uint32_t acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;

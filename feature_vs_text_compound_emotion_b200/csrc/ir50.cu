@@ -262,17 +262,19 @@ static int build_conv_op(ConvOp* op, const ConvGeom& g, int n_cap) {
   return CER_OK;
 }
 
-template <int BN, int STAGES, bool BRES>
+template <int BN, int STAGES, bool BRES, bool ALIGNED>
 static int launch_conv_inst(const ConvKernelParams& p, int grid, cudaStream_t st) {
   using L = ConvSmem<BN, STAGES, BRES>;
   static_assert(L::kTotal <= 232448, "conv kernel shared memory exceeds 227 KB");
+  static_assert(!ALIGNED || (BRES ? STAGES % 3 == 0 : STAGES % 2 == 0), "aligned variant: producers must divide the ring");
   static bool configured = false;
   if (!configured) {
-    CER_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<BN, STAGES, BRES>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
+    CER_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<BN, STAGES, BRES, ALIGNED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  L::kTotal));
     configured = true;
   }
   if ((p.bias_classes + 1) * p.Cout > L::kTableFloats) return set_error(CER_ERR_INVALID, "conv: Cout too large for the epilogue table");
-  conv_igemm_kernel<BN, STAGES, BRES><<<grid, kConvThreads, L::kTotal, st>>>(p);
+  conv_igemm_kernel<BN, STAGES, BRES, ALIGNED><<<grid, kConvThreads, L::kTotal, st>>>(p);
   CER_CUDA(cudaGetLastError());
   return CER_OK;
 }
@@ -284,12 +286,21 @@ static int launch_conv(const ConvOp& op, int frames, int num_sms, cudaStream_t s
   const int tiles = p.num_m_tiles * p.num_n_tiles;
   if (tiles == 0) return CER_OK;
   const int grid = std::min(tiles, num_sms);
-  // weights-resident variant when the whole layer's B fits (Cin = 64 layers: 9 k-steps, one n-tile)
-  const bool bres = p.num_n_tiles == 1 && (p.ksteps_main + p.ksteps2) <= kBresSteps && tiles >= 4 * grid;
+  const int ksteps = p.ksteps_main + p.ksteps2;
+  // weights-resident variants when the whole layer's B fits (Cin = 64 layers: 9 k-steps, one n-tile)
+  const bool bres = p.num_n_tiles == 1 && ksteps <= kBresSteps && tiles >= 4 * grid;
   switch (op.bn) {
-    case 256: return launch_conv_inst<256, 4, false>(p, grid, st);
-    case 128: return bres ? launch_conv_inst<128, 4, true>(p, grid, st) : launch_conv_inst<128, 6, false>(p, grid, st);
-    default:  return bres ? launch_conv_inst<64, 8, true>(p, grid, st) : launch_conv_inst<64, 8, false>(p, grid, st);
+    case 256:
+      return ksteps % 4 == 0 ? launch_conv_inst<256, 4, false, true>(p, grid, st)
+                             : launch_conv_inst<256, 4, false, false>(p, grid, st);
+    case 128:
+      if (bres) return launch_conv_inst<128, 4, true, false>(p, grid, st);
+      return ksteps % 6 == 0 ? launch_conv_inst<128, 6, false, true>(p, grid, st)
+                             : launch_conv_inst<128, 6, false, false>(p, grid, st);
+    default:
+      if (bres && ksteps == 9) return launch_conv_inst<64, 9, true, true>(p, grid, st);
+      return ksteps % 8 == 0 ? launch_conv_inst<64, 8, false, true>(p, grid, st)
+                             : launch_conv_inst<64, 8, false, false>(p, grid, st);
   }
 }
 

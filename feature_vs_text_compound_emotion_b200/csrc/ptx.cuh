@@ -118,6 +118,14 @@ __device__ __forceinline__ void tma_load_im2col_4d(const CUtensorMap* m, uint64_
       : "memory");
 }
 
+// L2 prefetch of an im2col box (no shared memory, no barrier): used to pull the next tile's pixels
+// from HBM into L2 one tile ahead of the loads that need them.
+__device__ __forceinline__ void tma_prefetch_im2col_4d(const CUtensorMap* m, int c, int w, int h, int n, uint16_t off_w,
+                                                       uint16_t off_h) {
+  asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.im2col [%0, {%1, %2, %3, %4}], {%5, %6};"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h)
+               : "memory");
+}
 __device__ __forceinline__ void tma_load_2d_a(const CUtensorMap* m, uint32_t bar, uint32_t dst, int c0, int c1) {
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
