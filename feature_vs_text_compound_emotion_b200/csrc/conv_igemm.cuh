@@ -79,6 +79,107 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
+// One output tile of the fused epilogue, for one epilogue thread (warp 0-7):
+//   + bias[class(pixel)][co] -> PReLU(alpha[co]) -> + residual[m][co] -> bf16 | fp32.
+// `tmem_acc` is the accumulator's TMEM base column; `tfull` the barrier that says it is complete.
+template <int BN>
+__device__ __forceinline__ void conv_epilogue_tile(const ConvKernelParams& p, const float* s_bias, const float* s_alpha,
+                                                   uint32_t tmem_acc, int m_tile, int n_tile, int warp, int lane,
+                                                   uint32_t tfull, uint32_t parity) {
+  constexpr int kHalf = BN / 2;                // columns per thread per tile
+  const int quarter = warp & 3;                // TMEM lane quarter this warp may read
+  const int half = warp >> 2;                  // column half
+  const int row = quarter * 32 + lane;         // TMEM lane == row of the M tile
+  const uint32_t lane_addr = (static_cast<uint32_t>(quarter * 32) << 16);
+  const int hw = p.Hout * p.Wout;
+  const bool has_res = p.res != nullptr;
+  const bool has_alpha = p.alpha != nullptr;
+  const int m = m_tile * kBlockM + row;
+  const bool valid = m < p.M;
+  const int n0 = n_tile * BN + half * kHalf;
+  int cls = 0;
+  if (p.bias_classes == 9) {
+    const int rem = m % hw;
+    const int oh = rem / p.Wout;
+    const int ow = rem - oh * p.Wout;
+    cls = (oh == 0 ? 0 : (oh == p.Hout - 1 ? 2 : 1)) * 3 + (ow == 0 ? 0 : (ow == p.Wout - 1 ? 2 : 1));
+  }
+  const float* sb = s_bias + cls * p.Cout + n0;
+  const float* sal = s_alpha + n0;
+  const size_t out_off = static_cast<size_t>(m) * p.Cout + n0;
+  const bool ld_res = has_res && valid;
+
+  // residual of the first chunk is requested before the accumulator wait: its latency hides
+  // behind the MMA of this tile
+  uint4 rnext[4];
+  if (ld_res) {
+    const uint4* rp = reinterpret_cast<const uint4*>(p.res + out_off);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) rnext[j] = __ldg(rp + j);
+  }
+  mbar_wait_a(tfull, parity);
+  tc_fence_after();
+#pragma unroll
+  for (int c0 = 0; c0 < kHalf; c0 += 32) {
+    uint32_t v[32];
+    tmem_ld_32x32(tmem_acc + lane_addr + half * kHalf + c0, v);
+    uint4 rres[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) rres[j] = rnext[j];
+    if (c0 + 32 < kHalf && ld_res) {
+      const uint4* rp = reinterpret_cast<const uint4*>(p.res + out_off + c0 + 32);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) rnext[j] = __ldg(rp + j);
+    }
+    tmem_ld_wait();
+    float f[32];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 b = *reinterpret_cast<const float4*>(sb + c0 + 4 * j);
+      f[4 * j + 0] = __uint_as_float(v[4 * j + 0]) + b.x;
+      f[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + b.y;
+      f[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + b.z;
+      f[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + b.w;
+    }
+    if (has_alpha) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 a = *reinterpret_cast<const float4*>(sal + c0 + 4 * j);
+        f[4 * j + 0] = f[4 * j + 0] >= 0.f ? f[4 * j + 0] : f[4 * j + 0] * a.x;
+        f[4 * j + 1] = f[4 * j + 1] >= 0.f ? f[4 * j + 1] : f[4 * j + 1] * a.y;
+        f[4 * j + 2] = f[4 * j + 2] >= 0.f ? f[4 * j + 2] : f[4 * j + 2] * a.z;
+        f[4 * j + 3] = f[4 * j + 3] >= 0.f ? f[4 * j + 3] : f[4 * j + 3] * a.w;
+      }
+    }
+    if (ld_res) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t w[4] = {rres[j].x, rres[j].y, rres[j].z, rres[j].w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&w[q]);
+          f[8 * j + 2 * q + 0] += __bfloat162float(h.x);
+          f[8 * j + 2 * q + 1] += __bfloat162float(h.y);
+        }
+      }
+    }
+    if (valid) {
+      if (p.out_fp32) {
+        float4* op = reinterpret_cast<float4*>(static_cast<float*>(p.out) + out_off + c0);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) op[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+      } else {
+        uint4* op = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + out_off + c0);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          op[j] = make_uint4(pack_bf16x2(f[8 * j + 0], f[8 * j + 1]), pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
+                             pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), pack_bf16x2(f[8 * j + 6], f[8 * j + 7]));
+        }
+      }
+    }
+  }
+}
+
 // ALIGNED = true: the host guarantees ksteps % STAGES == 0, so every tile walks the ring a whole
 // number of times.  Stage indices are then compile-time inside the unrolled role loops: barrier,
 // smem and descriptor addresses are base + immediate, which shrinks the MMA-issue loop from ~70 to
@@ -370,106 +471,16 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
     }
   } else {
     // ===================== Epilogue (warps 0-7, 256 threads) =====================
-    constexpr int kHalf = BN / 2;                // columns per thread per tile
-    const int quarter = warp & 3;                // TMEM lane quarter this warp may read
-    const int half = warp >> 2;                  // column half
-    const int row = quarter * 32 + lane;         // TMEM lane == row of the M tile
-    const uint32_t lane_addr = (static_cast<uint32_t>(quarter * 32) << 16);
-    const int hw = p.Hout * p.Wout;
-    const bool has_res = p.res != nullptr;
-    const bool has_alpha = p.alpha != nullptr;
+    const uint32_t tfull0 = smem_u32(tfull_bar), tempty0 = smem_u32(tempty_bar);
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-      const int acc = it & 1;
+      const uint32_t acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       const int m_tile = tile / p.num_n_tiles;
       const int n_tile = tile - m_tile * p.num_n_tiles;
-      const int m = m_tile * kBlockM + row;
-      const bool valid = m < p.M;
-      const int n0 = n_tile * BN + half * kHalf;
-      int cls = 0;
-      if (p.bias_classes == 9) {
-        const int rem = m % hw;
-        const int oh = rem / p.Wout;
-        const int ow = rem - oh * p.Wout;
-        cls = (oh == 0 ? 0 : (oh == p.Hout - 1 ? 2 : 1)) * 3 + (ow == 0 ? 0 : (ow == p.Wout - 1 ? 2 : 1));
-      }
-      const float* sb = s_bias + cls * p.Cout + n0;
-      const float* sal = s_alpha + n0;
-      const size_t out_off = static_cast<size_t>(m) * p.Cout + n0;
-      const bool ld_res = has_res && valid;
-
-      // residual of the first chunk is requested before the accumulator wait: its latency hides
-      // behind the MMA of this tile
-      uint4 rnext[4];
-      if (ld_res) {
-        const uint4* rp = reinterpret_cast<const uint4*>(p.res + out_off);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) rnext[j] = __ldg(rp + j);
-      }
-      mbar_wait(&tfull_bar[acc], acc_phase);
-      tc_fence_after();
-#pragma unroll
-      for (int c0 = 0; c0 < kHalf; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld_32x32(tmem_base + lane_addr + acc * BN + half * kHalf + c0, v);
-        uint4 rres[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) rres[j] = rnext[j];
-        if (c0 + 32 < kHalf && ld_res) {
-          const uint4* rp = reinterpret_cast<const uint4*>(p.res + out_off + c0 + 32);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) rnext[j] = __ldg(rp + j);
-        }
-        tmem_ld_wait();
-        float f[32];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float4 b = *reinterpret_cast<const float4*>(sb + c0 + 4 * j);
-          f[4 * j + 0] = __uint_as_float(v[4 * j + 0]) + b.x;
-          f[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + b.y;
-          f[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + b.z;
-          f[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + b.w;
-        }
-        if (has_alpha) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 a = *reinterpret_cast<const float4*>(sal + c0 + 4 * j);
-            f[4 * j + 0] = f[4 * j + 0] >= 0.f ? f[4 * j + 0] : f[4 * j + 0] * a.x;
-            f[4 * j + 1] = f[4 * j + 1] >= 0.f ? f[4 * j + 1] : f[4 * j + 1] * a.y;
-            f[4 * j + 2] = f[4 * j + 2] >= 0.f ? f[4 * j + 2] : f[4 * j + 2] * a.z;
-            f[4 * j + 3] = f[4 * j + 3] >= 0.f ? f[4 * j + 3] : f[4 * j + 3] * a.w;
-          }
-        }
-        if (ld_res) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const uint32_t w[4] = {rres[j].x, rres[j].y, rres[j].z, rres[j].w};
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&w[q]);
-              f[8 * j + 2 * q + 0] += __bfloat162float(h.x);
-              f[8 * j + 2 * q + 1] += __bfloat162float(h.y);
-            }
-          }
-        }
-        if (valid) {
-          if (p.out_fp32) {
-            float4* op = reinterpret_cast<float4*>(static_cast<float*>(p.out) + out_off + c0);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) op[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
-          } else {
-            uint4* op = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + out_off + c0);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              op[j] = make_uint4(pack_bf16x2(f[8 * j + 0], f[8 * j + 1]), pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
-                                 pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), pack_bf16x2(f[8 * j + 6], f[8 * j + 7]));
-            }
-          }
-        }
-      }
+      conv_epilogue_tile<BN>(p, s_bias, s_alpha, tmem_base + acc * BN, m_tile, n_tile, warp, lane, tfull0 + acc * 8, acc_phase);
       tc_fence_before();
-      mbar_arrive(&tempty_bar[acc]);            // 256 arrivals release the accumulator stage
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tempty0 + acc * 8) : "memory");   // 256 arrivals free the accumulator
     }
   }
 

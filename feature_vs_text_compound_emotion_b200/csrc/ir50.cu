@@ -13,6 +13,8 @@
 #include "../../include/cer_b200.h"
 #include "common.h"
 #include "conv_igemm.cuh"
+#include "conv_igemm2.cuh"
+#include <cstdlib>
 
 namespace cer {
 
@@ -211,6 +213,7 @@ int make_tiled2d_map_generic(CUtensorMap* map, CUtensorMapDataType dt, int elem_
 
 struct ConvOp {
   ConvKernelParams kp;
+  CUtensorMap tmap_b_half;   // weights with a BN/2-row box: the CTA-pair variant loads half a B tile per CTA
   int bn;          // 64 / 128 / 256
   int hw_out;      // output pixels per frame
 };
@@ -244,6 +247,8 @@ static int build_conv_op(ConvOp* op, const ConvGeom& g, int n_cap) {
   }
   const int ktot = g.ksize * g.ksize * g.Cin + g.Cin2;
   rc = make_weight_map(&p.tmap_b, g.weight, g.Cout, ktot, op->bn);
+  if (rc) return rc;
+  rc = make_weight_map(&op->tmap_b_half, g.weight, g.Cout, ktot, op->bn / 2);
   if (rc) return rc;
   p.Hout = Hout; p.Wout = Wout; p.Cout = g.Cout;
   p.cin_chunks = g.Cin / kBlockK;
@@ -279,6 +284,38 @@ static int launch_conv_inst(const ConvKernelParams& p, int grid, cudaStream_t st
   return CER_OK;
 }
 
+template <int BN, int STAGES>
+static int launch_conv2_inst(const ConvKernelParams& p, int num_sms, cudaStream_t st) {
+  using L = Conv2Smem<BN, STAGES>;
+  static_assert(L::kTotal <= 232448, "pair conv kernel shared memory exceeds 227 KB");
+  static bool configured = false;
+  if (!configured) {
+    CER_CUDA(cudaFuncSetAttribute(conv_igemm2_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
+    configured = true;
+  }
+  if ((p.bias_classes + 1) * p.Cout > L::kTableFloats) return set_error(CER_ERR_INVALID, "conv: Cout too large for the epilogue table");
+  const int ptiles = ((p.num_m_tiles + 1) / 2) * p.num_n_tiles;
+  const int pairs = std::min(ptiles, num_sms / 2);
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof cfg);
+  cfg.gridDim = dim3(2 * pairs);
+  cfg.blockDim = dim3(kConvThreads);
+  cfg.dynamicSmemBytes = L::kTotal;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  CER_CUDA(cudaLaunchKernelEx(&cfg, conv_igemm2_kernel<BN, STAGES>, p));
+  return CER_OK;
+}
+
+static bool pair_mode_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("CER_NO_PAIR"); v = (e && e[0] == '1') ? 0 : 1; }
+  return v == 1;
+}
+
 static int launch_conv(const ConvOp& op, int frames, int num_sms, cudaStream_t st) {
   ConvKernelParams p = op.kp;
   p.M = frames * op.hw_out;
@@ -287,6 +324,12 @@ static int launch_conv(const ConvOp& op, int frames, int num_sms, cudaStream_t s
   if (tiles == 0) return CER_OK;
   const int grid = std::min(tiles, num_sms);
   const int ksteps = p.ksteps_main + p.ksteps2;
+  // CTA-pair (cta_group::2) variant: plain 3x3 / 1x1 layers whose k-steps fill the 6-stage ring a whole
+  // number of times and that have at least two waves of pair tiles
+  if (pair_mode_enabled() && p.ksteps2 == 0 && ksteps % 6 == 0 && tiles >= 4 * num_sms && op.bn >= 128) {
+    p.tmap_b = op.tmap_b_half;
+    return op.bn == 256 ? launch_conv2_inst<256, 6>(p, num_sms, st) : launch_conv2_inst<128, 6>(p, num_sms, st);
+  }
   // weights-resident variants when the whole layer's B fits (Cin = 64 layers: 9 k-steps, one n-tile)
   const bool bres = p.num_n_tiles == 1 && ksteps <= kBresSteps && tiles >= 4 * grid;
   switch (op.bn) {

@@ -75,6 +75,10 @@ CONV_CASES = [
     (48, 40, 64, 64, 3, 1, 9, True, False, False),      # 600 tiles >= 4 waves: weights-resident variant, BN = 64
     (48, 40, 64, 64, 3, 1, 1, False, True, False),      # same with residual epilogue
     (48, 40, 64, 128, 3, 1, 9, True, False, False),     # weights-resident variant, BN = 128
+    (800, 10, 256, 256, 3, 1, 9, True, False, False),   # 625 tiles (odd): CTA-pair (cta_group::2) variant, ragged last pair
+    (800, 10, 256, 256, 3, 1, 1, False, True, False),   # CTA-pair variant with residual epilogue
+    (200, 20, 128, 128, 3, 1, 9, True, False, False),   # CTA-pair variant, BN = 128
+    (1530, 5, 512, 512, 3, 1, 9, True, False, False),   # CTA-pair variant, two n-tiles, tiles span frames
 ]
 
 
