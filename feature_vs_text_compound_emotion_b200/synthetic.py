@@ -88,6 +88,38 @@ def visual_backbone_state_dict(seed: int = 0, units=IR50_UNITS, num_classes: int
     return OrderedDict((k, sd[k]) for k in order)
 
 
+VGGISH_CFG = (64, "M", 128, "M", 256, 256, "M", 512, 512, "M")     # models/backbone.py:43-53
+VGGISH_FC = ((512 * 4 * 6, 4096), (4096, 4096), (4096, 128))        # models/backbone.py:20-27
+
+
+def vggish_state_dict(seed: int = 0) -> "OrderedDict[str, torch.Tensor]":
+    """``VGGish.state_dict()`` layout = vggish.pth (models/backbone.py:16-66): 18 keys
+    ``features.{0,3,6,8,11,13}.{weight,bias}``, ``embeddings.{0,2,4}.{weight,bias}``.
+    He-uniform weights keep the ReLU activations O(1) through the stack."""
+    g = torch.Generator().manual_seed(seed + 7919)
+    sd: "OrderedDict[str, torch.Tensor]" = OrderedDict()
+    idx, cin = 0, 1
+    for v in VGGISH_CFG:
+        if v == "M":
+            idx += 1
+            continue
+        sd[f"features.{idx}.weight"] = _uniform(g, (v, cin, 3, 3), (6.0 / (cin * 9)) ** 0.5)
+        sd[f"features.{idx}.bias"] = 0.05 * torch.randn(v, generator=g)
+        idx += 2
+        cin = v
+    for i, (fin, fout) in zip((0, 2, 4), VGGISH_FC):
+        sd[f"embeddings.{i}.weight"] = _uniform(g, (fout, fin), (6.0 / fin) ** 0.5)
+        sd[f"embeddings.{i}.bias"] = 0.05 * torch.randn(fout, generator=g)
+    return sd
+
+
+def logmel_patches(n: int, seed: int = 1234, frames: int = 96, bands: int = 64) -> torch.Tensor:
+    """VGGish input examples [n, 96, 64]: log(mel + 0.01) values (vggish_input.py:37-82 /
+    mel_features.py:207-236) lie in about [-4.6, 3]; here N(-1.5, 1.2)."""
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(n, frames, bands, generator=g) * 1.2 - 1.5
+
+
 def head_state_dict(seed: int = 0, modalities: Sequence[str] = ("video", "vggish", "bert"),
                     output_dim: int = 7, kernel_size: int = 5, modal_dim: int = 32,
                     tcn_channels: Dict[str, List[int]] = None,
@@ -149,6 +181,9 @@ def lfan_state_dict(seed: int = 0, modalities: Sequence[str] = ("video", "vggish
     if "video" in modalities:
         for k, v in visual_backbone_state_dict(seed).items():
             sd["spatial.visual." + k] = v
+    if "logmel" in modalities:                      # models/model.py:460-463, AudioBackbone.backbone = VGGish
+        for k, v in vggish_state_dict(seed).items():
+            sd["spatial.audio.backbone." + k] = v
     for k, v in head.items():
         if not k.startswith("temporal."):
             sd[k] = v

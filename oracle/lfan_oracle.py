@@ -93,6 +93,34 @@ def ir50_forward(sd: SD, x: Tensor, prefix: str = "", units=IR50_UNITS) -> Tenso
 
 
 # --------------------------------------------------------------------------------------
+# VGGish audio backbone (models/backbone.py:16-66, :133-145)
+# --------------------------------------------------------------------------------------
+VGGISH_CFG = (64, "M", 128, "M", 256, 256, "M", 512, 512, "M")       # make_layers(), backbone.py:43-53
+VGGISH_CONV_IDX = (0, 3, 6, 8, 11, 13)                                # positions of the Conv2d's in `features`
+
+
+def vggish_forward(sd: SD, x: Tensor, prefix: str = "") -> Tensor:
+    """VGGish.forward -> VGG.forward (backbone.py:29-40, :63-66).  x: [N, 96, 64] log-mel patches
+    (the reference wraps them as [N,1,96,64]); returns [N,128].  Conv3x3(pad 1)+ReLU stacks with
+    2x2 max-pools, the feature map is flattened in (h, w, c) order (:34-37) and goes through
+    Linear-ReLU-Linear-ReLU-Linear (no final ReLU, :20-27)."""
+    h = x[:, None, :, :].float()                                                   # :64
+    li = 0
+    for v in VGGISH_CFG:
+        if v == "M":
+            h = F.max_pool2d(h, 2, 2)
+        else:
+            i = VGGISH_CONV_IDX[li]
+            h = F.relu(F.conv2d(h, sd[f"{prefix}features.{i}.weight"], sd[f"{prefix}features.{i}.bias"], 1, 1))
+            li += 1
+    h = h.transpose(1, 3).transpose(1, 2).contiguous()                             # NCHW -> NHWC, :34-36
+    h = h.view(h.shape[0], -1)
+    h = F.relu(F.linear(h, sd[prefix + "embeddings.0.weight"], sd[prefix + "embeddings.0.bias"]))
+    h = F.relu(F.linear(h, sd[prefix + "embeddings.2.weight"], sd[prefix + "embeddings.2.bias"]))
+    return F.linear(h, sd[prefix + "embeddings.4.weight"], sd[prefix + "embeddings.4.bias"])
+
+
+# --------------------------------------------------------------------------------------
 # TCN (models/temporal_convolutional_model.py:12-75)
 # --------------------------------------------------------------------------------------
 def weight_norm_effective(g: Tensor, v: Tensor) -> Tensor:
@@ -187,13 +215,17 @@ def head_forward(sd: SD, feats: Dict[str, Tensor], modalities: Sequence[str],
 def lfan_forward(sd: SD, X: Dict[str, Tensor], modalities: Sequence[str],
                  modal_dim: int = 32, num_heads: int = 2) -> Tensor:
     """LFAN.forward (model.py:487-526), classification task (no tanh, :523).
-    X['video']: [B,T,3,40,40]; other modalities [B,1,T,D]."""
+    X['video']: [B,T,3,40,40]; X['logmel']: [B,64,T,96]; other modalities [B,1,T,D]."""
     feats = {}
     for m in modalities:
         if m == "video":
             B, T = X[m].shape[:2]
             emb = ir50_forward(sd, X[m].reshape(B * T, *X[m].shape[2:]), "spatial.visual.backbone.")
             feats[m] = emb.view(B, T, -1)                             # :490-497
+        elif m == "logmel":
+            B, hh, T, ww = X[m].shape                                 # :500  [B, 64, T, 96]
+            patches = X[m].permute(0, 2, 3, 1).contiguous().view(-1, ww, hh)      # :501-502
+            feats[m] = vggish_forward(sd, patches, "spatial.audio.backbone.").view(B, T, -1)   # :504-507
         else:
             feats[m] = X[m].squeeze(1)
     return head_forward(sd, feats, modalities, modal_dim, num_heads)
