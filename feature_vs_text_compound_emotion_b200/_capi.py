@@ -32,6 +32,21 @@ class Ir50Weights(C.Structure):
                 ("fc_w", C.c_void_p), ("fc_bias", C.c_void_p)]
 
 
+class VggConv(C.Structure):
+    _fields_ = [("cin", C.c_int32), ("cout", C.c_int32), ("pool_after", C.c_int32), ("w", C.c_void_p), ("bias", C.c_void_p)]
+
+
+class VggFc(C.Structure):
+    _fields_ = [("in_dim", C.c_int32), ("out_dim", C.c_int32), ("relu", C.c_int32), ("w", C.c_void_p), ("bias", C.c_void_p)]
+
+
+class VggishWeights(C.Structure):
+    _fields_ = [("in_h", C.c_int32), ("in_w", C.c_int32), ("c1", C.c_int32),
+                ("conv1_w", C.c_void_p), ("conv1_bias", C.c_void_p),
+                ("n_convs", C.c_int32), ("convs", C.POINTER(VggConv)),
+                ("n_fcs", C.c_int32), ("fcs", C.POINTER(VggFc)), ("zeros", C.c_void_p)]
+
+
 class TcnBlock(C.Structure):
     _fields_ = [("c_in", C.c_int32), ("c_out", C.c_int32), ("kernel_size", C.c_int32), ("dilation", C.c_int32),
                 ("w1", C.c_void_p), ("b1", C.c_void_p), ("w2", C.c_void_p), ("b2", C.c_void_p),
@@ -60,6 +75,11 @@ SIGNATURES = {
     "cer_conv_forward": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
                                    C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p,
                                    C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
+    "cer_vggish_workspace_bytes": (C.c_size_t, [C.POINTER(VggishWeights), C.c_int64]),
+    "cer_vggish_create": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(VggishWeights), C.c_int64, C.c_void_p, C.c_size_t]),
+    "cer_vggish_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    "cer_vggish_launches": (C.c_int64, [C.c_void_p, C.c_int64]),
+    "cer_vggish_destroy": (None, [C.c_void_p]),
     "cer_tcn_block_workspace_bytes": (C.c_size_t, [C.POINTER(TcnBlock), C.c_int64, C.c_int64]),
     "cer_tcn_block_forward": (C.c_int, [C.POINTER(TcnBlock), C.c_void_p, C.c_void_p, C.c_int64, C.c_int64,
                                         C.c_void_p, C.c_size_t, C.c_void_p]),

@@ -70,7 +70,7 @@ struct ConvSmem {
   static constexpr int kBarOffset = kBresOffset + (BRES ? kBresSteps * kBBytes : 0);
   static constexpr int kNumBars = 2 * STAGES + 5;                                   // full, empty, tfull[2], tempty[2], bres
   static constexpr int kTableOffset = (kBarOffset + kNumBars * 8 + 16 + 15) & ~15;  // bias table + PReLU slopes (float4 reads)
-  static constexpr int kTableFloats = 10 * (BN == 256 ? 512 : BN);                 // [<=9][Cout] + [Cout]
+  static constexpr int kTableFloats = BN == 256 ? 8192 : 10 * BN;                   // [<=9][Cout] + [Cout]; 8192 = 2 x 4096 (VGGish FCs)
   static constexpr int kTotal = kTableOffset + kTableFloats * 4 + 1024 /*alignment slack*/;
 };
 

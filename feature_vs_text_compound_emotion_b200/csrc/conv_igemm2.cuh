@@ -73,7 +73,7 @@ struct Conv2Smem {
   static constexpr int kBarOffset = STAGES * kStageBytes;
   static constexpr int kNumBars = 2 * STAGES + 4;            // full, empty, tfull[2], tempty[2]
   static constexpr int kTableOffset = (kBarOffset + kNumBars * 8 + 16 + 15) & ~15;
-  static constexpr int kTableFloats = 10 * (BN == 256 ? 512 : BN);
+  static constexpr int kTableFloats = BN == 256 ? 8192 : 10 * BN;
   static constexpr int kTotal = kTableOffset + kTableFloats * 4 + 1024;
 };
 

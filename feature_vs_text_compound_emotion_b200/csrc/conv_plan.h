@@ -1,0 +1,31 @@
+// Host-side plan pieces of the tcgen05 implicit-GEMM convolution shared by the IR-50 and VGGish
+// plans: geometry -> tensor maps + kernel parameters, and the launcher that picks the kernel variant.
+// Definitions live in ir50.cu (the only TU that instantiates the conv kernels).
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include "conv_igemm.cuh"
+
+namespace cer {
+
+struct ConvOp {
+  ConvKernelParams kp;
+  CUtensorMap tmap_b_half;   // weights with a BN/2-row box: the CTA-pair variant loads half a B tile per CTA
+  int bn;          // 64 / 128 / 256
+  int hw_out;      // output pixels per frame
+};
+
+struct ConvGeom {
+  const void* src; int H, W, Cin, ksize, stride, pad;
+  const void* src2; int H2, W2, Cin2, stride2;       // fused shortcut operand (Cin2 = 0: none)
+  const void* weight; const float* bias; int bias_classes; const float* alpha;
+  const __nv_bfloat16* res; void* dst; int Cout; int out_fp32;
+};
+
+int load_driver_entry_points();
+// n_cap: frames the activation allocation holds (tensor-map N extent)
+int build_conv_op(ConvOp* op, const ConvGeom& g, int n_cap);
+int launch_conv(const ConvOp& op, int frames, int num_sms, cudaStream_t st);
+
+}  // namespace cer

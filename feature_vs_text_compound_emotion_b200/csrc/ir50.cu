@@ -12,7 +12,7 @@
 
 #include "../../include/cer_b200.h"
 #include "common.h"
-#include "conv_igemm.cuh"
+#include "conv_plan.h"
 #include "conv_igemm2.cuh"
 #include <cstdlib>
 
@@ -115,7 +115,7 @@ static PFN_encodeTiled g_encode_tiled = nullptr;
 static PFN_encodeIm2col g_encode_im2col = nullptr;
 static int g_driver_version = 0;
 
-static int load_driver_entry_points() {
+int load_driver_entry_points() {
   if (g_encode_tiled && g_encode_im2col) return CER_OK;
   cudaDriverEntryPointQueryResult q;
   void* fn = nullptr;
@@ -211,23 +211,9 @@ int make_tiled2d_map_generic(CUtensorMap* map, CUtensorMapDataType dt, int elem_
   return CER_OK;
 }
 
-struct ConvOp {
-  ConvKernelParams kp;
-  CUtensorMap tmap_b_half;   // weights with a BN/2-row box: the CTA-pair variant loads half a B tile per CTA
-  int bn;          // 64 / 128 / 256
-  int hw_out;      // output pixels per frame
-};
-
-struct ConvGeom {
-  const void* src; int H, W, Cin, ksize, stride, pad;
-  const void* src2; int H2, W2, Cin2, stride2;       // fused shortcut operand (Cin2 = 0: none)
-  const void* weight; const float* bias; int bias_classes; const float* alpha;
-  const __nv_bfloat16* res; void* dst; int Cout; int out_fp32;
-};
-
 static int pick_bn(int cout) { return cout % 256 == 0 ? 256 : (cout % 128 == 0 ? 128 : 64); }
 
-static int build_conv_op(ConvOp* op, const ConvGeom& g, int n_cap) {
+int build_conv_op(ConvOp* op, const ConvGeom& g, int n_cap) {
   if (g.Cin % kBlockK || g.Cin2 % kBlockK || g.Cout % 64) return set_error(CER_ERR_INVALID, "channels must be multiples of 64");
   memset(op, 0, sizeof *op);
   const int Hout = (g.H + 2 * g.pad - g.ksize) / g.stride + 1;
@@ -316,7 +302,7 @@ static bool pair_mode_enabled() {
   return v == 1;
 }
 
-static int launch_conv(const ConvOp& op, int frames, int num_sms, cudaStream_t st) {
+int launch_conv(const ConvOp& op, int frames, int num_sms, cudaStream_t st) {
   ConvKernelParams p = op.kp;
   p.M = frames * op.hw_out;
   p.num_m_tiles = (p.M + kBlockM - 1) / kBlockM;

@@ -11,7 +11,7 @@ from typing import Dict, List, Optional, Sequence
 import torch
 
 from . import _capi
-from ._capi import FusionWeights, Ir50Weights, IrUnit, TcnBlock, check, lib
+from ._capi import FusionWeights, Ir50Weights, IrUnit, TcnBlock, VggConv, VggFc, VggishWeights, check, lib
 
 
 def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
@@ -92,6 +92,65 @@ class Ir50Engine:
         if h:
             try:
                 lib().cer_ir50_destroy(h)
+            except Exception:
+                pass
+            self._h = None
+
+
+class VggishEngine:
+    """VGGish plan (cer_vggish_*): [N,96,64] fp32 log-mel examples -> [N,128] fp32."""
+
+    def __init__(self, packed: dict, device: torch.device, patches_per_pass: int = 1200):
+        _capi.require_gpu()
+        self.device = torch.device(device)
+        self.patches_per_pass = int(patches_per_pass)
+        self._keep: List[torch.Tensor] = []
+
+        def put(t):
+            d = t.to(self.device).contiguous()
+            self._keep.append(d)
+            return d.data_ptr()
+
+        self._convs = (VggConv * len(packed["convs"]))()
+        for i, c in enumerate(packed["convs"]):
+            self._convs[i] = VggConv(c["cin"], c["cout"], c["pool_after"], put(c["w"]), put(c["bias"]))
+        self._fcs = (VggFc * len(packed["fcs"]))()
+        for i, f in enumerate(packed["fcs"]):
+            self._fcs[i] = VggFc(f["in_dim"], f["out_dim"], f["relu"], put(f["w"]), put(f["bias"]))
+        self._w = VggishWeights(packed["in_h"], packed["in_w"], packed["c1"], put(packed["conv1_w"]),
+                                put(packed["conv1_bias"]), len(packed["convs"]), self._convs, len(packed["fcs"]),
+                                self._fcs, put(packed["zeros"]))
+        self.in_h, self.in_w, self.emb_dim = packed["in_h"], packed["in_w"], packed["emb_dim"]
+        with torch.cuda.device(self.device):
+            nbytes = lib().cer_vggish_workspace_bytes(C.byref(self._w), self.patches_per_pass)
+            self._ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+            h = C.c_void_p()
+            check(lib().cer_vggish_create(C.byref(h), C.byref(self._w), self.patches_per_pass, self._ws.data_ptr(), nbytes),
+                  "cer_vggish_create")
+        self._h = h
+
+    def forward(self, x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        if x.dim() != 3 or x.shape[1] != self.in_h or x.shape[2] != self.in_w:
+            raise ValueError(f"expected [N,{self.in_h},{self.in_w}], got {tuple(x.shape)}")
+        if x.device != self.device or x.dtype != torch.float32:
+            raise ValueError("input must be fp32 on the engine's CUDA device")
+        x = x.contiguous()
+        n = x.shape[0]
+        if out is None:
+            out = torch.empty(n, self.emb_dim, dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            check(lib().cer_vggish_forward(self._h, x.data_ptr(), n, out.data_ptr(), _capi.current_stream_ptr()),
+                  "cer_vggish_forward")
+        return out
+
+    def launches(self, n: int) -> int:
+        return int(lib().cer_vggish_launches(self._h, n))
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            try:
+                lib().cer_vggish_destroy(h)
             except Exception:
                 pass
             self._h = None

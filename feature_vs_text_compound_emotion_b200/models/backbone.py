@@ -1,2 +1,2 @@
-"""Mirror of reference models/backbone.py (VisualBackbone; VGGish is a later scope row)."""
-from ..modules import Flatten, VisualBackbone  # noqa: F401
+"""Mirror of reference models/backbone.py (VGG / VGGish / VisualBackbone / AudioBackbone)."""
+from ..modules import AudioBackbone, Flatten, VGG, VGGish, VisualBackbone, _vgg, make_layers  # noqa: F401

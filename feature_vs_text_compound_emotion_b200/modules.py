@@ -21,7 +21,7 @@ from torch import nn
 from torch.nn.utils import weight_norm
 
 from . import packing
-from .engine import FusionEngine, Ir50Engine, TcnEngine
+from .engine import FusionEngine, Ir50Engine, TcnEngine, VggishEngine
 
 TASKS = ("CLASSIFICATION", "REGRESSION")          # constants.py:17-20
 
@@ -173,6 +173,73 @@ class VisualBackbone(_PackedModule):
         return self.backbone(x)
 
     def extract(self, x):
+        return self.backbone(x)
+
+
+# ----------------------------------------------------------------------------------------------
+# VGGish (models/backbone.py:16-66, :133-145)
+# ----------------------------------------------------------------------------------------------
+def make_layers() -> nn.Sequential:
+    """Parameter layout of models/backbone.py:43-53 (features.{0,3,6,8,11,13})."""
+    layers, in_channels = [], 1
+    for v in packing.VGGISH_CFG:
+        if v == "M":
+            layers += [nn.MaxPool2d(kernel_size=2, stride=2)]
+        else:
+            layers += [nn.Conv2d(in_channels, v, kernel_size=3, padding=1), nn.ReLU(inplace=True)]
+            in_channels = v
+    return nn.Sequential(*layers)
+
+
+class VGG(_PackedModule):
+    """models/backbone.py:16-40.  ``forward(x[N,1,96,64]) -> [N,128]``."""
+
+    patches_per_pass = 1200     # patches per pass of the plan (workspace ~0.8 MB per patch)
+
+    def __init__(self, features):
+        super().__init__()
+        self.features = features
+        self.embeddings = nn.Sequential(nn.Linear(512 * 4 * 6, 4096), nn.ReLU(True), nn.Linear(4096, 4096),
+                                        nn.ReLU(True), nn.Linear(4096, 128))
+
+    def engine(self) -> VggishEngine:
+        if self.__dict__["_engine"] is None:
+            sd = {k: v.detach().cpu() for k, v in self.state_dict().items()}
+            self.__dict__["_engine"] = VggishEngine(packing.pack_vggish(sd), self._device(), self.patches_per_pass)
+        return self.__dict__["_engine"]
+
+    def forward(self, x):
+        self._check_inference()
+        if x.dim() != 4 or x.shape[1] != 1:
+            raise ValueError(f"expected [N,1,96,64], got {tuple(x.shape)}")
+        return self.engine().forward(x[:, 0].float())
+
+
+def _vgg():
+    return VGG(make_layers())
+
+
+class VGGish(VGG):
+    """models/backbone.py:59-66: takes [N,96,64] examples (adds the channel axis itself)."""
+
+    def __init__(self):
+        super().__init__(make_layers())
+
+    def forward(self, x, fs=None):
+        x = torch.as_tensor(x, device=self._device())[:, None, :, :].float()
+        return VGG.forward(self, x)
+
+
+class AudioBackbone(_PackedModule):
+    """models/backbone.py:133-145: frozen VGGish; ``forward(x[N,96,64]) -> [N,128]``."""
+
+    def __init__(self):
+        super().__init__()
+        self.backbone = VGGish()
+        for param in self.backbone.parameters():
+            param.requires_grad = False
+
+    def forward(self, x, extract_vggish=False):
         return self.backbone(x)
 
 
@@ -383,13 +450,25 @@ class LFAN(_PackedModule):
             param.requires_grad = False
         return resnet
 
-    def init(self, visual_state_dict=None):
-        """models/model.py:451-485.  ``visual_state_dict`` (optional, not in the reference) lets a
-        caller hand over the IR-50 weights directly instead of through root_dir/<name>.pth."""
+    def load_audio_backbone(self, backbone_settings, state_dict=None):
+        """models/model.py:437-449: vggish.pth is the VGGish (not AudioBackbone) state_dict."""
+        vggish = AudioBackbone()
+        if state_dict is None:
+            state_dict = torch.load(os.path.join(self.root_dir, backbone_settings['audio_state_dict'] + ".pth"),
+                                    map_location='cpu')
+        vggish.backbone.load_state_dict(state_dict)
+        for param in vggish.parameters():
+            param.requires_grad = False
+        return vggish
+
+    def init(self, visual_state_dict=None, audio_state_dict=None):
+        """models/model.py:451-485.  ``visual_state_dict`` / ``audio_state_dict`` (optional, not in
+        the reference) let a caller hand over the backbone weights directly instead of through
+        root_dir/<name>.pth."""
         if 'video' in self.modality:
             self.spatial["visual"] = self.load_visual_backbone(self.backbone_settings, visual_state_dict)
         if 'logmel' in self.modality:
-            raise NotImplementedError("inline VGGish ('logmel' modality) is a later scope row (SURVEY.md section 8 f3)")
+            self.spatial["audio"] = self.load_audio_backbone(self.backbone_settings, audio_state_dict)
         for modal in self.modality:
             self.temporal[modal] = TemporalConvNet(num_inputs=self.embedding_dim[modal], max_length=self.example_length,
                                                    num_channels=self.tcn_channel[modal], attention=self.tcn_attention,
@@ -419,6 +498,13 @@ class LFAN(_PackedModule):
         emb = self.spatial["visual"](video.reshape(B * T, *video.shape[2:]))
         return emb.view(B, T, -1)
 
+    def encode_logmel(self, logmel: torch.Tensor) -> torch.Tensor:
+        """[B,64,T,96] -> [B,T,128] through the VGGish kernels (model.py:499-509: one [96,64]
+        example per frame, laid out as [batch, bands, length, frames])."""
+        B, hh, T, ww = logmel.shape
+        patches = logmel.permute(0, 2, 3, 1).contiguous().view(-1, ww, hh)
+        return self.spatial["audio"](patches).view(B, T, -1)
+
     def forward_features(self, feats: Dict[str, torch.Tensor]) -> torch.Tensor:
         """feats[m]: [B,T,D_m] fp32 (visual = IR-50 embeddings) -> logits [B,T,output_dim]."""
         tcn, fus = self._head_engines()
@@ -432,10 +518,10 @@ class LFAN(_PackedModule):
 
     def forward(self, X):
         self._check_inference()
-        if 'logmel' in X:
-            raise NotImplementedError("inline VGGish ('logmel') is not built")
         if 'video' in X:
             X['video'] = self.encode_frames(X['video']).unsqueeze(1)
+        if 'logmel' in X:
+            X['logmel'] = self.encode_logmel(X['logmel']).unsqueeze(1)
         for modal in X:
             X[modal] = X[modal].squeeze(1)
         batch_size = X[self.modality[0]].shape[0]

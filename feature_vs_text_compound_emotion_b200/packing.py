@@ -179,3 +179,40 @@ def pack_fusion(sd: Dict[str, torch.Tensor], modalities: Sequence[str], modal_di
            "br": sd[regressor + ".bias"].float().contiguous()}
     out["n_out"] = int(out["br"].shape[0])
     return out
+
+
+VGGISH_CFG = (64, "M", 128, "M", 256, 256, "M", 512, 512, "M")     # make_layers(), models/backbone.py:43-53
+
+
+def pack_vggish(sd: Dict[str, torch.Tensor], prefix: str = "", in_hw=(96, 64),
+                operand_dtype: torch.dtype = torch.bfloat16) -> dict:
+    """vggish.pth layout (features.{0,3,6,8,11,13}, embeddings.{0,2,4}; models/backbone.py:16-66)
+    -> {'conv1_w' [9][64] fp32, 'conv1_bias', 'convs': [{cin,cout,pool_after,w [cout][9*cin],bias}],
+    'fcs': [{in_dim,out_dim,relu,w [out][in],bias}], 'zeros'}.  Conv weights go to K = (r,s,ci);
+    the first FC's K axis is already the (h,w,c) flatten the reference builds with its two
+    transposes (:34-37), which is the NHWC order the kernels produce, so it is used as is."""
+    idx, cin, convs = 0, 1, []
+    for j, v in enumerate(VGGISH_CFG):
+        if v == "M":
+            idx += 1
+            continue
+        W = sd[f"{prefix}features.{idx}.weight"].double()             # [cout, cin, 3, 3]
+        b = sd[f"{prefix}features.{idx}.bias"].float().contiguous()
+        pool = int(j + 1 < len(VGGISH_CFG) and VGGISH_CFG[j + 1] == "M")
+        if cin == 1:
+            if not pool:
+                raise ValueError("the first conv must be followed by a pool")
+            conv1 = (W.permute(2, 3, 1, 0).reshape(9, v).float().contiguous(), b)
+        else:
+            convs.append({"cin": cin, "cout": v, "pool_after": pool,
+                          "w": W.permute(0, 2, 3, 1).reshape(v, 9 * cin).to(operand_dtype).contiguous(), "bias": b})
+        idx += 2
+        cin = v
+    fcs = []
+    for i in (0, 2, 4):
+        W = sd[f"{prefix}embeddings.{i}.weight"]
+        fcs.append({"in_dim": int(W.shape[1]), "out_dim": int(W.shape[0]), "relu": int(i != 4),
+                    "w": W.to(operand_dtype).contiguous(), "bias": sd[f"{prefix}embeddings.{i}.bias"].float().contiguous()})
+    width = max([c["cout"] for c in convs] + [f["out_dim"] for f in fcs])
+    return {"in_h": in_hw[0], "in_w": in_hw[1], "c1": int(conv1[0].shape[1]), "conv1_w": conv1[0], "conv1_bias": conv1[1],
+            "convs": convs, "fcs": fcs, "zeros": torch.zeros(width), "emb_dim": fcs[-1]["out_dim"]}

@@ -100,6 +100,46 @@ int cer_conv_forward(const void* src_nhwc_dev, int32_t n_frames, int32_t n_alloc
                      void* dst_dev, int32_t out_fp32, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * VGGish audio backbone (the inline `logmel` modality).   Replaces AudioBackbone.forward /
+ * VGGish.forward / VGG.forward (models/backbone.py:29-40, :59-66, :133-145): six conv3x3+ReLU
+ * with four 2x2 max-pools (make_layers, :43-53), NHWC flatten (:34-37), Linear-ReLU-Linear-ReLU-
+ * Linear (:20-27).  Weights arrive pre-packed by packing.pack_vggish.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct cer_vgg_conv {
+  int32_t cin, cout, pool_after;  /* conv3x3 pad 1 + ReLU, then MaxPool2d(2,2) if pool_after        */
+  const void* w;                  /* bf16 [cout][9*cin], K = (r,s,ci)                                */
+  const float* bias;              /* fp32 [cout]                                                     */
+} cer_vgg_conv;
+
+typedef struct cer_vgg_fc {
+  int32_t in_dim, out_dim, relu;
+  const void* w;                  /* bf16 [out_dim][in_dim]; the first FC's K is the (h,w,c) flatten */
+  const float* bias;              /* fp32 [out_dim]                                                  */
+} cer_vgg_fc;
+
+typedef struct cer_vggish_weights {
+  int32_t in_h, in_w;             /* 96 frames x 64 mel bands                                        */
+  int32_t c1;                     /* outputs of the first conv (64); it is always followed by a pool */
+  const float* conv1_w;           /* fp32 [9][c1]  features.0.weight, row = r*3+s                    */
+  const float* conv1_bias;        /* fp32 [c1]                                                       */
+  int32_t n_convs;
+  const cer_vgg_conv* convs;      /* HOST array: features.3 .. features.13                           */
+  int32_t n_fcs;
+  const cer_vgg_fc* fcs;          /* HOST array: embeddings.0/2/4                                    */
+  const float* zeros;             /* fp32 [max(cout, out_dim)] zeros: ReLU = PReLU with slope 0      */
+} cer_vggish_weights;
+
+typedef struct cer_vggish cer_vggish;
+
+size_t cer_vggish_workspace_bytes(const cer_vggish_weights* w, int64_t patches_per_pass);
+int cer_vggish_create(cer_vggish** out, const cer_vggish_weights* w, int64_t patches_per_pass, void* workspace_dev,
+                      size_t workspace_bytes);
+/* x_dev: fp32 [n_patches][in_h][in_w] log-mel examples; emb_out_dev: fp32 [n_patches][128]. */
+int cer_vggish_forward(cer_vggish* plan, const float* x_dev, int64_t n_patches, float* emb_out_dev, void* stream);
+int64_t cer_vggish_launches(const cer_vggish* plan, int64_t n_patches);
+void cer_vggish_destroy(cer_vggish* plan);
+
+/* ------------------------------------------------------------------------------------------
  * One TemporalBlock, fused.   Replaces TemporalBlock.forward
  * (models/temporal_convolutional_model.py:21-54): weight-normed dilated Conv1d + Chomp1d +
  * LeakyReLU, twice, plus identity / 1x1 residual and the final LeakyReLU.  Optionally applies a

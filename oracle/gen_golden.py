@@ -9,6 +9,8 @@ reference modules, imported as they are, are the source of truth):
   * head_b2.pt      -- LFAN(cnn_res50,vggish,bert) forward, B=2 x T=300  (BASELINE cfg 1 shape)
   * lfan_b1.pt      -- LFAN(video,vggish,bert) forward from pixels, B=1 x T=300
   * state_keys.json -- the reference's own state_dict key/shape listing (534 keys)
+  * vggish_n6.pt    -- VGGish forward on 6 synthetic log-mel examples (+ its 18 state_dict keys)
+  * lfan_logmel_b1.pt -- LFAN(video,logmel,bert) forward from pixels and log-mel, B=1 x T=40
   * windowing.json  -- Trainer.windowing outputs for a set of lengths
 Weights are NOT stored: they are regenerated from the seed by
 feature_vs_text_compound_emotion_b200.synthetic (identical on every machine), and are loaded
@@ -99,6 +101,39 @@ def main():
     torch.save({"feat_seed": 77, "frame_seed": 78, "weights_seed": 0, "modalities": mods3, "logits": lg},
                os.path.join(OUT, "lfan_b1.pt"))
     print("lfan", lg.shape, float(lg.abs().mean()), len(keys), "keys")
+
+    # ---- VGGish + LFAN with the inline `logmel` modality ---------------------------------------
+    from models.backbone import VGGish
+    asd = synthetic.vggish_state_dict(seed=0)
+    vg = VGGish()
+    vg.load_state_dict(asd, strict=True)
+    vg.eval()
+    xa = synthetic.logmel_patches(6, seed=1234)
+    ya = vg(xa)
+    torch.save({"x_seed": 1234, "n": 6, "weights_seed": 0, "emb": ya, "keys": {k: list(v.shape) for k, v in vg.state_dict().items()}},
+               os.path.join(OUT, "vggish_n6.pt"))
+    print("vggish", ya.shape, float(ya.abs().mean()))
+
+    modsl = ["video", "logmel", "bert"]
+    TL = 40
+    torch.save(asd, os.path.join(tmp, "vggish.pth"))
+    lm = LFAN(backbone_settings=ref_configs.config["backbone_settings"], output_dim=7,
+              task="CLASSIFICATION", modality=modsl, kernel_size=5, example_length=TL,
+              tcn_channel=synthetic.TCN_CHANNELS, modal_dim=32, num_heads=2, root_dir=tmp, device="cpu")
+    lm.init()
+    lsd = synthetic.lfan_state_dict(seed=0, modalities=modsl)
+    assert list(lm.state_dict()) == list(lsd), "synthetic key order differs from the reference's (logmel)"
+    lm.load_state_dict(lsd, strict=True)
+    lm.eval()
+    fl = synthetic.feature_windows(1, TL, seed=91, modalities=["bert"])
+    Xl = {"video": synthetic.frames(TL, seed=92).view(1, TL, 3, 40, 40),
+          "logmel": synthetic.logmel_patches(TL, seed=93).view(1, TL, 96, 64).permute(0, 3, 1, 2).contiguous(),
+          "bert": fl["bert"]}
+    ll = lm({k: v.clone() for k, v in Xl.items()})
+    torch.save({"length": TL, "bert_seed": 91, "frame_seed": 92, "logmel_seed": 93, "weights_seed": 0,
+                "modalities": modsl, "logits": ll, "keys": {k: list(v.shape) for k, v in lm.state_dict().items()}},
+               os.path.join(OUT, "lfan_logmel_b1.pt"))
+    print("lfan logmel", ll.shape, float(ll.abs().mean()), len(lsd), "keys")
 
     # ---- windowing (trainer.py imports pynvml/munch, absent here: exec the one function) ----
     src = open(os.path.join(REF, "trainer.py")).read()

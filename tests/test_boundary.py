@@ -21,7 +21,8 @@ def _lfan(mods):
     m = LFAN(backbone_settings=BS, output_dim=7, task="CLASSIFICATION", modality=mods, kernel_size=5,
              example_length=300, tcn_channel=synthetic.TCN_CHANNELS, modal_dim=32, num_heads=2, root_dir="",
              device="cpu")
-    m.init(visual_state_dict=synthetic.visual_backbone_state_dict(0) if "video" in mods else None)
+    m.init(visual_state_dict=synthetic.visual_backbone_state_dict(0) if "video" in mods else None,
+           audio_state_dict=synthetic.vggish_state_dict(0) if "logmel" in mods else None)
     return m
 
 
@@ -36,6 +37,23 @@ def test_lfan_state_dict_layout_equals_reference(golden_dir):
     trainable = sum(p.numel() for p in m.parameters() if p.requires_grad)
     assert trainable == 5002503
     assert sum(p.numel() for p in m.parameters()) == 42290127
+
+
+def test_logmel_lfan_and_vggish_layouts_equal_reference(golden_dir, tmp_path):
+    g = torch.load(os.path.join(golden_dir, "lfan_logmel_b1.pt"))
+    m = _lfan(g["modalities"])
+    assert {k: list(v.shape) for k, v in m.state_dict().items()} == g["keys"]
+    assert list(m.state_dict()) == list(g["keys"])
+    m.load_state_dict(synthetic.lfan_state_dict(0, g["modalities"]), strict=True)
+    assert not any(p.requires_grad for p in m.spatial["audio"].parameters())
+    # vggish.pth layout through root_dir, as models/model.py:437-449 loads it
+    from feature_vs_text_compound_emotion_b200.models.model import LFAN
+    torch.save(synthetic.vggish_state_dict(0), tmp_path / "vggish.pth")
+    m2 = LFAN(backbone_settings=BS, output_dim=7, task="CLASSIFICATION", modality=["logmel"], root_dir=str(tmp_path),
+              tcn_channel=synthetic.TCN_CHANNELS, device="cpu")
+    m2.init()
+    v = torch.load(os.path.join(golden_dir, "vggish_n6.pt"))
+    assert {k: list(t.shape) for k, t in m2.spatial["audio"].backbone.state_dict().items()} == v["keys"]
 
 
 def test_feature_only_modalities():

@@ -23,12 +23,13 @@ def _dev():
     return torch.device("cuda:0")
 
 
-def _lfan(mods, dev, seed=0):
+def _lfan(mods, dev, seed=0, length=300):
     from feature_vs_text_compound_emotion_b200.models.model import LFAN
     m = LFAN(backbone_settings=BS, output_dim=7, task="CLASSIFICATION", modality=mods, kernel_size=5,
-             example_length=300, tcn_channel=synthetic.TCN_CHANNELS, modal_dim=32, num_heads=2, root_dir="",
+             example_length=length, tcn_channel=synthetic.TCN_CHANNELS, modal_dim=32, num_heads=2, root_dir="",
              device=dev)
-    m.init(visual_state_dict=synthetic.visual_backbone_state_dict(seed) if "video" in mods else None)
+    m.init(visual_state_dict=synthetic.visual_backbone_state_dict(seed) if "video" in mods else None,
+           audio_state_dict=synthetic.vggish_state_dict(seed) if "logmel" in mods else None)
     m.load_state_dict(synthetic.lfan_state_dict(seed, mods), strict=True)
     return m.to(dev).eval()
 
@@ -133,3 +134,49 @@ def test_long_video_windowing_dedup_and_stitch():
     want = O.windowed_inference(lambda c: fwd({"video": c["video"].unsqueeze(1), "vggish": c["vggish"], "bert": c["bert"]}), Xo)[0]
     assert (out - want).abs().max().item() <= 2e-2
     assert (out.argmax(-1) == want.argmax(-1)).float().mean().item() >= 0.995
+
+
+def test_vggish_module_vs_golden(golden_dir):
+    """AudioBackbone / VGGish drop-in: bf16 tensor-core convs vs the reference's fp32 output."""
+    dev = _dev()
+    from feature_vs_text_compound_emotion_b200.models.backbone import AudioBackbone
+    g = torch.load(os.path.join(golden_dir, "vggish_n6.pt"))
+    ab = AudioBackbone()
+    ab.backbone.load_state_dict(synthetic.vggish_state_dict(g["weights_seed"]), strict=True)
+    ab = ab.to(dev).eval()
+    emb = ab(synthetic.logmel_patches(g["n"], seed=g["x_seed"]).to(dev)).cpu()
+    assert emb.shape == (6, 128)
+    assert F.cosine_similarity(emb, g["emb"], dim=1).min().item() >= 0.999
+    assert ((emb - g["emb"]).abs().max() / g["emb"].abs().max()).item() <= 2e-2
+
+
+def test_vggish_many_patches_multi_pass():
+    """More patches than one pass holds (ragged last pass), against the oracle."""
+    dev = _dev()
+    from feature_vs_text_compound_emotion_b200.models.backbone import VGGish
+    sd = synthetic.vggish_state_dict(4)
+    VGGish.patches_per_pass = 40
+    try:
+        vg = VGGish()
+        vg.load_state_dict(sd, strict=True)
+        vg = vg.to(dev).eval()
+        x = synthetic.logmel_patches(97, seed=11)
+        emb = vg(x.to(dev)).cpu()
+    finally:
+        VGGish.patches_per_pass = 1200
+    ref = O.vggish_forward(sd, x)
+    assert F.cosine_similarity(emb, ref, dim=1).min().item() >= 0.999
+
+
+def test_lfan_logmel_from_pixels_vs_golden(golden_dir):
+    dev = _dev()
+    g = torch.load(os.path.join(golden_dir, "lfan_logmel_b1.pt"))
+    mods, T = g["modalities"], g["length"]
+    m = _lfan(mods, dev, g["weights_seed"], length=T)
+    X = {"video": synthetic.frames(T, seed=g["frame_seed"]).view(1, T, 3, 40, 40).to(dev),
+         "logmel": synthetic.logmel_patches(T, seed=g["logmel_seed"]).view(1, T, 96, 64).permute(0, 3, 1, 2).contiguous().to(dev),
+         "bert": synthetic.feature_windows(1, T, seed=g["bert_seed"], modalities=["bert"])["bert"].to(dev)}
+    out = m(X).cpu()
+    assert out.shape == (1, T, 7)
+    assert (out - g["logits"]).abs().max().item() <= 2e-2
+    assert (out.argmax(-1) == g["logits"].argmax(-1)).float().mean().item() >= 0.975   # 40 frames: at most one flip

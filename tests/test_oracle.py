@@ -82,3 +82,25 @@ def test_windowed_inference_overlap_average():
     X = {"vggish": torch.arange(L, dtype=torch.float32).view(1, 1, L, 1)}
     out = O.windowed_inference(fwd, X)
     assert torch.allclose(out[0, :, 0], torch.arange(L, dtype=torch.float32))
+
+
+def test_vggish_matches_reference(golden_dir):
+    g = torch.load(os.path.join(golden_dir, "vggish_n6.pt"))
+    sd = synthetic.vggish_state_dict(g["weights_seed"])
+    assert {k: list(v.shape) for k, v in sd.items()} == g["keys"] and len(sd) == 18
+    emb = O.vggish_forward(sd, synthetic.logmel_patches(g["n"], seed=g["x_seed"]))
+    assert emb.shape == (6, 128)
+    assert (emb - g["emb"]).abs().max().item() < 1e-4 * g["emb"].abs().max().item()
+
+
+def test_lfan_logmel_matches_reference(golden_dir):
+    """LFAN(video, logmel, bert): the inline-VGGish variant of the path (model.py:499-509)."""
+    g = torch.load(os.path.join(golden_dir, "lfan_logmel_b1.pt"))
+    mods, T = g["modalities"], g["length"]
+    sd = synthetic.lfan_state_dict(g["weights_seed"], mods)
+    assert {k: list(v.shape) for k, v in sd.items()} == g["keys"] and list(sd) == list(g["keys"])
+    X = {"video": synthetic.frames(T, seed=g["frame_seed"]).view(1, T, 3, 40, 40),
+         "logmel": synthetic.logmel_patches(T, seed=g["logmel_seed"]).view(1, T, 96, 64).permute(0, 3, 1, 2).contiguous(),
+         "bert": synthetic.feature_windows(1, T, seed=g["bert_seed"], modalities=["bert"])["bert"]}
+    logits = O.lfan_forward(sd, X, mods)
+    assert (logits - g["logits"]).abs().max().item() < 5e-5
