@@ -11,6 +11,7 @@ reference modules, imported as they are, are the source of truth):
   * state_keys.json -- the reference's own state_dict key/shape listing (534 keys)
   * vggish_n6.pt    -- VGGish forward on 6 synthetic log-mel examples (+ its 18 state_dict keys)
   * lfan_logmel_b1.pt -- LFAN(video,logmel,bert) forward from pixels and log-mel, B=1 x T=40
+  * train_b2.pt     -- two SGD-nesterov steps of the head in train mode (Dropout p=0): loss, gradients, BN stats
   * windowing.json  -- Trainer.windowing outputs for a set of lengths
 Weights are NOT stored: they are regenerated from the seed by
 feature_vs_text_compound_emotion_b200.synthetic (identical on every machine), and are loaded
@@ -24,6 +25,7 @@ import warnings
 
 import numpy as np
 import torch
+import torch._dynamo  # noqa: F401  (torch.optim pulls it in; must be imported before the reference edits sys.path)
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF = "/root/reference"
@@ -134,6 +136,39 @@ def main():
                 "modalities": modsl, "logits": ll, "keys": {k: list(v.shape) for k, v in lm.state_dict().items()}},
                os.path.join(OUT, "lfan_logmel_b1.pt"))
     print("lfan logmel", ll.shape, float(ll.abs().mean()), len(lsd), "keys")
+
+    # ---- fusion-head training step (cfg 4), dropout p = 0 so that it is reproducible ---------
+    sys.path[:] = [q for q in sys.path if isinstance(q, str)]
+    model.load_state_dict(hsd, strict=True)
+    model.train()
+    for mod in model.modules():
+        if isinstance(mod, torch.nn.Dropout):
+            mod.p = 0.0
+    Xt = synthetic.feature_windows(2, 300, seed=4321, modalities=mods)
+    labels = torch.randint(0, 7, (2, 300, 1), generator=torch.Generator().manual_seed(4322)).float()
+    opt_cfg = {"name": "sgd", "lr": 1e-2, "momentum": 0.9, "dampening": 0.0, "weight_decay": 1e-4, "nesterov": True}
+    params = [q for q in model.parameters() if q.requires_grad]
+    opt = torch.optim.SGD(params, lr=opt_cfg["lr"], momentum=0.9, dampening=0.0, weight_decay=1e-4, nesterov=True)
+    rec = {"x_seed": 4321, "label_seed": 4322, "weights_seed": 0, "modalities": mods, "opt": opt_cfg, "steps": []}
+    with torch.enable_grad():
+        for it in range(2):
+            opt.zero_grad(set_to_none=True)
+            outputs = model({k: v.clone() for k, v in Xt.items()})
+            loss = torch.nn.functional.cross_entropy(outputs.contiguous().view(600, 7), labels.view(600).long())
+            loss.backward()
+            grads = {k: q.grad.detach().clone() for k, q in model.named_parameters() if q.grad is not None}
+            opt.step()
+            after = model.state_dict()
+            step = {"loss": float(loss), "grad_sum": {k: float(g.double().sum()) for k, g in grads.items()},
+                    "grad_norm": {k: float(g.double().norm()) for k, g in grads.items()},
+                    "grad_small": {k: g for k, g in grads.items() if g.numel() <= 4096},
+                    "grad_sample": {k: g.flatten()[::997].clone() for k, g in grads.items() if g.numel() > 4096},
+                    "param_sample": {k: v.detach().flatten()[::997].clone() for k, v in after.items() if v.dtype.is_floating_point},
+                    "bn": {k: v.clone() for k, v in after.items() if k.startswith("bn.")}}
+            rec["steps"].append(step)
+            print("train step", it, float(loss), len(grads), "grads")
+    torch.save(rec, os.path.join(OUT, "train_b2.pt"))
+    torch.set_grad_enabled(False)
 
     # ---- windowing (trainer.py imports pynvml/munch, absent here: exec the one function) ----
     src = open(os.path.join(REF, "trainer.py")).read()

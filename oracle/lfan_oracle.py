@@ -263,3 +263,160 @@ def windowed_inference(forward_fn, X: Dict[str, Tensor], window_length: int = 30
         out[:, wd] += y
         cnt[wd] += 1
     return out / cnt.view(1, -1, 1)
+
+
+# --------------------------------------------------------------------------------------
+# Fusion-head training step (BASELINE config 4; trainer.py:365-391, experiment.py:133)
+# --------------------------------------------------------------------------------------
+BN_MOMENTUM = 0.1      # torch.nn.BatchNorm1d default (models/model.py:475)
+TCN_DROPOUT = 0.1      # models/model.py:471
+FUSION_DROPOUT = 0.1   # models/model.py:482
+
+
+def dropout_keep_mask(shape, p: float, seed: int, stream: int) -> Tensor:
+    """The dropout RNG of THIS repo's training kernels (csrc/train.cu `dropout_keep`), restated in
+    numpy so the oracle can apply exactly the masks the kernels draw.  It is not torch's Philox
+    stream: the reference's masks are not reproducible outside torch, so parity of the training
+    step is pinned with p = 0 against the reference and with these masks against the oracle.
+    keep(idx) = fmix32(idx * 0x9E3779B1 + seed + stream * 0x85EBCA6B) >= p * 2^32, idx = row-major
+    element index of the [rows, channels] activation."""
+    n = int(np.prod(shape))
+    with np.errstate(over="ignore"):
+        x = np.arange(n, dtype=np.uint32) * np.uint32(0x9E3779B1) + np.uint32((seed + stream * 0x85EBCA6B) & 0xFFFFFFFF)
+        x ^= x >> np.uint32(16)
+        x *= np.uint32(0x85EBCA6B)
+        x ^= x >> np.uint32(13)
+        x *= np.uint32(0xC2B2AE35)
+        x ^= x >> np.uint32(16)
+    thr = np.uint32(min(int(p * 4294967296.0), 0xFFFFFFFF))
+    return torch.from_numpy((x >= thr).astype(np.float32)).view(*shape)
+
+
+def _drop(x: Tensor, p: float, seed, stream: int) -> Tensor:
+    """nn.Dropout in training mode on a [B, T, C] (time-major) activation; seed None => p = 0."""
+    if seed is None or p <= 0.0:
+        return x
+    return x * dropout_keep_mask(tuple(x.shape), p, seed, stream) / (1.0 - p)
+
+
+def dropout_stream(modal_index: int, block: int, site: int) -> int:
+    """Stream ids shared with the kernels: TCN dropout1/dropout2 of block i of modality m."""
+    return modal_index * 16 + block * 2 + site
+
+
+FUSION_STREAM = 4096
+
+
+def head_forward_train(P: SD, buffers: SD, feats: Dict[str, Tensor], modalities: Sequence[str],
+                       modal_dim: int = 32, num_heads: int = 2, seed=None,
+                       p_tcn: float = TCN_DROPOUT, p_fusion: float = FUSION_DROPOUT) -> Tensor:
+    """LFAN.forward after the backbones in TRAINING mode (model.py:511-526 under model.train()):
+    Dropout active after both LeakyReLUs of every TemporalBlock (temporal_convolutional_model.py:
+    28,34) and on the attention output (transformer.py:194); BatchNorm1d uses batch statistics and
+    updates ``buffers`` (running_mean/var with the unbiased variance, momentum 0.1).
+    P: trainable tensors (reference names), feats[m]: [B, T, D_m].  Activations are kept
+    time-major [B, T, C] so that dropout indices match the kernels' layout."""
+    enc = {}
+    for mi, m in enumerate(modalities):
+        x = feats[m]
+        i = 0
+        while f"temporal.{m}.network.{i}.conv1.weight_v" in P:
+            p = f"temporal.{m}.network.{i}"
+            d = 2 ** i
+            w1 = weight_norm_effective(P[p + ".conv1.weight_g"], P[p + ".conv1.weight_v"])
+            w2 = weight_norm_effective(P[p + ".conv2.weight_g"], P[p + ".conv2.weight_v"])
+            xc = x.transpose(1, 2)
+            h = F.leaky_relu(causal_dilated_conv(xc, w1, P[p + ".conv1.bias"], d), LEAKY_SLOPE).transpose(1, 2)
+            h = _drop(h, p_tcn, seed, dropout_stream(mi, i, 0))
+            h = F.leaky_relu(causal_dilated_conv(h.transpose(1, 2), w2, P[p + ".conv2.bias"], d), LEAKY_SLOPE).transpose(1, 2)
+            h = _drop(h, p_tcn, seed, dropout_stream(mi, i, 1))
+            if (p + ".downsample.weight") in P:
+                res = F.conv1d(xc, P[p + ".downsample.weight"], P[p + ".downsample.bias"]).transpose(1, 2)
+            else:
+                res = x
+            x = F.leaky_relu(h + res, LEAKY_SLOPE)
+            i += 1
+        xb = F.batch_norm(x.transpose(1, 2), buffers[f"bn.{m}.running_mean"], buffers[f"bn.{m}.running_var"],
+                          P[f"bn.{m}.weight"], P[f"bn.{m}.bias"], True, BN_MOMENTUM, BN_EPS)
+        if f"bn.{m}.num_batches_tracked" in buffers:
+            buffers[f"bn.{m}.num_batches_tracked"] += 1
+        enc[m] = xb.transpose(1, 2)
+    hd = modal_dim // num_heads
+    a = "fusion.layers.self_attn."
+    qs, ks, vs = [], [], []
+    for m in modalities:
+        qkv = F.linear(enc[m], P[f"{a}qkv_proj.{m}.weight"], P[f"{a}qkv_proj.{m}.bias"])
+        B, T, _ = qkv.shape
+        qkv = qkv.view(B, T, num_heads, 3, hd)
+        qs.append(qkv[:, :, :, 0]); ks.append(qkv[:, :, :, 1]); vs.append(qkv[:, :, :, 2])
+    Q, K, V = torch.stack(qs, 3), torch.stack(ks, 3), torch.stack(vs, 3)
+    att = torch.softmax(torch.einsum("bthmd,bthnd->bthmn", Q, K) / math.sqrt(hd), dim=-1)
+    vals = (torch.einsum("bthmn,bthnd->bthmd", att, V) + V).reshape(B, T, -1)
+    o = F.linear(vals, P[a + "o_proj.weight"], P[a + "o_proj.bias"])
+    o = _drop(o, p_fusion, seed, FUSION_STREAM)
+    f = F.layer_norm(o, (o.shape[-1],), P["fusion.layers.norm1.weight"], P["fusion.layers.norm1.bias"], LN_EPS)
+    cat = torch.cat((enc[modalities[0]], f), dim=-1)
+    return F.linear(cat, P["regressor.weight"], P["regressor.bias"])
+
+
+def trainable_names(sd: SD) -> List[str]:
+    """Names of the head's trainable tensors in ``parameters()`` order: everything but spatial.*,
+    BatchNorm buffers and the duplicated net.{0,4}.* aliases of conv1/conv2."""
+    out = []
+    for k in sd:
+        if k.startswith("spatial.") or ".net." in k:
+            continue
+        if k.endswith("running_mean") or k.endswith("running_var") or k.endswith("num_batches_tracked"):
+            continue
+        out.append(k)
+    return out
+
+
+def train_step(sd: SD, feats: Dict[str, Tensor], labels: Tensor, modalities: Sequence[str], opt: dict,
+               opt_state: dict = None, seed=None, modal_dim: int = 32, num_heads: int = 2):
+    """One optimisation step as trainer.py:365-391 does it (fp32, no AMP): mean cross-entropy over
+    B*T frames (experiment.py:133), backward through the head only, one optimizer step.
+    opt = {'name': 'sgd'|'adam'|'adamw', 'lr', 'weight_decay', ('momentum','dampening','nesterov') |
+    ('beta1','beta2','eps')}; returns (loss, grads, new_sd, opt_state).  Optimizer arithmetic
+    follows torch.optim.{SGD,Adam,AdamW} (instantiators.py:60-100)."""
+    names = trainable_names(sd)
+    P = {k: sd[k].detach().clone().requires_grad_(True) for k in names}
+    buffers = {k: v.detach().clone() for k, v in sd.items() if k.startswith("bn.") and k not in P}
+    with torch.enable_grad():
+        logits = head_forward_train(P, buffers, {m: v.squeeze(1) if v.dim() == 4 else v for m, v in feats.items()},
+                                    modalities, modal_dim, num_heads, seed)
+        loss = F.cross_entropy(logits.reshape(-1, logits.shape[-1]), labels.reshape(-1).long())
+        grads = dict(zip(names, torch.autograd.grad(loss, [P[k] for k in names])))
+    st = opt_state if opt_state is not None else {"step": 0, "m": {}, "v": {}}
+    st["step"] += 1
+    t = st["step"]
+    new = {k: v.detach().clone() for k, v in sd.items()}
+    new.update(buffers)
+    lr, wd = opt["lr"], opt.get("weight_decay", 0.0)
+    for k in names:
+        p, g = P[k].detach(), grads[k]
+        if opt["name"] == "sgd":
+            mom, damp, nest = opt.get("momentum", 0.0), opt.get("dampening", 0.0), opt.get("nesterov", False)
+            g = g + wd * p
+            if mom != 0.0:
+                buf = g.clone() if k not in st["m"] else st["m"][k] * mom + (1 - damp) * g
+                st["m"][k] = buf
+                g = g + mom * buf if nest else buf
+            new[k] = p - lr * g
+        else:
+            b1, b2, eps = opt.get("beta1", 0.9), opt.get("beta2", 0.999), opt.get("eps", 1e-8)
+            if opt["name"] == "adamw":
+                p = p * (1 - lr * wd)
+            else:
+                g = g + wd * p
+            m = st["m"].get(k, torch.zeros_like(p)) * b1 + (1 - b1) * g
+            v = st["v"].get(k, torch.zeros_like(p)) * b2 + (1 - b2) * g * g
+            st["m"][k], st["v"][k] = m, v
+            denom = v.sqrt() / math.sqrt(1 - b2 ** t) + eps
+            new[k] = p - (lr / (1 - b1 ** t)) * m / denom
+    for k in list(new):            # keep the net.{0,4} aliases equal to conv1/conv2
+        if ".net.0." in k:
+            new[k] = new[k.replace(".net.0.", ".conv1.")]
+        elif ".net.4." in k:
+            new[k] = new[k.replace(".net.4.", ".conv2.")]
+    return loss.detach(), grads, new, st

@@ -104,3 +104,38 @@ def test_lfan_logmel_matches_reference(golden_dir):
          "bert": synthetic.feature_windows(1, T, seed=g["bert_seed"], modalities=["bert"])["bert"]}
     logits = O.lfan_forward(sd, X, mods)
     assert (logits - g["logits"]).abs().max().item() < 5e-5
+
+
+def test_train_step_matches_reference(golden_dir):
+    """Two SGD-nesterov steps of the head in training mode (BatchNorm1d batch statistics, Dropout
+    p = 0) -- loss, every gradient, BN running stats and updated parameters vs the reference."""
+    g = torch.load(os.path.join(golden_dir, "train_b2.pt"))
+    mods = g["modalities"]
+    sd = synthetic.lfan_state_dict(g["weights_seed"], mods)
+    X = synthetic.feature_windows(2, 300, seed=g["x_seed"], modalities=mods)
+    labels = torch.randint(0, 7, (2, 300, 1), generator=torch.Generator().manual_seed(g["label_seed"])).float()
+    st = None
+    for step in g["steps"]:
+        loss, grads, sd, st = O.train_step(sd, X, labels, mods, g["opt"], st)
+        assert abs(float(loss) - step["loss"]) < 2e-5
+        assert set(grads) == set(step["grad_norm"]) and len(grads) == 102
+        for k, gr in grads.items():
+            tol = 2e-4 * step["grad_norm"][k] + 1e-7
+            if k in step["grad_small"]:
+                assert (gr - step["grad_small"][k]).abs().max().item() <= tol, k
+            else:
+                assert (gr.flatten()[::997] - step["grad_sample"][k]).abs().max().item() <= tol, k
+            assert abs(float(gr.double().norm()) - step["grad_norm"][k]) <= 1e-3 * step["grad_norm"][k] + 1e-7, k
+        for k, v in step["bn"].items():
+            assert (sd[k].float() - v.float()).abs().max().item() < 1e-5, k
+        for k, v in step["param_sample"].items():
+            assert (sd[k].flatten()[::997] - v).abs().max().item() < 1e-5, k
+
+
+def test_dropout_mask_statistics_and_determinism():
+    m1 = O.dropout_keep_mask((600, 256), 0.1, seed=1234, stream=O.dropout_stream(1, 2, 0))
+    m2 = O.dropout_keep_mask((600, 256), 0.1, seed=1234, stream=O.dropout_stream(1, 2, 0))
+    m3 = O.dropout_keep_mask((600, 256), 0.1, seed=1234, stream=O.dropout_stream(1, 2, 1))
+    assert torch.equal(m1, m2) and not torch.equal(m1, m3)
+    assert abs(m1.mean().item() - 0.9) < 5e-3
+    assert abs((m1 * m3).mean().item() - 0.81) < 8e-3       # streams are independent
