@@ -53,6 +53,35 @@ class TcnBlock(C.Structure):
                 ("wd", C.c_void_p), ("bd", C.c_void_p), ("post_scale", C.c_void_p), ("post_shift", C.c_void_p)]
 
 
+CER_MAX_TCN_BLOCKS = 4
+_F = C.c_void_p
+
+
+class TrainConv(C.Structure):
+    _fields_ = [("g", _F), ("v", _F), ("bias", _F), ("dg", _F), ("dv", _F), ("dbias", _F)]
+
+
+class TrainBlock(C.Structure):
+    _fields_ = [("c_in", C.c_int32), ("c_out", C.c_int32), ("dilation", C.c_int32), ("reserved", C.c_int32),
+                ("conv1", TrainConv), ("conv2", TrainConv), ("wd", _F), ("bd", _F), ("dwd", _F), ("dbd", _F)]
+
+
+class TrainModal(C.Structure):
+    _fields_ = [("in_dim", C.c_int32), ("n_blocks", C.c_int32), ("blocks", TrainBlock * CER_MAX_TCN_BLOCKS),
+                ("bn_w", _F), ("bn_b", _F), ("dbn_w", _F), ("dbn_b", _F), ("bn_mean", _F), ("bn_var", _F),
+                ("wqkv", _F), ("bqkv", _F), ("dwqkv", _F), ("dbqkv", _F)]
+
+
+class HeadTrainSpec(C.Structure):
+    _fields_ = [("n_modals", C.c_int32), ("kernel_size", C.c_int32), ("modal_dim", C.c_int32), ("num_heads", C.c_int32),
+                ("n_out", C.c_int32), ("reserved", C.c_int32),
+                ("p_tcn", C.c_double), ("p_fusion", C.c_double), ("bn_momentum", C.c_double),
+                ("modal", TrainModal * CER_MAX_MODALS),
+                ("wo", _F), ("bo", _F), ("ln_g", _F), ("ln_b", _F), ("wr", _F), ("br", _F),
+                ("dwo", _F), ("dbo", _F), ("dln_g", _F), ("dln_b", _F), ("dwr", _F), ("dbr", _F),
+                ("grad_flat", _F), ("grad_count", C.c_int64)]
+
+
 class FusionWeights(C.Structure):
     _fields_ = [("n_modals", C.c_int32), ("dim", C.c_int32 * CER_MAX_MODALS),
                 ("modal_dim", C.c_int32), ("num_heads", C.c_int32), ("n_out", C.c_int32),
@@ -88,6 +117,15 @@ SIGNATURES = {
                                            C.c_void_p, C.c_size_t, C.c_void_p]),
     "cer_fusion_head_forward": (C.c_int, [C.POINTER(FusionWeights), C.POINTER(C.c_void_p), C.c_int64, C.c_void_p,
                                           C.c_void_p, C.c_void_p]),
+    "cer_head_train_workspace_bytes": (C.c_size_t, [C.POINTER(HeadTrainSpec), C.c_int64, C.c_int64]),
+    "cer_head_train_create": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(HeadTrainSpec), C.c_int64, C.c_int64, C.c_void_p,
+                                        C.c_size_t]),
+    "cer_head_train_forward": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_uint32, C.c_void_p, C.c_void_p]),
+    "cer_head_train_backward": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p]),
+    "cer_head_train_destroy": (None, [C.c_void_p]),
+    "cer_ce_loss": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "cer_optimizer_step": (C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_float,
+                                     C.c_float, C.c_float, C.c_float, C.c_float, C.c_int32, C.c_int32, C.c_float, C.c_void_p]),
     "cer_stitch_windows": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int64,
                                      C.c_void_p, C.c_void_p]),
 }

@@ -1,0 +1,1004 @@
+// Fusion-head training step (BASELINE config 4): forward in training mode, mean cross-entropy,
+// backward through TCN x M / BatchNorm1d / cross-modal attention / LayerNorm / classifier, and the
+// fused SGD / Adam / AdamW update.  C-ABI: cer_head_train_*, cer_ce_loss, cer_optimizer_step
+// (include/cer_b200.h).
+//
+// Reference semantics: trainer.py:365-391 (step), experiment.py:133 (CrossEntropyLoss mean),
+// models/model.py:511-526 under model.train(): Dropout after both LeakyReLUs of every
+// TemporalBlock (temporal_convolutional_model.py:28,34) and on the attention output
+// (transformer.py:194), BatchNorm1d with batch statistics + running-stat update (model.py:475,515),
+// weight_norm re-parameterisation w = g v/||v|| (temporal_convolutional_model.py:24,30).
+//
+// Everything here is exact fp32 (CUDA cores): the step is 30 MFLOP/frame, three orders of
+// magnitude below the IR-50 pass, and gradient parity with the reference at 1e-4 matters more than
+// tensor-core throughput.  All activations are time-major rows [R = B*T][C].
+//
+// The dropout masks come from a counter hash (dropout_keep) that oracle/lfan_oracle.py restates,
+// so forward AND backward are checkable element by element with dropout on.
+#include <cuda_runtime.h>
+#include <algorithm>
+#include <cstdint>
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "../../include/cer_b200.h"
+#include "common.h"
+
+namespace cer {
+
+constexpr float kLeaky = 0.01f;
+constexpr float kBnEps = 1e-5f;
+constexpr float kLnEps = 1e-5f;
+
+__host__ __device__ __forceinline__ uint32_t fmix32(uint32_t x) {
+  x ^= x >> 16; x *= 0x85EBCA6Bu; x ^= x >> 13; x *= 0xC2B2AE35u; x ^= x >> 16;
+  return x;
+}
+struct Drop {            // p == 0 <=> thr == 0 (everything kept, scale 1)
+  uint32_t key;          // seed + stream * 0x85EBCA6B
+  uint32_t thr;          // keep iff hash >= thr
+  float scale;           // 1 / (1 - p)
+};
+__device__ __forceinline__ float drop_factor(const Drop& d, uint32_t idx) {
+  if (d.thr == 0) return 1.f;
+  return fmix32(idx * 0x9E3779B1u + d.key) >= d.thr ? d.scale : 0.f;
+}
+__device__ __forceinline__ float lrelu(float x) { return x > 0.f ? x : x * kLeaky; }
+__device__ __forceinline__ float lrelu_grad(float saved) { return saved > 0.f ? 1.f : kLeaky; }
+
+// ------------------------------------------------------------------------------------------
+// Row GEMM with taps:  C[r, n] (+)= sum_j sum_k A[r + shift_j, k] * B_j(k, n)   (+ epilogue)
+//   rows are grouped in windows of T (one per batch element); a shifted row outside its window
+//   reads as zero (causal padding forward, anti-causal in dgrad).
+//   B_KN = false: B_j is [N][K] row-major (torch Linear / conv weight: forward);
+//   B_KN = true : B_j is [K][N] row-major (the same storage read transposed: dgrad).
+// 64x64 tile, BK = 16, 256 threads, 4x4 outputs per thread.
+// ------------------------------------------------------------------------------------------
+enum Epi { EPI_LINEAR = 0, EPI_LRELU_DROP = 1, EPI_BLOCK_OUT = 2, EPI_DGRAD_ACT = 3 };
+
+struct RowGemm {
+  const float* A; int lda;
+  const float* B; long long b_tap_stride;   // elements between consecutive taps' matrices
+  float* C; int ldc;
+  int R, T, N, K;
+  int taps, shift0, shift_step;             // shift_j = shift0 + j*shift_step (rows)
+  const float* bias;                        // [N] or null
+  const float* addend; int ld_add;          // [R][N] added before the activation, or null
+  int accumulate;                           // C += result (EPI_LINEAR only)
+  int epi;
+  float* aux; int ld_aux;                   // BLOCK_OUT: h2d out; DGRAD_ACT: saved activation in
+  Drop drop;
+};
+
+template <bool B_KN>
+__global__ void __launch_bounds__(256) row_gemm_kernel(const RowGemm g) {
+  __shared__ float As[16][64 + 4];
+  __shared__ float Bs[16][64 + 4];
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;          // 16 x 16 threads; thread -> rows ty*4.., cols tx*4..
+  const int row0 = blockIdx.y * 64, col0 = blockIdx.x * 64;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  // loader mapping: A tile 64 rows x 16 k -> thread loads 4 consecutive k of one row
+  const int a_r = tid >> 2, a_k = (tid & 3) * 4;
+  const int arow = row0 + a_r;
+  const int a_t = arow < g.R ? arow % g.T : 0;
+  for (int j = 0; j < g.taps; ++j) {
+    const int shift = g.shift0 + j * g.shift_step;
+    const bool a_ok = arow < g.R && (a_t + shift) >= 0 && (a_t + shift) < g.T;
+    const float* ap = g.A + (long long)(arow + shift) * g.lda;
+    const float* bp = g.B + j * g.b_tap_stride;
+    for (int k0 = 0; k0 < g.K; k0 += 16) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int k = k0 + a_k + q;
+        As[a_k + q][a_r] = (a_ok && k < g.K) ? __ldg(ap + k) : 0.f;
+      }
+      if (B_KN) {      // B[k][n]: thread loads 4 consecutive n of one k
+        const int b_k = tid >> 4, b_n = (tid & 15) * 4;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int k = k0 + b_k, n = col0 + b_n + q;
+          Bs[b_k][b_n + q] = (k < g.K && n < g.N) ? __ldg(bp + (long long)k * g.N + n) : 0.f;
+        }
+      } else {         // B[n][k]: thread loads 4 consecutive k of one n
+        const int b_n = tid >> 2, b_k = (tid & 3) * 4;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int k = k0 + b_k + q, n = col0 + b_n;
+          Bs[b_k + q][b_n] = (k < g.K && n < g.N) ? __ldg(bp + (long long)n * g.K + k) : 0.f;
+        }
+      }
+      __syncthreads();
+#pragma unroll
+      for (int kk = 0; kk < 16; ++kk) {
+        const float4 a = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+        const float4 b = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+        const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) acc[i][jj] = fmaf(av[i], bv[jj], acc[i][jj]);
+      }
+      __syncthreads();
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = row0 + ty * 4 + i;
+    if (r >= g.R) continue;
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) {
+      const int n = col0 + tx * 4 + jj;
+      if (n >= g.N) continue;
+      float v = acc[i][jj];
+      if (g.bias) v += __ldg(g.bias + n);
+      const uint32_t idx = (uint32_t)r * (uint32_t)g.N + (uint32_t)n;
+      float* cp = g.C + (long long)r * g.ldc + n;
+      if (g.epi == EPI_LINEAR) {
+        if (g.addend) v += g.addend[(long long)r * g.ld_add + n];
+        if (g.accumulate) v += *cp;
+        *cp = v;
+      } else if (g.epi == EPI_LRELU_DROP) {
+        *cp = lrelu(v) * drop_factor(g.drop, idx);
+      } else if (g.epi == EPI_BLOCK_OUT) {
+        const float h2d = lrelu(v) * drop_factor(g.drop, idx);
+        g.aux[(long long)r * g.ld_aux + n] = h2d;
+        *cp = lrelu(h2d + g.addend[(long long)r * g.ld_add + n]);
+      } else {   // EPI_DGRAD_ACT: gradient w.r.t. the pre-activation of a LReLU+dropout site
+        if (g.addend) v += g.addend[(long long)r * g.ld_add + n];
+        const float saved = g.aux[(long long)r * g.ld_aux + n];
+        *cp = v * drop_factor(g.drop, idx) * lrelu_grad(saved);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Weight gradient with taps:  dW_j[n][k] += sum_r G[r, n] * A[r + shift_j, k]
+// grid = (ceil(K/64) * taps, ceil(N/64), row splits); fp32 atomicAdd into a zeroed buffer.
+// ------------------------------------------------------------------------------------------
+struct WGrad {
+  const float* G; int ldg;
+  const float* A; int lda;
+  float* dW; long long w_tap_stride;
+  int R, T, N, K;
+  int taps, shift0, shift_step;
+  int k_tiles;
+  int rows_per_split;
+};
+
+__global__ void __launch_bounds__(256) wgrad_kernel(const WGrad g) {
+  __shared__ float Gs[16][64 + 4];
+  __shared__ float As[16][64 + 4];
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;          // thread -> n = ty*4.., k = tx*4..
+  const int j = blockIdx.x / g.k_tiles;
+  const int k0 = (blockIdx.x - j * g.k_tiles) * 64;
+  const int n0 = blockIdx.y * 64;
+  const int shift = g.shift0 + j * g.shift_step;
+  const int r_begin = blockIdx.z * g.rows_per_split;
+  const int r_end = min(g.R, r_begin + g.rows_per_split);
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) acc[i][q] = 0.f;
+  const int l_r = tid >> 4, l_c = (tid & 15) * 4;    // 16 rows x 64 cols per tile, 4 cols per thread
+  for (int r0 = r_begin; r0 < r_end; r0 += 16) {
+    const int r = r0 + l_r;
+    const bool r_ok = r < r_end;
+    const int t = r_ok ? r % g.T : 0;
+    const bool a_ok = r_ok && (t + shift) >= 0 && (t + shift) < g.T;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int n = n0 + l_c + q, k = k0 + l_c + q;
+      Gs[l_r][l_c + q] = (r_ok && n < g.N) ? __ldg(g.G + (long long)r * g.ldg + n) : 0.f;
+      As[l_r][l_c + q] = (a_ok && k < g.K) ? __ldg(g.A + (long long)(r + shift) * g.lda + k) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int rr = 0; rr < 16; ++rr) {
+      const float4 a = *reinterpret_cast<const float4*>(&Gs[rr][ty * 4]);
+      const float4 b = *reinterpret_cast<const float4*>(&As[rr][tx * 4]);
+      const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc[i][q] = fmaf(av[i], bv[q], acc[i][q]);
+    }
+    __syncthreads();
+  }
+  float* wp = g.dW + j * g.w_tap_stride;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int n = n0 + ty * 4 + i;
+    if (n >= g.N) continue;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int k = k0 + tx * 4 + q;
+      if (k < g.K) atomicAdd(wp + (long long)n * g.K + k, acc[i][q]);
+    }
+  }
+}
+
+// Column sums  out[n] += sum_r X[r, n] (bias gradients).  grid = (ceil(N/32), row splits), block 32x8.
+__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ X, int ldx, int R, int N,
+                                                     float* __restrict__ out, int rows_per_split) {
+  __shared__ float red[8][33];
+  const int n = blockIdx.x * 32 + threadIdx.x;
+  const int r_begin = blockIdx.y * rows_per_split, r_end = min(R, r_begin + rows_per_split);
+  float s = 0.f;
+  if (n < N)
+    for (int r = r_begin + threadIdx.y; r < r_end; r += 8) s += X[(long long)r * ldx + n];
+  red[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && n < N) {
+#pragma unroll
+    for (int i = 1; i < 8; ++i) s += red[i][threadIdx.x];
+    atomicAdd(out + n, s);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// weight_norm: W_eff[j][co][ci] = g[co] * v[co][ci][j] / ||v[co]||   (one block per co)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float block_sum(float v, float* red) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  __syncthreads();
+  if (l == 0) red[w] = v;
+  __syncthreads();
+  float s = 0.f;
+  for (int i = 0; i < (int)(blockDim.x >> 5); ++i) s += red[i];
+  return s;
+}
+
+__global__ void __launch_bounds__(256) wn_fwd_kernel(const float* __restrict__ gparam, const float* __restrict__ v,
+                                                     float* __restrict__ w_eff, float* __restrict__ inv_norm, int cout,
+                                                     int cin, int k) {
+  __shared__ float red[8];
+  const int co = blockIdx.x;
+  const int n = cin * k;
+  const float* vp = v + (long long)co * n;
+  float ss = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) ss += vp[i] * vp[i];
+  ss = block_sum(ss, red);
+  const float inv = 1.f / sqrtf(ss);
+  const float s = gparam[co] * inv;
+  if (threadIdx.x == 0) inv_norm[co] = inv;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int ci = i / k, j = i - ci * k;
+    w_eff[((long long)j * cout + co) * cin + ci] = s * vp[i];
+  }
+}
+
+// dg[co] = <dW, v>/||v||;  dv = g/||v|| * (dW - <dW, v>/||v||^2 * v)
+__global__ void __launch_bounds__(256) wn_bwd_kernel(const float* __restrict__ gparam, const float* __restrict__ v,
+                                                     const float* __restrict__ dw_eff, const float* __restrict__ inv_norm,
+                                                     float* __restrict__ dg, float* __restrict__ dv, int cout, int cin, int k) {
+  __shared__ float red[8];
+  const int co = blockIdx.x;
+  const int n = cin * k;
+  const float* vp = v + (long long)co * n;
+  float dot = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int ci = i / k, j = i - ci * k;
+    dot += dw_eff[((long long)j * cout + co) * cin + ci] * vp[i];
+  }
+  dot = block_sum(dot, red);
+  const float inv = inv_norm[co];
+  if (threadIdx.x == 0) dg[co] = dot * inv;
+  const float s = gparam[co] * inv, c = dot * inv * inv;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int ci = i / k, j = i - ci * k;
+    dv[(long long)co * n + i] = s * (dw_eff[((long long)j * cout + co) * cin + ci] - c * vp[i]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Block backward, first elementwise stage: from gy (grad of the block output y):
+//   gpre = gy * LReLU'(y)                       (grad of h2d + res; also the residual-branch grad)
+//   ga2  = gpre * drop2 * LReLU'(h2d)           (grad of conv2's pre-activation)
+// ------------------------------------------------------------------------------------------
+__global__ void block_bwd_pre_kernel(const float* __restrict__ gy, const float* __restrict__ y,
+                                     const float* __restrict__ h2d, float* __restrict__ gpre, float* __restrict__ ga2,
+                                     long long total, Drop drop) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const float gp = gy[i] * lrelu_grad(y[i]);
+    gpre[i] = gp;
+    ga2[i] = gp * drop_factor(drop, (uint32_t)i) * lrelu_grad(h2d[i]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// BatchNorm1d, training mode.  One block per 32 channels, 32x8 threads, three passes over the
+// (L2-resident) column slab: mean, centred variance, normalise.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) bn_train_fwd_kernel(const float* __restrict__ x, int ldx, int R, int C,
+                                                           const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                           float* __restrict__ z, int ldz, float* __restrict__ save_mean,
+                                                           float* __restrict__ save_invstd, float* __restrict__ run_mean,
+                                                           float* __restrict__ run_var, float momentum) {
+  __shared__ float red[8][33];
+  __shared__ float s_mean[32], s_inv[32];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  const bool ok = c < C;
+  float s = 0.f;
+  if (ok) for (int r = threadIdx.y; r < R; r += 8) s += x[(long long)r * ldx + c];
+  red[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0) {
+    for (int i = 1; i < 8; ++i) s += red[i][threadIdx.x];
+    s_mean[threadIdx.x] = s / R;
+  }
+  __syncthreads();
+  const float mean = s_mean[threadIdx.x];
+  float v = 0.f;
+  if (ok) for (int r = threadIdx.y; r < R; r += 8) { const float d = x[(long long)r * ldx + c] - mean; v += d * d; }
+  red[threadIdx.y][threadIdx.x] = v;
+  __syncthreads();
+  if (threadIdx.y == 0) {
+    for (int i = 1; i < 8; ++i) v += red[i][threadIdx.x];
+    const float var = v / R;
+    s_inv[threadIdx.x] = 1.f / sqrtf(var + kBnEps);
+    if (ok) {
+      save_mean[c] = mean;
+      save_invstd[c] = s_inv[threadIdx.x];
+      run_mean[c] = (1.f - momentum) * run_mean[c] + momentum * mean;
+      run_var[c] = (1.f - momentum) * run_var[c] + momentum * (R > 1 ? v / (R - 1) : var);
+    }
+  }
+  __syncthreads();
+  if (!ok) return;
+  const float inv = s_inv[threadIdx.x], ga = gamma[c], be = beta[c];
+  for (int r = threadIdx.y; r < R; r += 8) z[(long long)r * ldz + c] = (x[(long long)r * ldx + c] - mean) * inv * ga + be;
+}
+
+__global__ void __launch_bounds__(256) bn_train_bwd_kernel(const float* __restrict__ gz, int ldgz, const float* __restrict__ x,
+                                                           int ldx, int R, int C, const float* __restrict__ gamma,
+                                                           const float* __restrict__ save_mean,
+                                                           const float* __restrict__ save_invstd, float* __restrict__ gx,
+                                                           int ldgx, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  __shared__ float red[2][8][33];
+  __shared__ float s_sum[2][32];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  const bool ok = c < C;
+  const float mean = ok ? save_mean[c] : 0.f, inv = ok ? save_invstd[c] : 0.f;
+  float sb = 0.f, sg = 0.f;
+  if (ok)
+    for (int r = threadIdx.y; r < R; r += 8) {
+      const float g = gz[(long long)r * ldgz + c];
+      sb += g;
+      sg += g * (x[(long long)r * ldx + c] - mean) * inv;
+    }
+  red[0][threadIdx.y][threadIdx.x] = sb;
+  red[1][threadIdx.y][threadIdx.x] = sg;
+  __syncthreads();
+  if (threadIdx.y == 0) {
+    for (int i = 1; i < 8; ++i) { sb += red[0][i][threadIdx.x]; sg += red[1][i][threadIdx.x]; }
+    s_sum[0][threadIdx.x] = sb;
+    s_sum[1][threadIdx.x] = sg;
+    if (ok) { dbeta[c] = sb; dgamma[c] = sg; }
+  }
+  __syncthreads();
+  if (!ok) return;
+  sb = s_sum[0][threadIdx.x]; sg = s_sum[1][threadIdx.x];
+  const float k = gamma[c] * inv, invR = 1.f / R;
+  for (int r = threadIdx.y; r < R; r += 8) {
+    const float xh = (x[(long long)r * ldx + c] - mean) * inv;
+    gx[(long long)r * ldgx + c] = k * (gz[(long long)r * ldgz + c] - sb * invR - xh * sg * invR);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Cross-modal attention over the M modality tokens (transformer.py:132-161).  qkv[m]: [R][3*md],
+// per head h the slice [h*3*hd, (h+1)*3*hd) is q|k|v.  vals[r][(h*M + m)*hd + d].
+// One thread per (row, head); M <= 4, hd <= 32.
+// ------------------------------------------------------------------------------------------
+struct AttnArgs {
+  const float* qkv[CER_MAX_MODALS];
+  float* gqkv[CER_MAX_MODALS];
+  float* vals;          // fwd out [R][M*md]
+  const float* gvals;   // bwd in
+  int R, M, H, hd;
+};
+
+__device__ __forceinline__ void attn_probs(const AttnArgs& a, int r, int h, float att[CER_MAX_MODALS][CER_MAX_MODALS]) {
+  const int md3 = 3 * a.H * a.hd;
+  const float scale = rsqrtf((float)a.hd);
+  for (int m = 0; m < a.M; ++m) {
+    const float* q = a.qkv[m] + (long long)r * md3 + h * 3 * a.hd;
+    float mx = -1e30f;
+    for (int n = 0; n < a.M; ++n) {
+      const float* k = a.qkv[n] + (long long)r * md3 + h * 3 * a.hd + a.hd;
+      float s = 0.f;
+      for (int d = 0; d < a.hd; ++d) s = fmaf(q[d], k[d], s);
+      att[m][n] = s * scale;
+      mx = fmaxf(mx, att[m][n]);
+    }
+    float den = 0.f;
+    for (int n = 0; n < a.M; ++n) { att[m][n] = __expf(att[m][n] - mx); den += att[m][n]; }
+    const float inv = 1.f / den;
+    for (int n = 0; n < a.M; ++n) att[m][n] *= inv;
+  }
+}
+
+__global__ void attn_fwd_kernel(const AttnArgs a) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.R * a.H) return;
+  const int r = i / a.H, h = i - r * a.H;
+  const int md3 = 3 * a.H * a.hd, E = a.M * a.H * a.hd;
+  float att[CER_MAX_MODALS][CER_MAX_MODALS];
+  attn_probs(a, r, h, att);
+  for (int m = 0; m < a.M; ++m) {
+    float* o = a.vals + (long long)r * E + (h * a.M + m) * a.hd;
+    const float* vm = a.qkv[m] + (long long)r * md3 + h * 3 * a.hd + 2 * a.hd;
+    for (int d = 0; d < a.hd; ++d) {
+      float s = vm[d];                                     // "+ V" residual (transformer.py:157)
+      for (int n = 0; n < a.M; ++n) s = fmaf(att[m][n], a.qkv[n][(long long)r * md3 + h * 3 * a.hd + 2 * a.hd + d], s);
+      o[d] = s;
+    }
+  }
+}
+
+__global__ void attn_bwd_kernel(const AttnArgs a) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.R * a.H) return;
+  const int r = i / a.H, h = i - r * a.H;
+  const int md3 = 3 * a.H * a.hd, E = a.M * a.H * a.hd;
+  const float scale = rsqrtf((float)a.hd);
+  float att[CER_MAX_MODALS][CER_MAX_MODALS], gl[CER_MAX_MODALS][CER_MAX_MODALS];
+  attn_probs(a, r, h, att);
+  const long long base = (long long)r * md3 + h * 3 * a.hd;
+  for (int m = 0; m < a.M; ++m) {
+    const float* gv = a.gvals + (long long)r * E + (h * a.M + m) * a.hd;
+    float dotsum = 0.f;
+    for (int n = 0; n < a.M; ++n) {
+      const float* vn = a.qkv[n] + base + 2 * a.hd;
+      float s = 0.f;
+      for (int d = 0; d < a.hd; ++d) s = fmaf(gv[d], vn[d], s);
+      gl[m][n] = s;                       // d loss / d att[m][n]
+      dotsum = fmaf(att[m][n], s, dotsum);
+    }
+    for (int n = 0; n < a.M; ++n) gl[m][n] = att[m][n] * (gl[m][n] - dotsum) * scale;   // d loss / d (q.k)
+  }
+  for (int m = 0; m < a.M; ++m) {
+    float* gq = a.gqkv[m] + base;
+    float* gk = gq + a.hd;
+    float* gvv = gq + 2 * a.hd;
+    const float* gvm = a.gvals + (long long)r * E + (h * a.M + m) * a.hd;
+    for (int d = 0; d < a.hd; ++d) {
+      float sq = 0.f, sk = 0.f, sv = gvm[d];
+      for (int n = 0; n < a.M; ++n) {
+        sq = fmaf(gl[m][n], a.qkv[n][base + a.hd + d], sq);            // dq_m = sum_n gl[m][n] k_n
+        sk = fmaf(gl[n][m], a.qkv[n][base + d], sk);                   // dk_m = sum_n gl[n][m] q_n
+        sv = fmaf(att[n][m], a.gvals[(long long)r * E + (h * a.M + n) * a.hd + d], sv);   // dv_m = sum_n att[n][m] gvals_n + gvals_m
+      }
+      gq[d] = sq; gk[d] = sk; gvv[d] = sv;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Dropout + LayerNorm over E <= 128 features, one warp per row (transformer.py:194-196).
+// fwd: od = drop(o) (in place), f = LN(od) written with leading dimension ldf; saves mean, rstd.
+// bwd: gf (ld ldg) -> go = dLN * drop;  dgamma/dbeta via per-block smem partials + atomicAdd.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) ln_drop_fwd_kernel(float* __restrict__ o, int R, int E, const float* __restrict__ gamma,
+                                                          const float* __restrict__ beta, float* __restrict__ f, int ldf,
+                                                          float* __restrict__ save_mean, float* __restrict__ save_rstd,
+                                                          Drop drop) {
+  const int r = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (r >= R) return;
+  float v[4];
+  float s = 0.f;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int e = lane + 32 * q;
+    v[q] = 0.f;
+    if (e < E) {
+      v[q] = o[(long long)r * E + e] * drop_factor(drop, (uint32_t)r * (uint32_t)E + (uint32_t)e);
+      o[(long long)r * E + e] = v[q];
+      s += v[q];
+    }
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+  const float mean = s / E;
+  float ss = 0.f;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) if (lane + 32 * q < E) { const float d = v[q] - mean; ss += d * d; }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, off);
+  const float rstd = 1.f / sqrtf(ss / E + kLnEps);
+  if (lane == 0) { save_mean[r] = mean; save_rstd[r] = rstd; }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int e = lane + 32 * q;
+    if (e < E) f[(long long)r * ldf + e] = (v[q] - mean) * rstd * gamma[e] + beta[e];
+  }
+}
+
+__global__ void __launch_bounds__(256) ln_drop_bwd_kernel(const float* __restrict__ gf, int ldg, const float* __restrict__ od,
+                                                          int R, int E, const float* __restrict__ gamma,
+                                                          const float* __restrict__ save_mean, const float* __restrict__ save_rstd,
+                                                          float* __restrict__ go, float* __restrict__ dgamma,
+                                                          float* __restrict__ dbeta, Drop drop, int rows_per_block) {
+  __shared__ float s_dg[128], s_db[128];
+  if (threadIdx.x < 128) { s_dg[threadIdx.x] = 0.f; s_db[threadIdx.x] = 0.f; }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  float pdg[4] = {0.f, 0.f, 0.f, 0.f}, pdb[4] = {0.f, 0.f, 0.f, 0.f};
+  const int r_begin = blockIdx.x * rows_per_block, r_end = min(R, r_begin + rows_per_block);
+  for (int r = r_begin + w; r < r_end; r += 8) {
+    const float mean = save_mean[r], rstd = save_rstd[r];
+    float xh[4], gg[4];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int e = lane + 32 * q;
+      xh[q] = 0.f; gg[q] = 0.f;
+      if (e < E) {
+        const float g = gf[(long long)r * ldg + e];
+        xh[q] = (od[(long long)r * E + e] - mean) * rstd;
+        gg[q] = g * gamma[e];
+        pdg[q] += g * xh[q];
+        pdb[q] += g;
+        s1 += gg[q];
+        s2 += gg[q] * xh[q];
+      }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, off); s2 += __shfl_xor_sync(0xffffffffu, s2, off); }
+    s1 /= E; s2 /= E;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int e = lane + 32 * q;
+      if (e < E) go[(long long)r * E + e] = rstd * (gg[q] - s1 - xh[q] * s2) * drop_factor(drop, (uint32_t)r * (uint32_t)E + (uint32_t)e);
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int e = lane + 32 * q;
+    if (e < E) { atomicAdd(&s_dg[e], pdg[q]); atomicAdd(&s_db[e], pdb[q]); }
+  }
+  __syncthreads();
+  if (threadIdx.x < E) { atomicAdd(dgamma + threadIdx.x, s_dg[threadIdx.x]); atomicAdd(dbeta + threadIdx.x, s_db[threadIdx.x]); }
+}
+
+// Mean cross-entropy over rows + its gradient (experiment.py:133; trainer.py:372-381).
+__global__ void __launch_bounds__(256) ce_loss_kernel(const float* __restrict__ logits, const long long* __restrict__ labels,
+                                                      int R, int n_cls, float* __restrict__ loss, float* __restrict__ dlogits) {
+  __shared__ float red[8];
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  float l = 0.f;
+  if (r < R) {
+    const float* p = logits + (long long)r * n_cls;
+    float mx = p[0];
+    for (int c = 1; c < n_cls; ++c) mx = fmaxf(mx, p[c]);
+    float den = 0.f;
+    for (int c = 0; c < n_cls; ++c) den += expf(p[c] - mx);
+    const float lse = logf(den) + mx;
+    const int y = (int)labels[r];
+    const float invR = 1.f / R;
+    l = (lse - p[y]) * invR;
+    if (dlogits)
+      for (int c = 0; c < n_cls; ++c) dlogits[(long long)r * n_cls + c] = (expf(p[c] - lse) - (c == y ? 1.f : 0.f)) * invR;
+  }
+  l = block_sum(l, red);
+  if (threadIdx.x == 0) atomicAdd(loss, l);
+}
+
+// Fused optimizer update on a flat fp32 buffer (torch.optim.{SGD,Adam,AdamW} arithmetic;
+// instantiators.py:60-100).  kind 0: SGD(momentum, dampening, nesterov); 1: Adam; 2: AdamW.
+__global__ void optimizer_kernel(int kind, float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                 float* __restrict__ v, long long n, float lr, float wd, float b1, float b2, float eps,
+                                 int nesterov, int step, float bc1, float bc2_sqrt, float grad_scale) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float w = p[i], gr = g[i] * grad_scale;
+    if (kind == 0) {
+      gr = fmaf(wd, w, gr);
+      if (b1 != 0.f) {
+        const float buf = step == 1 ? gr : m[i] * b1 + (1.f - b2) * gr;      // b2 carries the dampening
+        m[i] = buf;
+        gr = nesterov ? gr + b1 * buf : buf;
+      }
+      p[i] = w - lr * gr;
+    } else {
+      if (kind == 2) w *= (1.f - lr * wd); else gr = fmaf(wd, w, gr);
+      const float mm = m[i] * b1 + (1.f - b1) * gr;
+      const float vv = v[i] * b2 + (1.f - b2) * gr * gr;
+      m[i] = mm; v[i] = vv;
+      const float denom = sqrtf(vv) / bc2_sqrt + eps;
+      p[i] = w - (lr / bc1) * mm / denom;
+    }
+  }
+}
+
+}  // namespace cer
+
+using namespace cer;
+
+// ==========================================================================================
+// Host side
+// ==========================================================================================
+namespace {
+
+struct ConvBuf {          // per weight-normed conv
+  float* w_eff;           // [k][cout][cin]
+  float* inv_norm;        // [cout]
+  float* dw_eff;          // [k][cout][cin] (zeroed per backward)
+};
+struct BlockBuf {
+  ConvBuf c1, c2;
+  float *h1d, *h2d, *y, *res;     // [R][cout]; res only with a downsample
+};
+struct ModalBuf {
+  std::vector<BlockBuf> blk;
+  float *bn_mean, *bn_invstd;     // [C]
+  float* z;                       // [R][C] (modality 0: inside `cat`, leading dimension ld_z)
+  int ld_z;
+  float *qkv, *gqkv;              // [R][3*md]
+};
+
+inline size_t align_up(size_t x) { return (x + 255) & ~size_t(255); }
+
+int launch_row_gemm(const RowGemm& g, bool b_kn, cudaStream_t st) {
+  dim3 grid((g.N + 63) / 64, (g.R + 63) / 64);
+  if (b_kn) row_gemm_kernel<true><<<grid, 256, 0, st>>>(g);
+  else row_gemm_kernel<false><<<grid, 256, 0, st>>>(g);
+  CER_CUDA(cudaGetLastError());
+  return CER_OK;
+}
+
+int launch_wgrad(WGrad g, int num_sms, cudaStream_t st) {
+  g.k_tiles = (g.K + 63) / 64;
+  const int tiles = g.k_tiles * g.taps * ((g.N + 63) / 64);
+  int splits = std::max(1, std::min((4 * num_sms + tiles - 1) / tiles, (g.R + 255) / 256));
+  g.rows_per_split = (((g.R + splits - 1) / splits) + 15) / 16 * 16;
+  splits = (g.R + g.rows_per_split - 1) / g.rows_per_split;
+  dim3 grid(g.k_tiles * g.taps, (g.N + 63) / 64, splits);
+  wgrad_kernel<<<grid, 256, 0, st>>>(g);
+  CER_CUDA(cudaGetLastError());
+  return CER_OK;
+}
+
+int launch_colsum(const float* X, int ldx, int R, int N, float* out, cudaStream_t st) {
+  const int splits = std::max(1, std::min(32, R / 256));
+  const int rps = (R + splits - 1) / splits;
+  dim3 grid((N + 31) / 32, (R + rps - 1) / rps), block(32, 8);
+  colsum_kernel<<<grid, block, 0, st>>>(X, ldx, R, N, out, rps);
+  CER_CUDA(cudaGetLastError());
+  return CER_OK;
+}
+
+Drop make_drop(double p, uint32_t seed, uint32_t stream) {
+  Drop d;
+  d.key = seed + stream * 0x85EBCA6Bu;
+  if (p <= 0.0) { d.thr = 0; d.scale = 1.f; return d; }
+  const double t = p * 4294967296.0;
+  d.thr = t >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)(long long)t;
+  d.scale = 1.0f / (1.0f - (float)p);
+  return d;
+}
+
+}  // namespace
+
+struct cer_head_train {
+  cer_head_train_spec s;
+  int B, T, R, E, md3, num_sms;
+  std::vector<ModalBuf> mod;
+  float *vals, *o, *ln_mean, *ln_rstd, *cat, *gcat, *go, *gvals;
+  float *ga, *gb, *gc, *gd;       // backward ping-pong [R][max C]
+  float* scratch_zero; size_t scratch_zero_bytes;    // all dw_eff buffers, zeroed per backward
+  uint32_t seed;                  // seed of the last forward (backward re-derives the masks)
+  int ld_cat;
+};
+
+static int spec_check(const cer_head_train_spec* s) {
+  if (!s || s->n_modals < 1 || s->n_modals > CER_MAX_MODALS || s->kernel_size < 1 || s->modal_dim % s->num_heads ||
+      s->modal_dim / s->num_heads > 32 || s->modal_dim * s->n_modals > 128 || s->n_out < 1 || !s->grad_flat)
+    return set_error(CER_ERR_INVALID, "cer_head_train: bad spec");
+  for (int m = 0; m < s->n_modals; ++m)
+    if (s->modal[m].n_blocks < 1 || s->modal[m].n_blocks > CER_MAX_TCN_BLOCKS) return set_error(CER_ERR_INVALID, "cer_head_train: n_blocks");
+  return CER_OK;
+}
+
+static size_t plan_layout(const cer_head_train_spec* s, int64_t B, int64_t T, cer_head_train* p, uint8_t* base) {
+  // walks the workspace; with p == nullptr only the size is computed
+  size_t off = 0;
+  auto take = [&](size_t floats) { float* q = base ? reinterpret_cast<float*>(base + off) : nullptr; off += align_up(floats * 4); return q; };
+  const size_t R = (size_t)B * T;
+  const int k = s->kernel_size;
+  const int E = s->modal_dim * s->n_modals, md3 = 3 * s->modal_dim;
+  const int c0 = s->modal[0].blocks[s->modal[0].n_blocks - 1].c_out;
+  int maxc = std::max(E, c0 + E);
+  // zeroed scratch first (contiguous)
+  size_t zero_begin = off;
+  std::vector<std::vector<std::pair<float*, float*>>> dws(s->n_modals);
+  for (int m = 0; m < s->n_modals; ++m)
+    for (int i = 0; i < s->modal[m].n_blocks; ++i) {
+      const cer_train_block& b = s->modal[m].blocks[i];
+      float* d1 = take((size_t)k * b.c_out * b.c_in);
+      float* d2 = take((size_t)k * b.c_out * b.c_out);
+      dws[m].push_back({d1, d2});
+      maxc = std::max(maxc, std::max(b.c_in, b.c_out));
+    }
+  size_t zero_end = off;
+  if (p) { p->scratch_zero = reinterpret_cast<float*>(base + zero_begin); p->scratch_zero_bytes = zero_end - zero_begin; }
+  float* cat = take(R * (c0 + E));
+  if (p) { p->cat = cat; p->ld_cat = c0 + E; p->mod.resize(s->n_modals); }
+  for (int m = 0; m < s->n_modals; ++m) {
+    ModalBuf mb;
+    for (int i = 0; i < s->modal[m].n_blocks; ++i) {
+      const cer_train_block& b = s->modal[m].blocks[i];
+      BlockBuf bb;
+      bb.c1.w_eff = take((size_t)k * b.c_out * b.c_in); bb.c1.inv_norm = take(b.c_out); bb.c1.dw_eff = dws[m][i].first;
+      bb.c2.w_eff = take((size_t)k * b.c_out * b.c_out); bb.c2.inv_norm = take(b.c_out); bb.c2.dw_eff = dws[m][i].second;
+      bb.h1d = take(R * b.c_out); bb.h2d = take(R * b.c_out); bb.y = take(R * b.c_out);
+      bb.res = b.wd ? take(R * b.c_out) : nullptr;
+      mb.blk.push_back(bb);
+    }
+    const int C = s->modal[m].blocks[s->modal[m].n_blocks - 1].c_out;
+    mb.bn_mean = take(C); mb.bn_invstd = take(C);
+    if (m == 0) { mb.z = cat; mb.ld_z = c0 + E; } else { mb.z = take(R * C); mb.ld_z = C; }
+    mb.qkv = take(R * md3); mb.gqkv = take(R * md3);
+    if (p) p->mod[m] = mb;
+  }
+  float* vals = take(R * E); float* o = take(R * E); float* lm = take(R); float* lr = take(R);
+  float* gcat = take(R * (c0 + E)); float* go = take(R * E); float* gvals = take(R * E);
+  float* ga = take(R * maxc); float* gb = take(R * maxc); float* gc = take(R * maxc); float* gd = take(R * maxc);
+  if (p) { p->vals = vals; p->o = o; p->ln_mean = lm; p->ln_rstd = lr; p->gcat = gcat; p->go = go; p->gvals = gvals;
+           p->ga = ga; p->gb = gb; p->gc = gc; p->gd = gd; }
+  return off + 256;
+}
+
+extern "C" size_t cer_head_train_workspace_bytes(const cer_head_train_spec* s, int64_t batch, int64_t length) {
+  if (spec_check(s) || batch <= 0 || length <= 0) return 0;
+  return plan_layout(s, batch, length, nullptr, nullptr);
+}
+
+extern "C" int cer_head_train_create(cer_head_train** out, const cer_head_train_spec* s, int64_t batch, int64_t length,
+                                     void* workspace_dev, size_t workspace_bytes) {
+  int rc = spec_check(s);
+  if (rc) return rc;
+  if (!out || !workspace_dev || batch <= 0 || length <= 0 || batch * length > (1 << 22))
+    return set_error(CER_ERR_INVALID, "cer_head_train_create: bad argument");
+  rc = cer_check_device();
+  if (rc) return rc;
+  if (workspace_bytes < plan_layout(s, batch, length, nullptr, nullptr)) return set_error(CER_ERR_WORKSPACE, "cer_head_train_create: workspace too small");
+  cer_head_train* p = new cer_head_train();
+  p->s = *s;
+  p->B = (int)batch; p->T = (int)length; p->R = (int)(batch * length);
+  p->E = s->modal_dim * s->n_modals; p->md3 = 3 * s->modal_dim;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&p->num_sms, cudaDevAttrMultiProcessorCount, dev);
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(workspace_dev) + 255) & ~uintptr_t(255));
+  plan_layout(s, batch, length, p, base);
+  p->seed = 0;
+  *out = p;
+  return CER_OK;
+}
+
+extern "C" void cer_head_train_destroy(cer_head_train* p) { delete p; }
+
+#define RC(x) do { int _rc = (x); if (_rc) return _rc; } while (0)
+
+extern "C" int cer_head_train_forward(cer_head_train* p, const float* const* feats, uint32_t seed, float* logits, void* stream) {
+  if (!p || !feats || !logits) return set_error(CER_ERR_INVALID, "cer_head_train_forward: bad argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const cer_head_train_spec& s = p->s;
+  const int R = p->R, T = p->T, k = s.kernel_size;
+  p->seed = seed;
+  for (int m = 0; m < s.n_modals; ++m) {
+    const cer_train_modal& M = s.modal[m];
+    ModalBuf& mb = p->mod[m];
+    const float* x = feats[m];
+    if (!x) return set_error(CER_ERR_INVALID, "cer_head_train_forward: null feature pointer");
+    for (int i = 0; i < M.n_blocks; ++i) {
+      const cer_train_block& b = M.blocks[i];
+      BlockBuf& bb = mb.blk[i];
+      wn_fwd_kernel<<<b.c_out, 256, 0, st>>>(b.conv1.g, b.conv1.v, bb.c1.w_eff, bb.c1.inv_norm, b.c_out, b.c_in, k);
+      wn_fwd_kernel<<<b.c_out, 256, 0, st>>>(b.conv2.g, b.conv2.v, bb.c2.w_eff, bb.c2.inv_norm, b.c_out, b.c_out, k);
+      CER_CUDA(cudaGetLastError());
+      RowGemm g{};
+      g.R = R; g.T = T; g.taps = k; g.shift0 = -(k - 1) * b.dilation; g.shift_step = b.dilation;
+      // conv1: h1d = drop(LReLU(conv1(x) + b1))
+      g.A = x; g.lda = b.c_in; g.K = b.c_in; g.B = bb.c1.w_eff; g.b_tap_stride = (long long)b.c_out * b.c_in;
+      g.C = bb.h1d; g.ldc = b.c_out; g.N = b.c_out; g.bias = b.conv1.bias; g.epi = EPI_LRELU_DROP;
+      g.drop = make_drop(s.p_tcn, seed, m * 16 + i * 2 + 0);
+      RC(launch_row_gemm(g, false, st));
+      // residual branch
+      const float* res = x; int ld_res = b.c_in;
+      if (b.wd) {
+        RowGemm d{};
+        d.R = R; d.T = T; d.taps = 1; d.A = x; d.lda = b.c_in; d.K = b.c_in; d.B = b.wd; d.C = bb.res; d.ldc = b.c_out;
+        d.N = b.c_out; d.bias = b.bd; d.epi = EPI_LINEAR;
+        RC(launch_row_gemm(d, false, st));
+        res = bb.res; ld_res = b.c_out;
+      }
+      // conv2: h2d = drop(LReLU(conv2(h1d) + b2)); y = LReLU(h2d + res)
+      g.A = bb.h1d; g.lda = b.c_out; g.K = b.c_out; g.B = bb.c2.w_eff; g.b_tap_stride = (long long)b.c_out * b.c_out;
+      g.C = bb.y; g.bias = b.conv2.bias; g.epi = EPI_BLOCK_OUT; g.aux = bb.h2d; g.ld_aux = b.c_out;
+      g.addend = res; g.ld_add = ld_res;
+      g.drop = make_drop(s.p_tcn, seed, m * 16 + i * 2 + 1);
+      RC(launch_row_gemm(g, false, st));
+      x = bb.y;
+    }
+    const int C = M.blocks[M.n_blocks - 1].c_out;
+    bn_train_fwd_kernel<<<(C + 31) / 32, dim3(32, 8), 0, st>>>(x, C, R, C, M.bn_w, M.bn_b, mb.z, mb.ld_z, mb.bn_mean,
+                                                                mb.bn_invstd, M.bn_mean, M.bn_var, (float)s.bn_momentum);
+    CER_CUDA(cudaGetLastError());
+    RowGemm q{};
+    q.R = R; q.T = T; q.taps = 1; q.A = mb.z; q.lda = mb.ld_z; q.K = C; q.B = M.wqkv; q.C = mb.qkv; q.ldc = p->md3;
+    q.N = p->md3; q.bias = M.bqkv; q.epi = EPI_LINEAR;
+    RC(launch_row_gemm(q, false, st));
+  }
+  AttnArgs a{};
+  for (int m = 0; m < s.n_modals; ++m) a.qkv[m] = p->mod[m].qkv;
+  a.vals = p->vals; a.R = R; a.M = s.n_modals; a.H = s.num_heads; a.hd = s.modal_dim / s.num_heads;
+  attn_fwd_kernel<<<(R * a.H + 127) / 128, 128, 0, st>>>(a);
+  CER_CUDA(cudaGetLastError());
+  const int E = p->E, c0 = p->ld_cat - E;
+  RowGemm o{};
+  o.R = R; o.T = T; o.taps = 1; o.A = p->vals; o.lda = E; o.K = E; o.B = s.wo; o.C = p->o; o.ldc = E; o.N = E; o.bias = s.bo;
+  o.epi = EPI_LINEAR;
+  RC(launch_row_gemm(o, false, st));
+  ln_drop_fwd_kernel<<<(R + 7) / 8, 256, 0, st>>>(p->o, R, E, s.ln_g, s.ln_b, p->cat + c0, p->ld_cat, p->ln_mean, p->ln_rstd,
+                                                  make_drop(s.p_fusion, seed, 4096));
+  CER_CUDA(cudaGetLastError());
+  RowGemm r{};
+  r.R = R; r.T = T; r.taps = 1; r.A = p->cat; r.lda = p->ld_cat; r.K = p->ld_cat; r.B = s.wr; r.C = logits; r.ldc = s.n_out;
+  r.N = s.n_out; r.bias = s.br; r.epi = EPI_LINEAR;
+  RC(launch_row_gemm(r, false, st));
+  return CER_OK;
+}
+
+extern "C" int cer_head_train_backward(cer_head_train* p, const float* const* feats, const float* dlogits, void* stream) {
+  if (!p || !feats || !dlogits) return set_error(CER_ERR_INVALID, "cer_head_train_backward: bad argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const cer_head_train_spec& s = p->s;
+  const int R = p->R, T = p->T, k = s.kernel_size, E = p->E, c0 = p->ld_cat - E, sms = p->num_sms;
+  const uint32_t seed = p->seed;
+  CER_CUDA(cudaMemsetAsync(s.grad_flat, 0, (size_t)s.grad_count * 4, st));
+  CER_CUDA(cudaMemsetAsync(p->scratch_zero, 0, p->scratch_zero_bytes, st));
+
+  // classifier: logits = cat Wr^T + br
+  { WGrad w{}; w.G = dlogits; w.ldg = s.n_out; w.A = p->cat; w.lda = p->ld_cat; w.dW = s.dwr; w.R = R; w.T = T; w.N = s.n_out;
+    w.K = p->ld_cat; w.taps = 1; RC(launch_wgrad(w, sms, st)); }
+  RC(launch_colsum(dlogits, s.n_out, R, s.n_out, s.dbr, st));
+  { RowGemm g{}; g.R = R; g.T = T; g.taps = 1; g.A = dlogits; g.lda = s.n_out; g.K = s.n_out; g.B = s.wr; g.C = p->gcat;
+    g.ldc = p->ld_cat; g.N = p->ld_cat; g.epi = EPI_LINEAR; RC(launch_row_gemm(g, true, st)); }
+  // LayerNorm + dropout
+  { const int rpb = std::max(8, (R + 4 * sms - 1) / (4 * sms));
+    ln_drop_bwd_kernel<<<(R + rpb - 1) / rpb, 256, 0, st>>>(p->gcat + c0, p->ld_cat, p->o, R, E, s.ln_g, p->ln_mean, p->ln_rstd,
+                                                             p->go, s.dln_g, s.dln_b, make_drop(s.p_fusion, seed, 4096), rpb);
+    CER_CUDA(cudaGetLastError()); }
+  // o_proj
+  { WGrad w{}; w.G = p->go; w.ldg = E; w.A = p->vals; w.lda = E; w.dW = s.dwo; w.R = R; w.T = T; w.N = E; w.K = E; w.taps = 1;
+    RC(launch_wgrad(w, sms, st)); }
+  RC(launch_colsum(p->go, E, R, E, s.dbo, st));
+  { RowGemm g{}; g.R = R; g.T = T; g.taps = 1; g.A = p->go; g.lda = E; g.K = E; g.B = s.wo; g.C = p->gvals; g.ldc = E; g.N = E;
+    g.epi = EPI_LINEAR; RC(launch_row_gemm(g, true, st)); }
+  // attention
+  { AttnArgs a{};
+    for (int m = 0; m < s.n_modals; ++m) { a.qkv[m] = p->mod[m].qkv; a.gqkv[m] = p->mod[m].gqkv; }
+    a.gvals = p->gvals; a.R = R; a.M = s.n_modals; a.H = s.num_heads; a.hd = s.modal_dim / s.num_heads;
+    attn_bwd_kernel<<<(R * a.H + 127) / 128, 128, 0, st>>>(a);
+    CER_CUDA(cudaGetLastError()); }
+
+  for (int m = 0; m < s.n_modals; ++m) {
+    const cer_train_modal& M = s.modal[m];
+    ModalBuf& mb = p->mod[m];
+    const int C = M.blocks[M.n_blocks - 1].c_out;
+    // qkv projection
+    { WGrad w{}; w.G = mb.gqkv; w.ldg = p->md3; w.A = mb.z; w.lda = mb.ld_z; w.dW = M.dwqkv; w.R = R; w.T = T; w.N = p->md3;
+      w.K = C; w.taps = 1; RC(launch_wgrad(w, sms, st)); }
+    RC(launch_colsum(mb.gqkv, p->md3, R, p->md3, M.dbqkv, st));
+    float* gz = p->ga;        // [R][C]
+    { RowGemm g{}; g.R = R; g.T = T; g.taps = 1; g.A = mb.gqkv; g.lda = p->md3; g.K = p->md3; g.B = M.wqkv; g.C = gz; g.ldc = C;
+      g.N = C; g.epi = EPI_LINEAR;
+      if (m == 0) { g.addend = p->gcat; g.ld_add = p->ld_cat; }        // the leader also feeds the classifier directly
+      RC(launch_row_gemm(g, true, st)); }
+    // BatchNorm1d
+    float* gy = p->gb;
+    bn_train_bwd_kernel<<<(C + 31) / 32, dim3(32, 8), 0, st>>>(gz, C, mb.blk[M.n_blocks - 1].y, C, R, C, M.bn_w, mb.bn_mean,
+                                                                mb.bn_invstd, gy, C, M.dbn_w, M.dbn_b);
+    CER_CUDA(cudaGetLastError());
+    float* spare = p->ga;     // gz is dead from here on
+    for (int i = M.n_blocks - 1; i >= 0; --i) {
+      const cer_train_block& b = M.blocks[i];
+      BlockBuf& bb = mb.blk[i];
+      const float* x = i == 0 ? feats[m] : mb.blk[i - 1].y;
+      float* gpre = p->gc;
+      float* ga2 = p->gd;
+      const long long tot = (long long)R * b.c_out;
+      block_bwd_pre_kernel<<<(int)std::min<long long>((tot + 255) / 256, 8LL * sms), 256, 0, st>>>(
+          gy, bb.y, bb.h2d, gpre, ga2, tot, make_drop(s.p_tcn, seed, m * 16 + i * 2 + 1));
+      CER_CUDA(cudaGetLastError());
+      // conv2: bias, weight, input gradients
+      RC(launch_colsum(ga2, b.c_out, R, b.c_out, b.conv2.dbias, st));
+      { WGrad w{}; w.G = ga2; w.ldg = b.c_out; w.A = bb.h1d; w.lda = b.c_out; w.dW = bb.c2.dw_eff;
+        w.w_tap_stride = (long long)b.c_out * b.c_out; w.R = R; w.T = T; w.N = b.c_out; w.K = b.c_out; w.taps = k;
+        w.shift0 = -(k - 1) * b.dilation; w.shift_step = b.dilation; RC(launch_wgrad(w, sms, st)); }
+      wn_bwd_kernel<<<b.c_out, 256, 0, st>>>(b.conv2.g, b.conv2.v, bb.c2.dw_eff, bb.c2.inv_norm, b.conv2.dg, b.conv2.dv,
+                                             b.c_out, b.c_out, k);
+      CER_CUDA(cudaGetLastError());
+      float* ga1 = gy;         // gy is dead once gpre/ga2 exist
+      { RowGemm g{}; g.R = R; g.T = T; g.taps = k; g.shift0 = (k - 1) * b.dilation; g.shift_step = -b.dilation;
+        g.A = ga2; g.lda = b.c_out; g.K = b.c_out; g.B = bb.c2.w_eff; g.b_tap_stride = (long long)b.c_out * b.c_out;
+        g.C = ga1; g.ldc = b.c_out; g.N = b.c_out; g.epi = EPI_DGRAD_ACT; g.aux = bb.h1d; g.ld_aux = b.c_out;
+        g.drop = make_drop(s.p_tcn, seed, m * 16 + i * 2 + 0);
+        RC(launch_row_gemm(g, true, st)); }
+      // conv1: bias, weight gradients
+      RC(launch_colsum(ga1, b.c_out, R, b.c_out, b.conv1.dbias, st));
+      { WGrad w{}; w.G = ga1; w.ldg = b.c_out; w.A = x; w.lda = b.c_in; w.dW = bb.c1.dw_eff;
+        w.w_tap_stride = (long long)b.c_out * b.c_in; w.R = R; w.T = T; w.N = b.c_out; w.K = b.c_in; w.taps = k;
+        w.shift0 = -(k - 1) * b.dilation; w.shift_step = b.dilation; RC(launch_wgrad(w, sms, st)); }
+      wn_bwd_kernel<<<b.c_out, 256, 0, st>>>(b.conv1.g, b.conv1.v, bb.c1.dw_eff, bb.c1.inv_norm, b.conv1.dg, b.conv1.dv,
+                                             b.c_out, b.c_in, k);
+      CER_CUDA(cudaGetLastError());
+      // downsample parameters
+      if (b.wd) {
+        RC(launch_colsum(gpre, b.c_out, R, b.c_out, b.dbd, st));
+        WGrad w{}; w.G = gpre; w.ldg = b.c_out; w.A = x; w.lda = b.c_in; w.dW = b.dwd; w.R = R; w.T = T; w.N = b.c_out;
+        w.K = b.c_in; w.taps = 1; RC(launch_wgrad(w, sms, st));
+      }
+      if (i == 0) break;       // the input features need no gradient
+      // gx = dgrad(conv1)(ga1) + residual-branch gradient
+      float* gx = spare;
+      { RowGemm g{}; g.R = R; g.T = T; g.taps = k; g.shift0 = (k - 1) * b.dilation; g.shift_step = -b.dilation;
+        g.A = ga1; g.lda = b.c_out; g.K = b.c_out; g.B = bb.c1.w_eff; g.b_tap_stride = (long long)b.c_out * b.c_in;
+        g.C = gx; g.ldc = b.c_in; g.N = b.c_in; g.epi = EPI_LINEAR;
+        if (!b.wd) { g.addend = gpre; g.ld_add = b.c_out; }
+        RC(launch_row_gemm(g, true, st)); }
+      if (b.wd) {
+        RowGemm g{}; g.R = R; g.T = T; g.taps = 1; g.A = gpre; g.lda = b.c_out; g.K = b.c_out; g.B = b.wd; g.C = gx; g.ldc = b.c_in;
+        g.N = b.c_in; g.epi = EPI_LINEAR; g.accumulate = 1;
+        RC(launch_row_gemm(g, true, st));
+      }
+      spare = gy;              // ga1's buffer is free again after the next block's pre-stage reads gx
+      gy = gx;
+    }
+  }
+  return CER_OK;
+}
+
+extern "C" int cer_ce_loss(const float* logits, const int64_t* labels, int64_t rows, int32_t n_cls, float* loss_out,
+                           float* dlogits_out, void* stream) {
+  if (!logits || !labels || !loss_out || rows <= 0 || n_cls <= 0 || rows > (1 << 30))
+    return set_error(CER_ERR_INVALID, "cer_ce_loss: bad argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CER_CUDA(cudaMemsetAsync(loss_out, 0, 4, st));
+  ce_loss_kernel<<<(int)((rows + 255) / 256), 256, 0, st>>>(logits, reinterpret_cast<const long long*>(labels), (int)rows, n_cls,
+                                                            loss_out, dlogits_out);
+  CER_CUDA(cudaGetLastError());
+  return CER_OK;
+}
+
+extern "C" int cer_optimizer_step(int32_t kind, float* params, const float* grads, float* state_m, float* state_v, int64_t n,
+                                  float lr, float weight_decay, float beta1_or_momentum, float beta2_or_dampening, float eps,
+                                  int32_t nesterov, int32_t step, float grad_scale, void* stream) {
+  if (!params || !grads || n <= 0 || kind < 0 || kind > 2 || step < 1) return set_error(CER_ERR_INVALID, "cer_optimizer_step: bad argument");
+  if ((kind == 0 && beta1_or_momentum != 0.f && !state_m) || (kind > 0 && (!state_m || !state_v)))
+    return set_error(CER_ERR_INVALID, "cer_optimizer_step: missing optimizer state");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  float bc1 = 1.f, bc2s = 1.f;
+  if (kind > 0) {
+    bc1 = (float)(1.0 - pow((double)beta1_or_momentum, (double)step));
+    bc2s = (float)sqrt(1.0 - pow((double)beta2_or_dampening, (double)step));
+  }
+  const int blocks = (int)std::min<int64_t>((n + 255) / 256, 148 * 16);
+  optimizer_kernel<<<blocks, 256, 0, st>>>(kind, params, grads, state_m, state_v, (long long)n, lr, weight_decay,
+                                           beta1_or_momentum, beta2_or_dampening, eps, nesterov, step, bc1, bc2s, grad_scale);
+  CER_CUDA(cudaGetLastError());
+  return CER_OK;
+}

@@ -8,8 +8,9 @@ the modules drop in under experiment.py:298-315 / trainer.py:368,485,852.
 The torch sub-modules declared here are PARAMETER CONTAINERS ONLY (they pin names and shapes);
 none of their ``forward`` methods is ever called.  ``forward`` of the mirrors packs the weights
 once (packing.py), keeps them resident on the GPU and calls the sm_100a kernels through the
-C-ABI (engine.py).  Inference only: the kernels have no backward, so a forward in training
-mode with grad enabled raises instead of silently running something else.
+C-ABI (engine.py).  The sub-modules are inference-only (a forward in training mode with grad
+enabled raises instead of silently running something else); LFAN.forward in training mode runs
+the head's training plan (training.py, csrc/train.cu) and is attached to autograd.
 """
 from __future__ import annotations
 
@@ -516,8 +517,29 @@ class LFAN(_PackedModule):
         logits = fus.forward([e.view(B * T, -1) for e in enc])
         return logits.view(B, T, -1)
 
+    def _training_forward(self, X):
+        """model.train() + grad enabled (trainer.py:365-391): the frozen backbones run their
+        inference kernels under no_grad (the CUDA kernels fold BatchNorm, i.e. the backbones stay in
+        eval mode -- the reference would switch IR-50's BatchNorms to batch statistics under
+        model.train(); train from pre-extracted features for step-for-step parity), the head runs
+        the training plan and is attached to autograd."""
+        from . import training
+        with torch.no_grad():
+            if 'video' in X:
+                X['video'] = self.encode_frames(X['video']).unsqueeze(1)
+            if 'logmel' in X:
+                X['logmel'] = self.encode_logmel(X['logmel']).unsqueeze(1)
+        feats = {m: X[m].squeeze(1) for m in self.modality}
+        out = training.forward_with_grad(self, feats)
+        for m in X:
+            X[m] = feats.get(m, X[m])
+        if self.task == "REGRESSION":
+            out = torch.tanh(out)
+        return out
+
     def forward(self, X):
-        self._check_inference()
+        if self.training and torch.is_grad_enabled():
+            return self._training_forward(X)
         if 'video' in X:
             X['video'] = self.encode_frames(X['video']).unsqueeze(1)
         if 'logmel' in X:

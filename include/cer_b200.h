@@ -197,6 +197,74 @@ int cer_fusion_head_forward(const cer_fusion_weights* w, const float* const* fea
                             float* logits_dev, float* fused_out_dev /* [rows][E] or NULL */, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Fusion-head training step (BASELINE config 4).   Replaces, for the trainable head of LFAN
+ * (TCN x M, BatchNorm1d, cross-modal attention, LayerNorm, classifier), the forward in
+ * training mode + loss + backward + optimizer step of trainer.py:365-391 / experiment.py:133 /
+ * instantiators.py:60-100.  Exact fp32.  Parameters are read in the reference's own layouts
+ * (weight_g [cout], weight_v [cout][cin][k], Linear weight [out][in]); gradients are written in
+ * the same layouts.  All gradient pointers must lie inside one flat buffer [grad_flat,
+ * grad_flat + grad_count) (zeroed by backward; one NCCL all-reduce covers it).
+ * Dropout masks come from a counter hash of (seed, site, element) that oracle/lfan_oracle.py
+ * restates; p_tcn = p_fusion = 0 disables dropout.
+ * ------------------------------------------------------------------------------------------ */
+#define CER_MAX_TCN_BLOCKS 4
+typedef struct cer_train_conv {
+  const float *g, *v, *bias;        /* weight_g [cout], weight_v [cout][cin][k], bias [cout]       */
+  float *dg, *dv, *dbias;
+} cer_train_conv;
+
+typedef struct cer_train_block {
+  int32_t c_in, c_out, dilation, reserved;
+  cer_train_conv conv1, conv2;
+  const float *wd, *bd;             /* downsample.weight [cout][cin] / bias, NULL when c_in == c_out */
+  float *dwd, *dbd;
+} cer_train_block;
+
+typedef struct cer_train_modal {
+  int32_t in_dim, n_blocks;
+  cer_train_block blocks[CER_MAX_TCN_BLOCKS];
+  const float *bn_w, *bn_b;         /* bn.<m>.weight / bias                                          */
+  float *dbn_w, *dbn_b;
+  float *bn_mean, *bn_var;          /* running statistics, updated in place by forward               */
+  const float *wqkv, *bqkv;         /* qkv_proj.<m>.weight [3*modal_dim][c_last], bias               */
+  float *dwqkv, *dbqkv;
+} cer_train_modal;
+
+typedef struct cer_head_train_spec {
+  int32_t n_modals, kernel_size, modal_dim, num_heads, n_out, reserved;
+  double p_tcn, p_fusion, bn_momentum;   /* 0.1, 0.1, 0.1 in the reference (model.py:471,482)        */
+  cer_train_modal modal[CER_MAX_MODALS]; /* modality 0 is the leader                                 */
+  const float *wo, *bo, *ln_g, *ln_b, *wr, *br;
+  float *dwo, *dbo, *dln_g, *dln_b, *dwr, *dbr;
+  float* grad_flat;
+  int64_t grad_count;
+} cer_head_train_spec;
+
+typedef struct cer_head_train cer_head_train;
+
+size_t cer_head_train_workspace_bytes(const cer_head_train_spec* spec, int64_t batch, int64_t length);
+int cer_head_train_create(cer_head_train** out, const cer_head_train_spec* spec, int64_t batch, int64_t length,
+                          void* workspace_dev, size_t workspace_bytes);
+/* feats_dev[m]: fp32 [batch*length][in_dim[m]] time-major rows; logits_dev: fp32 [batch*length][n_out].
+ * Saves the activations backward needs in the workspace and updates the BatchNorm running stats. */
+int cer_head_train_forward(cer_head_train* plan, const float* const* feats_dev, uint32_t seed, float* logits_dev, void* stream);
+/* dlogits_dev: fp32 [batch*length][n_out] = d loss / d logits; writes every gradient of the spec. */
+int cer_head_train_backward(cer_head_train* plan, const float* const* feats_dev, const float* dlogits_dev, void* stream);
+void cer_head_train_destroy(cer_head_train* plan);
+
+/* Mean cross-entropy over `rows` rows and (optionally) its gradient w.r.t. the logits
+ * (nn.CrossEntropyLoss(reduction="mean"), experiment.py:133).  labels: int64 [rows]. */
+int cer_ce_loss(const float* logits_dev, const int64_t* labels_dev, int64_t rows, int32_t n_cls, float* loss_out_dev,
+                float* dlogits_out_dev /* or NULL */, void* stream);
+
+/* Fused optimizer update over a flat fp32 buffer.  kind 0: SGD (beta1 = momentum, beta2 = dampening,
+ * nesterov), 1: Adam, 2: AdamW -- torch.optim arithmetic (instantiators.py:60-100).  step counts
+ * from 1.  grads are multiplied by grad_scale first (1/world_size after a sum all-reduce). */
+int cer_optimizer_step(int32_t kind, float* params_dev, const float* grads_dev, float* state_m_dev, float* state_v_dev,
+                       int64_t n, float lr, float weight_decay, float beta1_or_momentum, float beta2_or_dampening, float eps,
+                       int32_t nesterov, int32_t step, float grad_scale, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Window stitching.   Replaces the sum / overlap-count / divide of
  * Trainer.inference_forward_windows (trainer.py:864-890) on device.
  * win_logits: fp32 [n_windows][win_len][n_out]; win_start: int32 [n_windows] first frame of each

@@ -82,10 +82,26 @@ def test_forward_fails_loudly_without_gpu():
             m(X)
 
 
-def test_training_mode_is_rejected_not_silently_wrong():
+def test_training_mode_never_falls_back():
+    """LFAN in training mode goes to the CUDA training plan (CerError without a GPU); the
+    inference-only sub-modules refuse a training-mode forward instead of computing something else."""
     m = _lfan(["cnn_res50", "vggish", "bert"]).train()
+    if not torch.cuda.is_available():
+        with pytest.raises(_capi.CerError), torch.enable_grad():
+            m(synthetic.feature_windows(1, 300))
     with pytest.raises(NotImplementedError), torch.enable_grad():
-        m(synthetic.feature_windows(1, 300))
+        m.temporal["vggish"](torch.randn(1, 128, 300))
+
+
+def test_head_parameter_order_matches_oracle_and_flat_layout():
+    from feature_vs_text_compound_emotion_b200 import training
+    from oracle import lfan_oracle as O
+    mods = ["cnn_res50", "vggish", "bert"]
+    m = _lfan(mods)
+    names = [k for k, _ in training.head_parameters(m)]
+    assert names == O.trainable_names(synthetic.lfan_state_dict(0, mods))
+    assert sum(p.numel() for _, p in training.head_parameters(m)) == 5002503
+    assert ctypes.sizeof(_capi.TrainConv) == 48 and ctypes.sizeof(_capi.TrainBlock) == 16 + 2 * 48 + 32
 
 
 def test_capi_exports_every_declared_symbol():

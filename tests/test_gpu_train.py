@@ -1,0 +1,188 @@
+"""GPU parity of the fusion-head training step (BASELINE config 4) -- forward in training mode,
+cross-entropy, backward, optimizer -- against the reference-generated golden (Dropout p = 0) and
+against the oracle with this repo's dropout masks.  Tolerances: fp32 kernels vs fp32 CPU autograd,
+gradients within 2e-4 of each tensor's norm, loss within 2e-5."""
+import os
+import warnings
+
+import pytest
+import torch
+
+from feature_vs_text_compound_emotion_b200 import synthetic
+from oracle import lfan_oracle as O
+
+pytestmark = pytest.mark.gpu
+warnings.filterwarnings("ignore")
+BS = {"visual_state_dict": "res50_ir_0.887", "audio_state_dict": "vggish"}
+MODS = ["cnn_res50", "vggish", "bert"]
+
+
+def _dev():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    return torch.device("cuda:0")
+
+
+def _lfan(mods, dev, seed=0, length=300, p_drop=None):
+    from feature_vs_text_compound_emotion_b200.models.model import LFAN
+    m = LFAN(backbone_settings=BS, output_dim=7, task="CLASSIFICATION", modality=mods, kernel_size=5,
+             example_length=length, tcn_channel=synthetic.TCN_CHANNELS, modal_dim=32, num_heads=2, root_dir="",
+             device=dev)
+    m.init()
+    m.load_state_dict(synthetic.lfan_state_dict(seed, mods), strict=True)
+    m = m.to(dev).train()
+    if p_drop is not None:
+        for mod in m.modules():
+            if isinstance(mod, torch.nn.Dropout):
+                mod.p = p_drop
+    return m
+
+
+def _check_grads(tr, grads, rel=2e-4):
+    worst = 0.0
+    for k, g in grads.items():
+        mine = tr.grad(k).cpu()
+        tol = rel * float(g.double().norm()) + 1e-7
+        err = (mine - g).abs().max().item()
+        assert err <= tol, (k, err, tol)
+        worst = max(worst, err / tol)
+    return worst
+
+
+def test_two_sgd_steps_vs_reference_golden(golden_dir):
+    from feature_vs_text_compound_emotion_b200.training import HeadTrainer
+    dev = _dev()
+    g = torch.load(os.path.join(golden_dir, "train_b2.pt"))
+    mods = g["modalities"]
+    m = _lfan(mods, dev, g["weights_seed"], p_drop=0.0)
+    tr = HeadTrainer(m, 2, 300, optimizer=g["opt"])
+    X = {k: v.to(dev) for k, v in synthetic.feature_windows(2, 300, seed=g["x_seed"], modalities=mods).items()}
+    labels = torch.randint(0, 7, (2, 300, 1), generator=torch.Generator().manual_seed(g["label_seed"])).float().to(dev)
+    for step in g["steps"]:
+        loss = tr.step(X, labels)
+        assert abs(loss.item() - step["loss"]) < 2e-5
+        for k, gn in step["grad_norm"].items():
+            mine = tr.grad(k).cpu()
+            tol = 2e-4 * gn + 1e-7
+            ref = step["grad_small"][k] if k in step["grad_small"] else step["grad_sample"][k]
+            got = mine if k in step["grad_small"] else mine.flatten()[::997]
+            assert (got - ref).abs().max().item() <= tol, k
+            assert abs(float(mine.double().norm()) - gn) <= 1e-3 * gn + 1e-7, k
+        sd = m.state_dict()
+        for k, v in step["bn"].items():
+            assert (sd[k].cpu().float() - v.float()).abs().max().item() < 1e-5, k
+        for k, v in step["param_sample"].items():
+            assert (sd[k].cpu().flatten()[::997] - v).abs().max().item() < 1e-5, k
+
+
+def test_dropout_forward_backward_vs_oracle():
+    """Dropout ON (p = 0.1 as model.py:471,482): the kernels' counter-hash masks are restated by
+    the oracle, so logits, loss and every gradient are compared element by element."""
+    from feature_vs_text_compound_emotion_b200.training import HeadTrainer
+    dev = _dev()
+    m = _lfan(MODS, dev, seed=3)
+    tr = HeadTrainer(m, 2, 300)
+    sd = synthetic.lfan_state_dict(3, MODS)
+    X = synthetic.feature_windows(2, 300, seed=21, modalities=MODS)
+    labels = torch.randint(0, 7, (2, 300, 1), generator=torch.Generator().manual_seed(22)).float()
+    seed = 0xC0FFEE
+    logits = tr.forward({k: v.to(dev) for k, v in X.items()}, seed=seed)
+    loss, dl = tr.cross_entropy(logits, labels.to(dev))
+    tr.backward(dl)
+    P = {k: sd[k] for k in O.trainable_names(sd)}
+    buffers = {k: v.clone() for k, v in sd.items() if k.startswith("bn.") and k not in P}
+    want = O.head_forward_train(P, buffers, {k: v.squeeze(1) for k, v in X.items()}, MODS, seed=seed)
+    assert (logits.cpu() - want).abs().max().item() < 2e-4
+    ref_loss, grads, _, _ = O.train_step(sd, X, labels, MODS, {"name": "sgd", "lr": 0.0}, None, seed=seed)
+    assert abs(loss.item() - float(ref_loss)) < 2e-5
+    _check_grads(tr, grads)
+    # a different seed draws different masks
+    logits2 = tr.forward({k: v.to(dev) for k, v in X.items()}, seed=seed + 1)
+    assert (logits2 - logits).abs().max().item() > 1e-3
+
+
+@pytest.mark.parametrize("name,cfg", [
+    ("adamw", {"name": "adamw", "lr": 1e-3, "weight_decay": 1e-2}),
+    ("adam", {"name": "adam", "lr": 1e-3, "weight_decay": 1e-4}),
+    ("sgd_plain", {"name": "sgd", "lr": 5e-2, "momentum": 0.0, "weight_decay": 0.0}),
+])
+def test_optimizers_vs_oracle(name, cfg):
+    from feature_vs_text_compound_emotion_b200.training import HeadTrainer
+    dev = _dev()
+    mods = ["vggish", "bert"]          # a two-modality head: E = 64, leader width 32
+    m = _lfan(mods, dev, seed=1, length=120, p_drop=0.0)
+    tr = HeadTrainer(m, 3, 120, optimizer=cfg)
+    sd = synthetic.lfan_state_dict(1, mods)
+    X = synthetic.feature_windows(3, 120, seed=31, modalities=mods)
+    labels = torch.randint(0, 7, (3, 120, 1), generator=torch.Generator().manual_seed(32)).float()
+    st = None
+    for it in range(2):
+        loss = tr.step({k: v.to(dev) for k, v in X.items()}, labels.to(dev))
+        before = sd
+        ref_loss, grads, sd, st = O.train_step(sd, X, labels, mods, cfg, st)
+        if it == 0:
+            assert abs(loss.item() - float(ref_loss)) < 2e-5
+            _check_grads(tr, grads)
+        cur = m.state_dict()
+        for k, g in grads.items():
+            err = (cur[k].cpu() - sd[k]).abs()
+            if cfg["name"] != "sgd_plain" and it == 0:
+                # Adam's first update is lr*sign(g): elements whose gradient is round-off noise may flip
+                # (the update is g/(|g|+eps): a relative gradient error e moves it by about lr*e)
+                noise = g.abs() <= 1e-3 * g.abs().max()
+                err = torch.where(noise, torch.zeros_like(err), err)
+            if it == 0:
+                tol = 2e-5 if cfg["name"] == "sgd_plain" else 0.1 * cfg["lr"]
+                assert err.max().item() <= tol, (k, err.max().item())
+        del before
+
+
+def test_autograd_bridge_matches_trainer_and_torch_optim_steps():
+    """The reference's loop shape: out = model(X); loss = criterion(out, y); loss.backward(); opt.step()."""
+    dev = _dev()
+    m = _lfan(MODS, dev, seed=2, p_drop=0.0)
+    sd = synthetic.lfan_state_dict(2, MODS)
+    X = synthetic.feature_windows(2, 300, seed=41, modalities=MODS)
+    labels = torch.randint(0, 7, (2, 300, 1), generator=torch.Generator().manual_seed(42)).float()
+    params = [p for p in m.parameters() if p.requires_grad]
+    with torch.enable_grad():
+        out = m({k: v.to(dev) for k, v in X.items()})
+        assert out.requires_grad and out.shape == (2, 300, 7)
+        loss = torch.nn.functional.cross_entropy(out.view(600, 7), labels.view(600).long().to(dev))
+        loss.backward()
+    ref_loss, grads, new_sd, _ = O.train_step(sd, X, labels, MODS, {"name": "sgd", "lr": 1e-2, "momentum": 0.9, "nesterov": True,
+                                                                    "weight_decay": 1e-4}, None)
+    assert abs(loss.item() - float(ref_loss)) < 2e-5
+    named = dict(m.named_parameters())
+    for k, g in grads.items():
+        assert named[k].grad is not None, k
+        assert (named[k].grad.cpu() - g).abs().max().item() <= 5e-4 * float(g.norm()) + 1e-7, k
+    opt = torch.optim.SGD(params, lr=1e-2, momentum=0.9, nesterov=True, weight_decay=1e-4)
+    opt.step()
+    cur = m.state_dict()
+    for k in grads:
+        assert (cur[k].cpu() - new_sd[k]).abs().max().item() < 1e-5, k
+    # eval after training uses the updated weights (engines are re-packed)
+    m.eval()
+    with torch.no_grad():
+        ev = m({k: v.to(dev) for k, v in X.items()}).cpu()
+    want = O.lfan_forward({**new_sd}, X, MODS)
+    assert (ev - want).abs().max().item() <= 2e-2
+
+
+def test_ce_loss_and_optimizer_entry_points():
+    from feature_vs_text_compound_emotion_b200 import _capi
+    dev = _dev()
+    g = torch.Generator().manual_seed(5)
+    logits = torch.randn(1000, 7, generator=g) * 3
+    labels = torch.randint(0, 7, (1000,), generator=g)
+    ref = torch.nn.functional.cross_entropy(logits, labels)
+    lg = logits.clone().requires_grad_(True)
+    torch.nn.functional.cross_entropy(lg, labels).backward()
+    ld, yd = logits.to(dev), labels.to(dev)
+    loss = torch.empty(1, device=dev)
+    dl = torch.empty_like(ld)
+    _capi.check(_capi.lib().cer_ce_loss(ld.data_ptr(), yd.data_ptr(), 1000, 7, loss.data_ptr(), dl.data_ptr(),
+                                        _capi.current_stream_ptr()))
+    assert abs(loss.item() - ref.item()) < 1e-5
+    assert (dl.cpu() - lg.grad).abs().max().item() < 1e-7
