@@ -269,6 +269,46 @@ class FusionEngine:
         return (logits, fused) if want_fused else logits
 
 
+class PreprocEngine:
+    """The reference's eval video transform on the device (cer_preproc_*): uint8 [N,H,W,3] stored
+    crops -> fp32 [N,3,crop,crop] in [-1,1], bit-exact with PIL resize + crop + normalise."""
+
+    def __init__(self, in_h: int, in_w: int, device: torch.device, resize: int = 48, crop: int = 40):
+        _capi.require_gpu()
+        self.device = torch.device(device)
+        self.in_h, self.in_w, self.crop = int(in_h), int(in_w), int(crop)
+        with torch.cuda.device(self.device):
+            nbytes = lib().cer_preproc_workspace_bytes()
+            self._ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+            h = C.c_void_p()
+            check(lib().cer_preproc_create(C.byref(h), self.in_h, self.in_w, resize, crop, self._ws.data_ptr(), nbytes),
+                  "cer_preproc_create")
+        self._h = h
+
+    def forward(self, frames: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        if frames.dim() != 4 or tuple(frames.shape[1:]) != (self.in_h, self.in_w, 3) or frames.dtype != torch.uint8:
+            raise ValueError(f"expected uint8 [N,{self.in_h},{self.in_w},3], got {frames.dtype} {tuple(frames.shape)}")
+        if frames.device != self.device:
+            raise ValueError("frames must be on the engine's CUDA device")
+        frames = frames.contiguous()
+        n = frames.shape[0]
+        if out is None:
+            out = torch.empty(n, 3, self.crop, self.crop, dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            check(lib().cer_preproc_forward(self._h, frames.data_ptr(), n, out.data_ptr(), _capi.current_stream_ptr()),
+                  "cer_preproc_forward")
+        return out
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            try:
+                lib().cer_preproc_destroy(h)
+            except Exception:
+                pass
+            self._h = None
+
+
 def stitch_windows(win_logits: torch.Tensor, win_start: torch.Tensor, length: int) -> torch.Tensor:
     """win_logits [n_win, win_len, n_out] fp32, win_start int32 [n_win] -> [length, n_out] mean over
     the windows covering each frame (trainer.py:864-890)."""

@@ -212,3 +212,18 @@ def feature_windows(batch: int, length: int = 300, seed: int = 1234,
             x = torch.nn.functional.normalize(x, dim=-1)
         out[m] = x
     return out
+
+
+def raw_frames_u8(n: int, seed: int = 1234, h: int = 256, w: int = 256) -> torch.Tensor:
+    """Stored aligned face crops as the reference keeps them on disk: uint8 [n, h, w, 3]
+    (video.npy, abaw5_pre_processing/project/abaw5/configs.py:20,236).  Low-frequency content plus
+    noise, so that the antialiased resize has structure to preserve."""
+    g = torch.Generator().manual_seed(seed)
+    yy = torch.arange(h, dtype=torch.float32).view(1, h, 1, 1)
+    xx = torch.arange(w, dtype=torch.float32).view(1, 1, w, 1)
+    ph = torch.rand(n, 1, 1, 3, generator=g) * 6.28
+    fy = (torch.rand(n, 1, 1, 3, generator=g) * 3 + 1) * 6.28 / h
+    fx = (torch.rand(n, 1, 1, 3, generator=g) * 3 + 1) * 6.28 / w
+    base = 127.5 + 80 * torch.sin(yy * fy + xx * fx + ph)
+    noise = torch.randint(-40, 41, (n, h, w, 3), generator=g).float()
+    return (base + noise).clamp(0, 255).to(torch.uint8)

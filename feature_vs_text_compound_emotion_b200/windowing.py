@@ -36,21 +36,57 @@ def gather_windows(feat: torch.Tensor, starts: Sequence[int], window_length: int
     return feat[idx]
 
 
+def preprocess_frames(model, frames_u8: torch.Tensor, resize: int = 48, crop: int = 40) -> torch.Tensor:
+    """uint8 [T,H,W,3] on the GPU -> fp32 [T,3,crop,crop]; the plan is cached on the model per input size."""
+    from .engine import PreprocEngine
+    cache = model.__dict__.setdefault("_preproc", {})
+    key = (int(frames_u8.shape[1]), int(frames_u8.shape[2]), resize, crop, str(frames_u8.device))
+    if key not in cache:
+        cache[key] = PreprocEngine(key[0], key[1], frames_u8.device, resize, crop)
+    return cache[key].forward(frames_u8)
+
+
+def video_level_prediction(frame_logits: torch.Tensor, ignore_last_class: bool = False) -> Dict[str, int]:
+    """The three video-level decision rules of metrics.py:88-145 (format_trg_pred_video) on
+    per-frame logits [T, n_cls]: FRAMES_VOTE (majority of per-frame argmax; ties go to the class
+    that appears first, as Counter.most_common does), FRAMES_AVG_LOGITS, FRAMES_AVG_PROBS.
+    ``ignore_last_class`` drops the 'Other' class first (C-EXPR-DB, metrics.py:118-119)."""
+    lg = frame_logits[:, :-1] if ignore_last_class else frame_logits
+    n_cls = lg.shape[-1]
+    pred = lg.argmax(-1)
+    votes = torch.bincount(pred, minlength=n_cls)
+    first = torch.full((n_cls,), pred.numel(), dtype=torch.long, device=pred.device)
+    first.scatter_reduce_(0, pred, torch.arange(pred.numel(), device=pred.device), reduce="amin")
+    best = votes.max()
+    cand = torch.where(votes == best, first, torch.full_like(first, pred.numel() + 1))
+    return {"FRAMES_VOTE": int(cand.argmin()),
+            "FRAMES_AVG_LOGITS": int(lg.mean(0).argmax()),
+            "FRAMES_AVG_PROBS": int(torch.softmax(lg, -1).mean(0).argmax())}
+
+
 @torch.no_grad()
 def infer_video(model, video: torch.Tensor, feats: Dict[str, torch.Tensor], window_length: int = 300,
                 hop_length: int = 200) -> torch.Tensor:
     """One whole video through the LFAN mirror.
 
-    video: [T,3,40,40] fp32 on the GPU (post eval-transform), feats[m]: [T, D_m] for the
-    non-visual modalities.  Returns per-frame logits [T, n_out] = the reference's stitched output.
+    video: [T,3,40,40] fp32 on the GPU (post eval-transform) or the stored uint8 [T,H,W,3] crops
+    (then base/dataset.py:503-510 runs on the device, engine.PreprocEngine); feats[m]: [T, D_m] for
+    the non-visual modalities ('logmel': [T,96,64] examples, encoded by the VGGish kernels).  Returns per-frame logits [T, n_out] = the reference's stitched output.
     """
     from .engine import stitch_windows
     T = video.shape[0]
+    if video.dtype == torch.uint8:                             # stored crops: the eval transform runs on the device
+        video = preprocess_frames(model, video)
     emb = model.spatial["visual"](video)                       # every unique frame once
     starts = window_starts(T, window_length, hop_length)
     batch = {}
     for m in model.modality:
-        src = emb if m == "video" else feats[m]
+        if m == "video":
+            src = emb
+        elif m == "logmel":
+            src = model.spatial["audio"](feats[m])              # one example per frame (audio.py:126-127)
+        else:
+            src = feats[m]
         batch[m] = gather_windows(src, starts, window_length).contiguous()
     logits = model.forward_features(batch)                     # [n_windows, window_length, n_out]
     start_t = torch.as_tensor(starts, dtype=torch.int32, device=video.device)

@@ -265,6 +265,22 @@ int cer_optimizer_step(int32_t kind, float* params_dev, const float* grads_dev, 
                        int32_t nesterov, int32_t step, float grad_scale, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Eval-time input pipeline.   Replaces the video transform of base/dataset.py:503-510
+ * (GroupNumpyToPILImage -> GroupScale(48) -> GroupCenterCrop(40) -> Stack -> ToTorchFormatTensor
+ * -> GroupNormalize(.5,.5); base/transforms3D.py:15-144) including Pillow's antialiased 8-bit
+ * BILINEAR resize, bit-exactly, for the crop window only.
+ * frames_dev: uint8 [n][in_h][in_w][3] as stored (video.npy); out_dev: fp32 [n][3][crop][crop].
+ * cer_preproc_create copies its coefficient tables into workspace_dev (cer_preproc_workspace_bytes
+ * bytes, caller-owned, must outlive the plan) with a synchronous cudaMemcpy.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct cer_preproc cer_preproc;
+size_t cer_preproc_workspace_bytes(void);
+int cer_preproc_create(cer_preproc** out, int32_t in_h, int32_t in_w, int32_t resize, int32_t crop, void* workspace_dev,
+                       size_t workspace_bytes);
+int cer_preproc_forward(cer_preproc* plan, const uint8_t* frames_dev, int64_t n_frames, float* out_dev, void* stream);
+void cer_preproc_destroy(cer_preproc* plan);
+
+/* ------------------------------------------------------------------------------------------
  * Window stitching.   Replaces the sum / overlap-count / divide of
  * Trainer.inference_forward_windows (trainer.py:864-890) on device.
  * win_logits: fp32 [n_windows][win_len][n_out]; win_start: int32 [n_windows] first frame of each

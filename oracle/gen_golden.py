@@ -12,6 +12,7 @@ reference modules, imported as they are, are the source of truth):
   * vggish_n6.pt    -- VGGish forward on 6 synthetic log-mel examples (+ its 18 state_dict keys)
   * lfan_logmel_b1.pt -- LFAN(video,logmel,bert) forward from pixels and log-mel, B=1 x T=40
   * train_b2.pt     -- two SGD-nesterov steps of the head in train mode (Dropout p=0): loss, gradients, BN stats
+  * eval_transform.pt -- the reference's eval transform classes (PIL resize 48, crop 40, normalise) on seeded uint8 frames
   * windowing.json  -- Trainer.windowing outputs for a set of lengths
 Weights are NOT stored: they are regenerated from the seed by
 feature_vs_text_compound_emotion_b200.synthetic (identical on every machine), and are loaded
@@ -169,6 +170,21 @@ def main():
             print("train step", it, float(loss), len(grads), "grads")
     torch.save(rec, os.path.join(OUT, "train_b2.pt"))
     torch.set_grad_enabled(False)
+
+    # ---- eval input transform (base/dataset.py:503-510) through the reference's own classes ----
+    import torchvision.transforms as TT
+    from base.transforms3D import (GroupCenterCrop, GroupNormalize, GroupNumpyToPILImage, GroupScale, Stack,
+                                   ToTorchFormatTensor)
+    tr = TT.Compose([GroupNumpyToPILImage(use_inverse=False), GroupScale(48), GroupCenterCrop(40), Stack(),
+                     ToTorchFormatTensor(), GroupNormalize([0.5, 0.5, 0.5], [0.5, 0.5, 0.5])])
+    cases = {}
+    for name, (n, hh, ww, sd_) in {"256": (3, 256, 256, 501), "112": (2, 112, 112, 502), "64x80": (2, 64, 80, 503),
+                                   "40": (1, 40, 40, 504)}.items():
+        raw = synthetic.raw_frames_u8(n, seed=sd_, h=hh, w=ww)
+        cases[name] = {"n": n, "h": hh, "w": ww, "seed": sd_, "out": tr(raw.numpy())}
+    import PIL
+    torch.save({"cases": cases, "pillow": PIL.__version__}, os.path.join(OUT, "eval_transform.pt"))
+    print("eval transform", {k: tuple(v["out"].shape) for k, v in cases.items()}, "Pillow", PIL.__version__)
 
     # ---- windowing (trainer.py imports pynvml/munch, absent here: exec the one function) ----
     src = open(os.path.join(REF, "trainer.py")).read()

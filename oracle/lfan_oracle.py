@@ -420,3 +420,93 @@ def train_step(sd: SD, feats: Dict[str, Tensor], labels: Tensor, modalities: Seq
         elif ".net.4." in k:
             new[k] = new[k.replace(".net.4.", ".conv2.")]
     return loss.detach(), grads, new, st
+
+
+# --------------------------------------------------------------------------------------
+# Eval-time input pipeline (base/dataset.py:503-510, base/transforms3D.py:15-144)
+#   GroupNumpyToPILImage -> GroupScale(48) -> GroupCenterCrop(40) -> Stack ->
+#   ToTorchFormatTensor (/255) -> GroupNormalize(mean .5, std .5)
+# The resize is PIL's antialiased two-pass BILINEAR on uint8 (third-party: Pillow, un-pinned in the
+# reference's environment; restated from its published algorithm -- libImaging/Resample.c:
+# precompute_coeffs / normalize_coeffs_8bpc / ImagingResampleHorizontal_8bpc / Vertical_8bpc --
+# and pinned bit-exactly against the Pillow installed in the build container, tests/golden/).
+# --------------------------------------------------------------------------------------
+PIL_PRECISION_BITS = 32 - 8 - 2
+
+
+def pil_bilinear_coeffs(in_size: int, out_size: int):
+    """precompute_coeffs + normalize_coeffs_8bpc for the triangle filter (support 1.0) over the
+    whole axis.  Returns (bounds[out,2] = (xmin, count), kk[out, ksize] int32 fixed point)."""
+    scale = float(in_size) / out_size
+    filterscale = max(scale, 1.0)
+    support = 1.0 * filterscale
+    ksize = int(math.ceil(support)) * 2 + 1
+    bounds = np.zeros((out_size, 2), dtype=np.int32)
+    kk = np.zeros((out_size, ksize), dtype=np.int32)
+    ss = 1.0 / filterscale
+    for xx in range(out_size):
+        center = (xx + 0.5) * scale
+        xmin = max(int(center - support + 0.5), 0)
+        xmax = min(int(center + support + 0.5), in_size) - xmin
+        w = np.array([max(0.0, 1.0 - abs((x + xmin - center + 0.5) * ss)) for x in range(xmax)], dtype=np.float64)
+        ww = 0.0
+        for v in w:                       # sequential sum, as the C loop does
+            ww += float(v)
+        if ww != 0.0:
+            w = w / ww
+        for x in range(xmax):
+            p = float(w[x]) * (1 << PIL_PRECISION_BITS)
+            kk[xx, x] = int(-0.5 + p) if w[x] < 0 else int(0.5 + p)
+        bounds[xx] = (xmin, xmax)
+    return bounds, kk
+
+
+def _pil_resample_axis(img: np.ndarray, out_size: int, axis: int) -> np.ndarray:
+    """One 8bpc pass: out = clip8((2^(P-1) + sum pixel*kk) >> P) along ``axis`` of uint8 [H,W,C]."""
+    bounds, kk = pil_bilinear_coeffs(img.shape[axis], out_size)
+    src = np.moveaxis(img, axis, 0).astype(np.int64)
+    out = np.empty((out_size,) + src.shape[1:], dtype=np.uint8)
+    for xx in range(out_size):
+        xmin, cnt = bounds[xx]
+        acc = (1 << (PIL_PRECISION_BITS - 1)) + np.tensordot(kk[xx, :cnt].astype(np.int64), src[xmin:xmin + cnt], axes=(0, 0))
+        out[xx] = np.clip(acc >> PIL_PRECISION_BITS, 0, 255).astype(np.uint8)
+    return np.moveaxis(out, 0, axis)
+
+
+def pil_resize_bilinear_u8(img: np.ndarray, out_h: int, out_w: int) -> np.ndarray:
+    """PIL.Image.resize((out_w, out_h), BILINEAR) on a uint8 [H,W,C] image: horizontal pass first,
+    rounded to uint8, then the vertical pass (ImagingResample)."""
+    tmp = _pil_resample_axis(img, out_w, 1) if out_w != img.shape[1] else img
+    return _pil_resample_axis(tmp, out_h, 0) if out_h != img.shape[0] else tmp
+
+
+def scaled_size(h: int, w: int, size: int):
+    """torchvision.transforms.Resize(int): the smaller edge becomes ``size`` (GroupScale,
+    base/transforms3D.py:103-117)."""
+    if w <= h:
+        return int(size * h / w), size
+    return size, int(size * w / h)
+
+
+def eval_transform(frames_u8: np.ndarray, size: int = 48, crop: int = 40) -> Tensor:
+    """base/dataset.py:503-510 on uint8 [T,H,W,3] -> fp32 [T,3,crop,crop] in [-1,1]."""
+    out = []
+    for f in frames_u8:
+        oh, ow = scaled_size(f.shape[0], f.shape[1], size)
+        r = pil_resize_bilinear_u8(f, oh, ow)
+        top, left = int(round((oh - crop) / 2.0)), int(round((ow - crop) / 2.0))       # torchvision CenterCrop
+        out.append(r[top:top + crop, left:left + crop])
+    x = torch.from_numpy(np.stack(out, 0)).permute(0, 3, 1, 2).contiguous().float().div(255)   # ToTorchFormatTensor
+    return (x - 0.5) / 0.5                                                                      # Normalize(.5, .5)
+
+
+def video_level_prediction(logits: np.ndarray, ignore_last_class: bool = False) -> Dict[str, int]:
+    """format_trg_pred_video's three decision rules (metrics.py:118-142) for one video."""
+    from collections import Counter
+    lg = logits[:, :-1] if ignore_last_class else logits
+    preds = np.argmax(lg, axis=1).flatten().tolist()
+    vote = Counter(preds).most_common(1)[0][0]
+    e = np.exp(lg)
+    probs = e / np.sum(e, axis=1).reshape((-1, 1))
+    return {"FRAMES_VOTE": int(vote), "FRAMES_AVG_LOGITS": int(np.argmax(lg.mean(axis=0))),
+            "FRAMES_AVG_PROBS": int(np.argmax(probs.mean(axis=0)))}

@@ -192,3 +192,28 @@ def test_stitch_windows_vs_oracle():
     starts = torch.tensor([int(w[0]) for w in wins], dtype=torch.int32)
     got = stitch_windows(wl.to(dev), starts.to(dev), L).cpu()
     assert (got - want).abs().max().item() < 1e-6
+
+
+def test_preprocess_bit_exact_vs_reference_golden(golden_dir):
+    """uint8 stored crops -> fp32 NCHW through cer_preproc_forward: integer pipeline, so the bar is
+    bit-exact against the reference transform (real Pillow) for square, non-square and up-scaled inputs."""
+    import os
+    from feature_vs_text_compound_emotion_b200.engine import PreprocEngine
+    dev = _dev()
+    g = torch.load(os.path.join(golden_dir, "eval_transform.pt"))
+    for name, c in g["cases"].items():
+        raw = synthetic.raw_frames_u8(c["n"], seed=c["seed"], h=c["h"], w=c["w"])
+        eng = PreprocEngine(c["h"], c["w"], dev)
+        out = eng.forward(raw.to(dev)).cpu()
+        assert torch.equal(out, c["out"]), (name, (out - c["out"]).abs().max().item())
+
+
+def test_preprocess_many_frames_vs_oracle():
+    from feature_vs_text_compound_emotion_b200.engine import PreprocEngine
+    dev = _dev()
+    raw = synthetic.raw_frames_u8(37, seed=77)
+    raw[0] = 0
+    raw[1] = 255
+    out = PreprocEngine(256, 256, dev).forward(raw.to(dev)).cpu()
+    assert torch.equal(out, O.eval_transform(raw.numpy()))
+    assert out[0].eq(-1).all() and out[1].eq(1).all()

@@ -180,3 +180,33 @@ def test_lfan_logmel_from_pixels_vs_golden(golden_dir):
     assert out.shape == (1, T, 7)
     assert (out - g["logits"]).abs().max().item() <= 2e-2
     assert (out.argmax(-1) == g["logits"].argmax(-1)).float().mean().item() >= 0.975   # 40 frames: at most one flip
+
+
+def test_infer_video_from_stored_uint8_crops_and_logmel():
+    """cfg-3 shape of the path on one short video: stored uint8 256x256 crops -> device eval
+    transform -> IR-50; log-mel examples -> VGGish; BERT features; windows; stitch; video vote."""
+    dev = _dev()
+    from feature_vs_text_compound_emotion_b200 import windowing
+    mods = ["video", "logmel", "bert"]
+    m = _lfan(mods, dev, seed=6)
+    sd = synthetic.lfan_state_dict(6, mods)
+    L = 330                                    # two windows: [0,300) and the tail [30,330)
+    raw = synthetic.raw_frames_u8(L, seed=61)
+    lm = synthetic.logmel_patches(L, seed=62)
+    bert = torch.randn(L, 768, generator=torch.Generator().manual_seed(63))
+    out = windowing.infer_video(m, raw.to(dev), {"logmel": lm.to(dev), "bert": bert.to(dev)}).cpu()
+    assert out.shape == (L, 7)
+    vid = O.eval_transform(raw.numpy())
+    emb = O.ir50_forward(sd, vid, "spatial.visual.backbone.")
+    aud = O.vggish_forward(sd, lm, "spatial.audio.backbone.")
+    feats = {"video": emb, "logmel": aud, "bert": bert}
+    want = torch.zeros(L, 7)
+    cnt = torch.zeros(L, 1)
+    for wd in O.windowing(L, 300, 200):
+        y = O.head_forward(sd, {k: v[wd].unsqueeze(0) for k, v in feats.items()}, mods)[0]
+        want[wd] += y
+        cnt[wd] += 1
+    want = want / cnt
+    assert (out - want).abs().max().item() <= 2e-2
+    assert (out.argmax(-1) == want.argmax(-1)).float().mean().item() >= 0.99
+    assert windowing.video_level_prediction(out)["FRAMES_AVG_LOGITS"] == O.video_level_prediction(want.numpy())["FRAMES_AVG_LOGITS"]

@@ -139,3 +139,13 @@ def test_dropout_mask_statistics_and_determinism():
     assert torch.equal(m1, m2) and not torch.equal(m1, m3)
     assert abs(m1.mean().item() - 0.9) < 5e-3
     assert abs((m1 * m3).mean().item() - 0.81) < 8e-3       # streams are independent
+
+
+def test_eval_transform_matches_reference(golden_dir):
+    """PIL antialiased resize(48) + center crop(40) + normalise, restated in integer arithmetic:
+    bit-exact against the reference's transform classes (which ran real Pillow)."""
+    g = torch.load(os.path.join(golden_dir, "eval_transform.pt"))
+    for name, c in g["cases"].items():
+        raw = synthetic.raw_frames_u8(c["n"], seed=c["seed"], h=c["h"], w=c["w"]).numpy()
+        out = O.eval_transform(raw)
+        assert torch.equal(out, c["out"]), name
