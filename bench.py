@@ -172,12 +172,189 @@ def run_reference(args):
     }))
 
 
+def _timed(fn, steps, warmup, world, dist, dev, local):
+    """warm-up, barrier, CUDA-event timing of `steps` calls, max over ranks -> (total ms, clocks)."""
+    for i in range(warmup):
+        fn(i)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        fn(i)
+    e1.record()
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    if world > 1:
+        dist.barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    return ms.item(), clocks
+
+
+def video_lengths(n, seed=7):
+    """SURVEY.md section 8d cfg 3/5: T_v ~ U{150..3000}, seeded."""
+    g = torch.Generator().manual_seed(seed)
+    return torch.randint(150, 3001, (n,), generator=g).tolist()
+
+
+def run_videos(args, dev, world, rank, local, dist):
+    """configs[2] / configs[4]: whole videos from stored uint8 256x256 crops + per-frame log-mel
+    examples + BERT features -> device eval transform -> IR-50 / VGGish -> TCN -> fusion -> window
+    stitching -> video-level vote.  Videos are sharded over the ranks (longest first); the only
+    collective is the final gather of per-frame logits."""
+    from feature_vs_text_compound_emotion_b200 import sharding, synthetic, windowing
+    from feature_vs_text_compound_emotion_b200.models.model import LFAN
+    mods = ["video", "logmel", "bert"]
+    m = LFAN(backbone_settings=BS, output_dim=7, task="CLASSIFICATION", modality=mods, kernel_size=5, example_length=LENGTH,
+             tcn_channel=synthetic.TCN_CHANNELS, modal_dim=32, num_heads=2, root_dir="", device=dev)
+    m.init(visual_state_dict=synthetic.visual_backbone_state_dict(0), audio_state_dict=synthetic.vggish_state_dict(0))
+    m.load_state_dict(synthetic.lfan_state_dict(0, mods), strict=True)
+    m = m.to(dev).eval()
+    n_videos = args.videos or (56 if args.workload == "full" else 1000)
+    lengths = video_lengths(n_videos)
+    mine = sharding.shard_videos(lengths, world)[rank]
+    tmax = max(lengths)
+    # one synthetic video of the maximum length; every video is a prefix of it (synthetic data, real sizes)
+    raw_host = synthetic.raw_frames_u8(64, seed=11 + rank).repeat((tmax + 63) // 64, 1, 1, 1)[:tmax].contiguous().pin_memory()
+    lm_host = synthetic.logmel_patches(tmax, seed=12 + rank).pin_memory()
+    bert_host = torch.randn(tmax, 768, generator=torch.Generator().manual_seed(13 + rank)).pin_memory()
+    raw, lm, bert = raw_host.to(dev), lm_host.to(dev), bert_host.to(dev)
+    votes = {}
+
+    def run_shard(from_host):
+        local_out = {}
+        for i in mine:
+            T = lengths[i]
+            if from_host:
+                r, a, b = raw_host[:T].to(dev, non_blocking=True), lm_host[:T].to(dev, non_blocking=True), bert_host[:T].to(dev, non_blocking=True)
+            else:
+                r, a, b = raw[:T], lm[:T], bert[:T]
+            local_out[i] = windowing.infer_video(m, r, {"logmel": a, "bert": b})
+            votes[i] = local_out[i]
+        return sharding.gather_predictions(local_out, lengths, 7, dev)
+
+    total_ms, clocks = _timed(lambda i: run_shard(False), args.steps, args.warmup, world, dist, dev, local)
+    frames_total = sum(lengths)
+    value = frames_total * args.steps / (total_ms / 1e3)
+    out_host = torch.empty(sum(lengths[i] for i in mine), 7).pin_memory()
+
+    def e2e(i):
+        outs = run_shard(True)
+        off = 0
+        for k in mine:
+            out_host[off:off + lengths[k]].copy_(outs[k], non_blocking=True)
+            off += lengths[k]
+
+    e2e_ms, _ = _timed(e2e, max(1, args.steps // 2), 1, world, dist, dev, local)
+    e2e_value = frames_total * max(1, args.steps // 2) / (e2e_ms / 1e3)
+    if rank == 0:
+        n_mine = sum(lengths[i] for i in mine)
+        windows = sum(len(windowing.window_starts(t)) for t in lengths)
+        pred = windowing.video_level_prediction(votes[mine[0]])
+        burst, sustained, hbm, src = _peaks()
+        flops = (IR50_GFLOP_PER_FRAME + 1.7278 + HEAD_MFLOP_PER_FRAME * 1e-3) * 1e9
+        line = {
+            "metric": "frames_per_s", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {n_videos} videos, T_v~U[150,3000] (seed 7), {frames_total} unique frames, "
+                                   f"{windows} windows of 300/hop 200; stored uint8 256x256 crops -> device eval transform -> IR-50; "
+                                   "log-mel 96x64 -> VGGish; BERT 768-d; TCN; fusion; stitch; video vote",
+                       "sharding": "videos, longest first", "l2": "each video streams >100 MB of crops and >1 GB of activations",
+                       "collective": "all_gather of per-frame logits" if world > 1 else "none",
+                       "example_vote": pred},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": n_mine * (256 * 256 * 3 + 96 * 64 * 4 + 768 * 4),
+                    "d2h_bytes_per_step": n_mine * 28},
+            "gpu_launches": None,
+            "roofline": {"bound": "tensor", "achieved": value / world * flops / 1e12, "peak": sustained, "unit": "TFLOP/s",
+                         "frac": value / world * flops / 1e12 / sustained, "traffic": None,
+                         "kernel": "whole pipeline, algorithmic 7.792 GFLOP per unique frame (IR-50 6.0545 + VGGish 1.7278 + head 0.010)",
+                         "peak_source": f"{src} sustained"},
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_train(args, dev, world, rank, local, dist):
+    """configs[3]: fusion-head training step on feature windows (frozen backbones => pre-extracted
+    512/128/768-d features), AdamW(lr 1e-4, wd 1e-4), gradients summed with ONE NCCL all-reduce of
+    the flat 20 MB bucket; weak scaling (B windows per rank)."""
+    from feature_vs_text_compound_emotion_b200 import synthetic
+    from feature_vs_text_compound_emotion_b200.models.model import LFAN
+    from feature_vs_text_compound_emotion_b200.training import HeadTrainer
+    torch.set_grad_enabled(True)
+    mods = ["cnn_res50", "vggish", "bert"]
+    B = args.train_batch
+    m = LFAN(backbone_settings=BS, output_dim=7, task="CLASSIFICATION", modality=mods, kernel_size=5, example_length=LENGTH,
+             tcn_channel=synthetic.TCN_CHANNELS, modal_dim=32, num_heads=2, root_dir="", device=dev)
+    m.init()
+    m.load_state_dict(synthetic.lfan_state_dict(0, mods), strict=True)
+    m = m.to(dev).train()
+    tr = HeadTrainer(m, B, LENGTH, optimizer={"name": "adamw", "lr": 1e-4, "weight_decay": 1e-4}, seed=rank)
+    host = [synthetic.feature_windows(B, LENGTH, seed=200 + i + 100 * rank, modalities=mods) for i in range(2)]
+    labs = [torch.randint(0, 7, (B, LENGTH, 1), generator=torch.Generator().manual_seed(300 + i + 100 * rank)) for i in range(2)]
+    devb = [{k: v.to(dev) for k, v in h.items()} for h in host]
+    devl = [l.to(dev) for l in labs]
+    losses = []
+    total_ms, clocks = _timed(lambda i: losses.append(tr.step(devb[i % 2], devl[i % 2])), args.steps, args.warmup, world, dist, dev, local)
+    frames = B * LENGTH
+    value = world * frames * args.steps / (total_ms / 1e3)
+    pinned = [{k: v.pin_memory() for k, v in h.items()} for h in host]
+    pl = [l.pin_memory() for l in labs]
+    loss_host = torch.empty(1).pin_memory()
+
+    def e2e(i):
+        b = {k: v.to(dev, non_blocking=True) for k, v in pinned[i % 2].items()}
+        loss_host.copy_(tr.step(b, pl[i % 2].to(dev, non_blocking=True)), non_blocking=True)
+
+    e2e_ms, _ = _timed(e2e, args.steps, 2, world, dist, dev, local)
+    if rank == 0:
+        burst, sustained, hbm, src = _peaks()
+        h2d = sum(v.numel() * v.element_size() for v in pinned[0].values()) + pl[0].numel() * 8
+        tf = 3 * HEAD_MFLOP_PER_FRAME * 1e6 * frames / (total_ms / args.steps * 1e-3) / 1e12
+        line = {
+            "metric": "frames_per_s", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"train: fusion-head step (fwd+CE+bwd+AdamW), {B} windows x {LENGTH} frames per GPU, "
+                                   "features 512/128/768-d, dropout 0.1, BatchNorm1d batch stats",
+                       "l2": "two rotating batches; 20 MB weights + ~120 MB of saved activations per step",
+                       "collective": "one all_reduce(SUM) of the flat 5,002,503-float gradient bucket" if world > 1 else "none",
+                       "loss_first_last": [float(losses[0]), float(losses[-1])]},
+            "clocks": clocks,
+            "e2e": {"value": world * frames * args.steps / (e2e_ms / 1e3), "unit": "frames/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": 4},
+            "gpu_launches": None,
+            "roofline": {"bound": "tensor", "achieved": tf, "peak": 72.0, "unit": "TFLOP/s", "frac": tf / 72.0, "traffic": None,
+                         "kernel": "row_gemm/wgrad (fp32 CUDA cores; peak = 148 SMs x 128 FMA x 2 x 1.9 GHz), algorithmic 3 x 9.988 MFLOP per frame",
+                         "peak_source": "nominal fp32 FMA rate"},
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="infer", choices=["infer", "full", "sweep", "train"],
+                    help="infer: BASELINE configs[1] shape through the whole path (default, the headline line); "
+                         "full: configs[2] -- 56 variable-length videos from stored uint8 crops + log-mel + BERT; "
+                         "sweep: configs[4] -- 1000 videos sharded over the ranks (strong scaling); "
+                         "train: configs[3] -- fusion-head training step, B=16 windows per rank, NCCL grad all-reduce")
+    ap.add_argument("--videos", type=int, default=0, help="override the number of videos of full/sweep")
+    ap.add_argument("--train-batch", type=int, default=16)
     ap.add_argument("--frames-per-pass", type=int, default=int(os.environ.get("CER_FRAMES_PER_PASS", "0")))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -201,6 +378,10 @@ def main():
     from feature_vs_text_compound_emotion_b200 import modules
     if args.frames_per_pass > 0:
         modules.Backbone.frames_per_pass = args.frames_per_pass
+    if args.workload in ("full", "sweep"):
+        return run_videos(args, dev, world, rank, local, dist)
+    if args.workload == "train":
+        return run_train(args, dev, world, rank, local, dist)
     model = build_model(dev)
     frames = WINDOWS * LENGTH
     ROT = 4   # rotating input sets: 4 x 54.7 MB > L2, and each step streams > 1 GB of activations
