@@ -40,6 +40,7 @@ struct alignas(64) ConvKernelParams {
   int num_m_tiles, num_n_tiles;
   int bias_classes;      // 1 or 9
   int out_fp32;          // 0: bf16 output, 1: fp32 output
+  int halo_frames, halo_bands, halo_cts;   // conv_halo_kernel only: frames, 16-row bands and 8-column tiles per frame
   const float* bias;     // [bias_classes][Cout]
   const float* alpha;    // [Cout] PReLU slopes or nullptr
   const __nv_bfloat16* res;  // [M][Cout] residual or nullptr
@@ -82,6 +83,13 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
 // One output tile of the fused epilogue, for one epilogue thread (warp 0-7):
 //   + bias[class(pixel)][co] -> PReLU(alpha[co]) -> + residual[m][co] -> bf16 | fp32.
 // `tmem_acc` is the accumulator's TMEM base column; `tfull` the barrier that says it is complete.
+// The caller maps its TMEM lane to an output pixel: `valid`, its border class `cls` and the
+// element offset `out_off` of (pixel, first channel of this thread's column half).
+template <int BN>
+__device__ __forceinline__ void conv_epilogue_core(const ConvKernelParams& p, const float* s_bias, const float* s_alpha,
+                                                   uint32_t tmem_acc, int n0, int warp, uint32_t tfull, uint32_t parity,
+                                                   bool valid, int cls, size_t out_off);
+
 template <int BN>
 __device__ __forceinline__ void conv_epilogue_tile(const ConvKernelParams& p, const float* s_bias, const float* s_alpha,
                                                    uint32_t tmem_acc, int m_tile, int n_tile, int warp, int lane,
@@ -90,10 +98,7 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvKernelParams& p, co
   const int quarter = warp & 3;                // TMEM lane quarter this warp may read
   const int half = warp >> 2;                  // column half
   const int row = quarter * 32 + lane;         // TMEM lane == row of the M tile
-  const uint32_t lane_addr = (static_cast<uint32_t>(quarter * 32) << 16);
   const int hw = p.Hout * p.Wout;
-  const bool has_res = p.res != nullptr;
-  const bool has_alpha = p.alpha != nullptr;
   const int m = m_tile * kBlockM + row;
   const bool valid = m < p.M;
   const int n0 = n_tile * BN + half * kHalf;
@@ -104,9 +109,22 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvKernelParams& p, co
     const int ow = rem - oh * p.Wout;
     cls = (oh == 0 ? 0 : (oh == p.Hout - 1 ? 2 : 1)) * 3 + (ow == 0 ? 0 : (ow == p.Wout - 1 ? 2 : 1));
   }
+  conv_epilogue_core<BN>(p, s_bias, s_alpha, tmem_acc, n0, warp, tfull, parity, valid, cls,
+                         static_cast<size_t>(m) * p.Cout + n0);
+}
+
+template <int BN>
+__device__ __forceinline__ void conv_epilogue_core(const ConvKernelParams& p, const float* s_bias, const float* s_alpha,
+                                                   uint32_t tmem_acc, int n0, int warp, uint32_t tfull, uint32_t parity,
+                                                   bool valid, int cls, size_t out_off) {
+  constexpr int kHalf = BN / 2;
+  const int quarter = warp & 3;
+  const int half = warp >> 2;
+  const uint32_t lane_addr = (static_cast<uint32_t>(quarter * 32) << 16);
+  const bool has_res = p.res != nullptr;
+  const bool has_alpha = p.alpha != nullptr;
   const float* sb = s_bias + cls * p.Cout + n0;
   const float* sal = s_alpha + n0;
-  const size_t out_off = static_cast<size_t>(m) * p.Cout + n0;
   const bool ld_res = has_res && valid;
 
   // residual of the first chunk is requested before the accumulator wait: its latency hides

@@ -14,6 +14,8 @@ struct ConvOp {
   CUtensorMap tmap_b_half;   // weights with a BN/2-row box: the CTA-pair variant loads half a B tile per CTA
   int bn;          // 64 / 128 / 256
   int hw_out;      // output pixels per frame
+  CUtensorMap tmap_halo;     // tiled 4-D map with an 18 x 10 pixel box (conv_halo_kernel); valid iff halo_ok
+  int halo_ok;               // 3x3 / stride 1 / pad 1, Cin = 64, Cout in {64, 128}, W % 8 == 0
 };
 
 struct ConvGeom {

@@ -14,6 +14,7 @@
 #include "common.h"
 #include "conv_plan.h"
 #include "conv_igemm2.cuh"
+#include "conv_halo.cuh"
 #include <cstdlib>
 
 namespace cer {
@@ -171,6 +172,24 @@ static int make_weight_map(CUtensorMap* map, const void* base, int Cout, int K, 
   return CER_OK;
 }
 
+// NHWC bf16 activation as a tiled 4-D map whose box is the (16+2) x (8+2) pixel halo of one output
+// tile, 64 channels deep (conv_halo_kernel).  Out-of-bounds pixels read as zero = the conv padding.
+static int make_halo_map(CUtensorMap* map, const void* base, int N, int H, int W, int C) {
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  cuuint32_t box[4] = {64, (cuuint32_t)(kHaloTileW + 2), (cuuint32_t)(kHaloTileH + 2), 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = g_encode_tiled(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char buf[128];
+    snprintf(buf, sizeof buf, "cuTensorMapEncodeTiled (halo) failed (%d) N=%d H=%d W=%d C=%d", (int)r, N, H, W, C);
+    return set_error(CER_ERR_CUDA, buf);
+  }
+  return CER_OK;
+}
+
 // Generic helpers shared with the TCN tensor-core path (tcn_tc.cu).
 int make_im2col_map_generic(CUtensorMap* map, CUtensorMapDataType dt, int elem_bytes, const void* base, int N, int H,
                             int W, int C, const int lower[2], const int upper[2], int stride, int channels_per_pixel) {
@@ -250,7 +269,35 @@ int build_conv_op(ConvOp* op, const ConvGeom& g, int n_cap) {
   p.bias_classes = g.bias_classes;
   p.out_fp32 = g.out_fp32;
   p.bias = g.bias; p.alpha = g.alpha; p.res = g.res; p.out = g.dst;
+  op->halo_ok = g.ksize == 3 && g.stride == 1 && g.pad == 1 && g.Cin == 64 && g.Cin2 == 0 && (g.Cout == 64 || g.Cout == 128) &&
+                g.W % kHaloTileW == 0 && !g.out_fp32;
+  if (op->halo_ok) {
+    rc = make_halo_map(&op->tmap_halo, g.src, n_cap, g.H, g.W, g.Cin);
+    if (rc) return rc;
+  }
   return CER_OK;
+}
+
+template <int BN>
+static int launch_halo_inst(const ConvKernelParams& p, int num_sms, cudaStream_t st) {
+  using L = HaloSmem<BN>;
+  static_assert(L::kTotal <= 232448, "halo conv kernel shared memory exceeds 227 KB");
+  static bool configured = false;
+  if (!configured) {
+    CER_CUDA(cudaFuncSetAttribute(conv_halo_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
+    configured = true;
+  }
+  const int tiles = p.halo_frames * p.halo_bands * p.halo_cts;
+  conv_halo_kernel<BN><<<std::min(tiles, num_sms), kHaloThreads, L::kTotal, st>>>(p);
+  CER_CUDA(cudaGetLastError());
+  return CER_OK;
+}
+
+// CER_HALO: unset/1 = halo kernel for the Cin = 64 layers, 0 = im2col kernel (A/B timing).
+static int halo_mode() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("CER_HALO"); v = e ? atoi(e) : 1; }
+  return v;
 }
 
 template <int BN, int STAGES, bool BRES, bool ALIGNED>
@@ -308,6 +355,13 @@ int launch_conv(const ConvOp& op, int frames, int num_sms, cudaStream_t st) {
   p.num_m_tiles = (p.M + kBlockM - 1) / kBlockM;
   const int tiles = p.num_m_tiles * p.num_n_tiles;
   if (tiles == 0) return CER_OK;
+  if (op.halo_ok && halo_mode() != 0 && tiles >= 2 * num_sms) {
+    p.tmap_a = op.tmap_halo;
+    p.halo_frames = frames;
+    p.halo_bands = (p.Hout + kHaloTileH - 1) / kHaloTileH;
+    p.halo_cts = p.Wout / kHaloTileW;
+    return op.bn == 64 ? launch_halo_inst<64>(p, num_sms, st) : launch_halo_inst<128>(p, num_sms, st);
+  }
   const int grid = std::min(tiles, num_sms);
   const int ksteps = p.ksteps_main + p.ksteps2;
   // CTA-pair (cta_group::2) variant: plain 3x3 / 1x1 layers whose k-steps fill the 6-stage ring a whole
