@@ -85,6 +85,8 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();
+  pdl_wait();
   const uint32_t smem_base = smem_u32(smem);
   const uint32_t full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar);
   const uint32_t tfull0 = smem_u32(tfull_bar), tempty0 = smem_u32(tempty_bar);

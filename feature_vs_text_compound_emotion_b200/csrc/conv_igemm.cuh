@@ -254,6 +254,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();     // everything above touched only constants: overlap it with the previous layer's tail
+  pdl_wait();                  // the previous layer's activations are complete and visible from here on
 
   if (warp >= kProdWarp0) {
     // ===================== TMA producers (one lane each) =====================

@@ -127,6 +127,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm2_kernel(const __gr
   cluster_sync_all();                     // both CTAs' barriers are initialised before any remote signal
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();
+  pdl_wait();
 
   const uint32_t smem_base = smem_u32(smem);
   const uint32_t full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar);

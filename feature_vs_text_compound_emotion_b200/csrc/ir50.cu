@@ -278,6 +278,42 @@ int build_conv_op(ConvOp* op, const ConvGeom& g, int n_cap) {
   return CER_OK;
 }
 
+// CER_PDL=0 disables programmatic dependent launch (A/B timing).
+static bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("CER_PDL"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v == 1;
+}
+
+// All conv launches go through here: optional 2-CTA cluster, programmatic stream serialization so
+// that the next layer's prologue overlaps this layer's tail (the kernels call griddepcontrol.wait
+// before touching activations).
+template <typename Kernel>
+static int launch_conv_kernel(Kernel kernel, int grid, int threads, size_t smem, cudaStream_t st, int cluster,
+                              const ConvKernelParams& p) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof cfg);
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(threads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (cluster > 1) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = cluster; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  if (pdl_enabled()) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = attr; cfg.numAttrs = na;
+  CER_CUDA(cudaLaunchKernelEx(&cfg, kernel, p));
+  return CER_OK;
+}
+
 template <int BN>
 static int launch_halo_inst(const ConvKernelParams& p, int num_sms, cudaStream_t st) {
   using L = HaloSmem<BN>;
@@ -288,9 +324,7 @@ static int launch_halo_inst(const ConvKernelParams& p, int num_sms, cudaStream_t
     configured = true;
   }
   const int tiles = p.halo_frames * p.halo_bands * p.halo_cts;
-  conv_halo_kernel<BN><<<std::min(tiles, num_sms), kHaloThreads, L::kTotal, st>>>(p);
-  CER_CUDA(cudaGetLastError());
-  return CER_OK;
+  return launch_conv_kernel(conv_halo_kernel<BN>, std::min(tiles, num_sms), kHaloThreads, L::kTotal, st, 1, p);
 }
 
 // CER_HALO: unset/1 = halo kernel for the Cin = 64 layers, 0 = im2col kernel (A/B timing).
@@ -312,9 +346,7 @@ static int launch_conv_inst(const ConvKernelParams& p, int grid, cudaStream_t st
     configured = true;
   }
   if ((p.bias_classes + 1) * p.Cout > L::kTableFloats) return set_error(CER_ERR_INVALID, "conv: Cout too large for the epilogue table");
-  conv_igemm_kernel<BN, STAGES, BRES, ALIGNED><<<grid, kConvThreads, L::kTotal, st>>>(p);
-  CER_CUDA(cudaGetLastError());
-  return CER_OK;
+  return launch_conv_kernel(conv_igemm_kernel<BN, STAGES, BRES, ALIGNED>, grid, kConvThreads, L::kTotal, st, 1, p);
 }
 
 template <int BN, int STAGES>
@@ -329,18 +361,7 @@ static int launch_conv2_inst(const ConvKernelParams& p, int num_sms, cudaStream_
   if ((p.bias_classes + 1) * p.Cout > L::kTableFloats) return set_error(CER_ERR_INVALID, "conv: Cout too large for the epilogue table");
   const int ptiles = ((p.num_m_tiles + 1) / 2) * p.num_n_tiles;
   const int pairs = std::min(ptiles, num_sms / 2);
-  cudaLaunchConfig_t cfg;
-  memset(&cfg, 0, sizeof cfg);
-  cfg.gridDim = dim3(2 * pairs);
-  cfg.blockDim = dim3(kConvThreads);
-  cfg.dynamicSmemBytes = L::kTotal;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr; cfg.numAttrs = 1;
-  CER_CUDA(cudaLaunchKernelEx(&cfg, conv_igemm2_kernel<BN, STAGES>, p));
-  return CER_OK;
+  return launch_conv_kernel(conv_igemm2_kernel<BN, STAGES>, 2 * pairs, kConvThreads, L::kTotal, st, 2, p);
 }
 
 static bool pair_mode_enabled() {

@@ -23,6 +23,14 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// ------------------------------------------------------------------ programmatic dependent launch
+// A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start (run its
+// prologue) while the previous kernel in the stream is still draining; pdl_wait() blocks until
+// that kernel has completed and its writes are visible.  pdl_launch_dependents() lets the NEXT
+// kernel's CTAs be scheduled as soon as SM resources free up.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ------------------------------------------------------------------ mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
