@@ -210,3 +210,18 @@ def test_infer_video_from_stored_uint8_crops_and_logmel():
     assert (out - want).abs().max().item() <= 2e-2
     assert (out.argmax(-1) == want.argmax(-1)).float().mean().item() >= 0.99
     assert windowing.video_level_prediction(out)["FRAMES_AVG_LOGITS"] == O.video_level_prediction(want.numpy())["FRAMES_AVG_LOGITS"]
+
+
+def test_host_prefetcher_matches_direct_calls():
+    """Double-buffered H2D staging must not change results or reorder batches."""
+    dev = _dev()
+    from feature_vs_text_compound_emotion_b200.pipeline import HostPrefetcher
+    mods = ["cnn_res50", "vggish", "bert"]
+    m = _lfan(mods, dev)
+    host = [{k: v.pin_memory() for k, v in synthetic.feature_windows(2, 300, seed=70 + i, modalities=mods).items()} for i in range(5)]
+    want = [m({k: v.to(dev) for k, v in h.items()}).cpu() for h in host]
+    got = {}
+    n = HostPrefetcher(dev).run(iter(host), lambda b: m(b), lambda i, out: got.__setitem__(i, out.cpu()))
+    assert n == 5
+    for i in range(5):
+        assert torch.equal(got[i], want[i]), i
