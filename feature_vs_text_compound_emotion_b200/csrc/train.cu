@@ -71,89 +71,175 @@ struct RowGemm {
   Drop drop;
 };
 
-template <bool B_KN>
-__global__ void __launch_bounds__(256) row_gemm_kernel(const RowGemm g) {
-  __shared__ float As[16][64 + 4];
-  __shared__ float Bs[16][64 + 4];
-  const int tid = threadIdx.x;
-  const int tx = tid & 15, ty = tid >> 4;          // 16 x 16 threads; thread -> rows ty*4.., cols tx*4..
-  const int row0 = blockIdx.y * 64, col0 = blockIdx.x * 64;
-  float acc[4][4];
+// ---- shared micro-kernel: 128 x 64 outputs per CTA, 256 threads, 8 x 4 per thread, packed FP32 FMAs ----
+// Blackwell issues two fp32 FMAs per instruction (fma.rn.f32x2).  The "m" operand comes from shared
+// memory as natural pairs (rows 2i, 2i+1); the "n" operand is stored DUPLICATED ({b, b}) so that no
+// register shuffling is needed: per k, 4 x LDS.128 feed 16 x FFMA2 (= 32 FMAs).
+__device__ __forceinline__ void ffma2(unsigned long long& d, unsigned long long a, unsigned long long b) {
+  asm volatile("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(d) : "l"(a), "l"(b));
+}
+struct alignas(16) Pair2 { unsigned long long x, y; };      // two packed float2 = one LDS.128
+
+constexpr int kGM = 128, kGN = 64, kGK = 16;
+
+template <int BM>
+__device__ __forceinline__ void micro_step(const float (*Ms)[BM + 4], const float2 (*Ns)[kGN], int kk, int ty, int tx,
+                                           unsigned long long (&acc)[4][4]) {
+  const Pair2 a01 = *reinterpret_cast<const Pair2*>(&Ms[kk][ty * 8]);          // rows (0,1) (2,3)
+  const Pair2 a23 = *reinterpret_cast<const Pair2*>(&Ms[kk][ty * 8 + 4]);      // rows (4,5) (6,7)
+  const Pair2 b01 = *reinterpret_cast<const Pair2*>(&Ns[kk][tx * 4]);          // {b0,b0} {b1,b1}
+  const Pair2 b23 = *reinterpret_cast<const Pair2*>(&Ns[kk][tx * 4 + 2]);      // {b2,b2} {b3,b3}
+  const unsigned long long a[4] = {a01.x, a01.y, a23.x, a23.y};
+  const unsigned long long b[4] = {b01.x, b01.y, b23.x, b23.y};
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < 4; ++j) ffma2(acc[i][j], a[i], b[j]);
+}
+__device__ __forceinline__ float2 unpack2(unsigned long long v) {
+  float2 r;
+  asm volatile("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+  return r;
+}
 
-  // loader mapping: A tile 64 rows x 16 k -> thread loads 4 consecutive k of one row
+// BM = 128 (256 threads) or 64 (128 threads): the smaller tile doubles the CTA count when the
+// problem has too few tiles to fill 148 SMs.
+template <bool B_KN, int BM>
+__global__ void __launch_bounds__(2 * BM) row_gemm_kernel(const RowGemm g) {
+  constexpr int NT = 2 * BM;                             // threads
+  __shared__ __align__(16) float As[kGK][BM + 4];        // [k][row]
+  __shared__ __align__(16) float2 Bs[kGK][kGN];          // [k][col] duplicated
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;                // thread -> rows ty*8.., cols tx*4..
+  const int row0 = blockIdx.y * BM, col0 = blockIdx.x * kGN;
+  unsigned long long acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0ull;
+
+  // loader mapping.  A tile: BM rows x 16 k, two float4 per thread (rows a_r and a_r + BM/2).
+  constexpr int AH = BM / 2;
   const int a_r = tid >> 2, a_k = (tid & 3) * 4;
-  const int arow = row0 + a_r;
-  const int a_t = arow < g.R ? arow % g.T : 0;
-  for (int j = 0; j < g.taps; ++j) {
+  const bool a_vec = (g.lda & 3) == 0 && (g.K & 3) == 0 && (reinterpret_cast<uintptr_t>(g.A) & 15) == 0;
+  int a_t[2];
+#pragma unroll
+  for (int h = 0; h < 2; ++h) { const int r = row0 + a_r + AH * h; a_t[h] = r < g.R ? r % g.T : -(1 << 30); }
+  // B tile: 16 k x 64 n = 256 float4; threads beyond 256 float4 slots (none) / fewer threads loop twice (BM = 64).
+  // [K][N] storage: slot -> one k, 4 consecutive n;  [N][K] storage: one n, 4 consecutive k.
+  constexpr int BP = 256 / NT;                           // B float4 slots per thread (1 or 2)
+  const int b_ld = B_KN ? g.N : g.K;
+  const bool b_vec = (b_ld & 3) == 0 && (reinterpret_cast<uintptr_t>(g.B) & 15) == 0 && (g.b_tap_stride & 3) == 0;
+
+  const int ksteps = (g.K + kGK - 1) / kGK;
+  const int total = g.taps * ksteps;
+  float4 ra[2], rbv[BP];
+  auto fetch = [&](int it) {
+    const int j = it / ksteps, k0 = (it - j * ksteps) * kGK;
     const int shift = g.shift0 + j * g.shift_step;
-    const bool a_ok = arow < g.R && (a_t + shift) >= 0 && (a_t + shift) < g.T;
-    const float* ap = g.A + (long long)(arow + shift) * g.lda;
-    const float* bp = g.B + j * g.b_tap_stride;
-    for (int k0 = 0; k0 < g.K; k0 += 16) {
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int k = k0 + a_k + q;
-        As[a_k + q][a_r] = (a_ok && k < g.K) ? __ldg(ap + k) : 0.f;
+    for (int h = 0; h < 2; ++h) {
+      const int r = row0 + a_r + AH * h;
+      const bool ok = (a_t[h] + shift) >= 0 && (a_t[h] + shift) < g.T;      // a_t < 0 for rows >= R
+      const float* ap = g.A + (long long)(r + shift) * g.lda + k0 + a_k;
+      if (ok && a_vec && k0 + a_k + 3 < g.K) ra[h] = __ldg(reinterpret_cast<const float4*>(ap));
+      else {
+        ra[h].x = (ok && k0 + a_k + 0 < g.K) ? __ldg(ap + 0) : 0.f;
+        ra[h].y = (ok && k0 + a_k + 1 < g.K) ? __ldg(ap + 1) : 0.f;
+        ra[h].z = (ok && k0 + a_k + 2 < g.K) ? __ldg(ap + 2) : 0.f;
+        ra[h].w = (ok && k0 + a_k + 3 < g.K) ? __ldg(ap + 3) : 0.f;
       }
-      if (B_KN) {      // B[k][n]: thread loads 4 consecutive n of one k
-        const int b_k = tid >> 4, b_n = (tid & 15) * 4;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int k = k0 + b_k, n = col0 + b_n + q;
-          Bs[b_k][b_n + q] = (k < g.K && n < g.N) ? __ldg(bp + (long long)k * g.N + n) : 0.f;
-        }
-      } else {         // B[n][k]: thread loads 4 consecutive k of one n
-        const int b_n = tid >> 2, b_k = (tid & 3) * 4;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int k = k0 + b_k + q, n = col0 + b_n;
-          Bs[b_k + q][b_n] = (k < g.K && n < g.N) ? __ldg(bp + (long long)n * g.K + k) : 0.f;
-        }
-      }
-      __syncthreads();
-#pragma unroll
-      for (int kk = 0; kk < 16; ++kk) {
-        const float4 a = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
-        const float4 b = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
-        const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-          for (int jj = 0; jj < 4; ++jj) acc[i][jj] = fmaf(av[i], bv[jj], acc[i][jj]);
-      }
-      __syncthreads();
     }
+    const float* bp = g.B + j * g.b_tap_stride;
+#pragma unroll
+    for (int u = 0; u < BP; ++u) {
+      const int slot = tid + u * NT;
+      const int b_a = B_KN ? (slot >> 4) : (slot >> 2);        // k (B_KN) or n (!B_KN)
+      const int b_b = B_KN ? (slot & 15) * 4 : (slot & 3) * 4; // n (B_KN) or k (!B_KN)
+      float4& rb = rbv[u];
+      if (B_KN) {
+        const int k = k0 + b_a, n = col0 + b_b;
+        const float* q = bp + (long long)k * g.N + n;
+        if (k < g.K && b_vec && n + 3 < g.N) rb = __ldg(reinterpret_cast<const float4*>(q));
+        else {
+          rb.x = (k < g.K && n + 0 < g.N) ? __ldg(q + 0) : 0.f;
+          rb.y = (k < g.K && n + 1 < g.N) ? __ldg(q + 1) : 0.f;
+          rb.z = (k < g.K && n + 2 < g.N) ? __ldg(q + 2) : 0.f;
+          rb.w = (k < g.K && n + 3 < g.N) ? __ldg(q + 3) : 0.f;
+        }
+      } else {
+        const int n = col0 + b_a, k = k0 + b_b;
+        const float* q = bp + (long long)n * g.K + k;
+        if (n < g.N && b_vec && k + 3 < g.K) rb = __ldg(reinterpret_cast<const float4*>(q));
+        else {
+          rb.x = (n < g.N && k + 0 < g.K) ? __ldg(q + 0) : 0.f;
+          rb.y = (n < g.N && k + 1 < g.K) ? __ldg(q + 1) : 0.f;
+          rb.z = (n < g.N && k + 2 < g.K) ? __ldg(q + 2) : 0.f;
+          rb.w = (n < g.N && k + 3 < g.K) ? __ldg(q + 3) : 0.f;
+        }
+      }
+    }
+  };
+  auto stash = [&]() {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      As[a_k + 0][a_r + AH * h] = ra[h].x; As[a_k + 1][a_r + AH * h] = ra[h].y;
+      As[a_k + 2][a_r + AH * h] = ra[h].z; As[a_k + 3][a_r + AH * h] = ra[h].w;
+    }
+#pragma unroll
+    for (int u = 0; u < BP; ++u) {
+      const int slot = tid + u * NT;
+      const int b_a = B_KN ? (slot >> 4) : (slot >> 2);
+      const int b_b = B_KN ? (slot & 15) * 4 : (slot & 3) * 4;
+      const float4 rb = rbv[u];
+      if (B_KN) {
+        Bs[b_a][b_b + 0] = make_float2(rb.x, rb.x); Bs[b_a][b_b + 1] = make_float2(rb.y, rb.y);
+        Bs[b_a][b_b + 2] = make_float2(rb.z, rb.z); Bs[b_a][b_b + 3] = make_float2(rb.w, rb.w);
+      } else {
+        Bs[b_b + 0][b_a] = make_float2(rb.x, rb.x); Bs[b_b + 1][b_a] = make_float2(rb.y, rb.y);
+        Bs[b_b + 2][b_a] = make_float2(rb.z, rb.z); Bs[b_b + 3][b_a] = make_float2(rb.w, rb.w);
+      }
+    }
+  };
+  fetch(0);
+  for (int it = 0; it < total; ++it) {
+    stash();
+    __syncthreads();
+    if (it + 1 < total) fetch(it + 1);           // global loads of the next tile fly during the FMAs
+#pragma unroll
+    for (int kk = 0; kk < kGK; ++kk) micro_step<BM>(As, Bs, kk, ty, tx, acc);
+    __syncthreads();
   }
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const int r = row0 + ty * 4 + i;
-    if (r >= g.R) continue;
 #pragma unroll
-    for (int jj = 0; jj < 4; ++jj) {
-      const int n = col0 + tx * 4 + jj;
-      if (n >= g.N) continue;
-      float v = acc[i][jj];
-      if (g.bias) v += __ldg(g.bias + n);
-      const uint32_t idx = (uint32_t)r * (uint32_t)g.N + (uint32_t)n;
-      float* cp = g.C + (long long)r * g.ldc + n;
-      if (g.epi == EPI_LINEAR) {
-        if (g.addend) v += g.addend[(long long)r * g.ld_add + n];
-        if (g.accumulate) v += *cp;
-        *cp = v;
-      } else if (g.epi == EPI_LRELU_DROP) {
-        *cp = lrelu(v) * drop_factor(g.drop, idx);
-      } else if (g.epi == EPI_BLOCK_OUT) {
-        const float h2d = lrelu(v) * drop_factor(g.drop, idx);
-        g.aux[(long long)r * g.ld_aux + n] = h2d;
-        *cp = lrelu(h2d + g.addend[(long long)r * g.ld_add + n]);
-      } else {   // EPI_DGRAD_ACT: gradient w.r.t. the pre-activation of a LReLU+dropout site
-        if (g.addend) v += g.addend[(long long)r * g.ld_add + n];
-        const float saved = g.aux[(long long)r * g.ld_aux + n];
-        *cp = v * drop_factor(g.drop, idx) * lrelu_grad(saved);
+    for (int half = 0; half < 2; ++half) {
+      const int r = row0 + ty * 8 + 2 * i + half;
+      if (r >= g.R) continue;
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        const int n = col0 + tx * 4 + jj;
+        if (n >= g.N) continue;
+        const float2 pr = unpack2(acc[i][jj]);
+        float v = half ? pr.y : pr.x;
+        if (g.bias) v += __ldg(g.bias + n);
+        const uint32_t idx = (uint32_t)r * (uint32_t)g.N + (uint32_t)n;
+        float* cp = g.C + (long long)r * g.ldc + n;
+        if (g.epi == EPI_LINEAR) {
+          if (g.addend) v += g.addend[(long long)r * g.ld_add + n];
+          if (g.accumulate) v += *cp;
+          *cp = v;
+        } else if (g.epi == EPI_LRELU_DROP) {
+          *cp = lrelu(v) * drop_factor(g.drop, idx);
+        } else if (g.epi == EPI_BLOCK_OUT) {
+          const float h2d = lrelu(v) * drop_factor(g.drop, idx);
+          g.aux[(long long)r * g.ld_aux + n] = h2d;
+          *cp = lrelu(h2d + g.addend[(long long)r * g.ld_add + n]);
+        } else {   // EPI_DGRAD_ACT: gradient w.r.t. the pre-activation of a LReLU+dropout site
+          if (g.addend) v += g.addend[(long long)r * g.ld_add + n];
+          const float saved = g.aux[(long long)r * g.ld_aux + n];
+          *cp = v * drop_factor(g.drop, idx) * lrelu_grad(saved);
+        }
       }
     }
   }
@@ -161,7 +247,8 @@ __global__ void __launch_bounds__(256) row_gemm_kernel(const RowGemm g) {
 
 // ------------------------------------------------------------------------------------------
 // Weight gradient with taps:  dW_j[n][k] += sum_r G[r, n] * A[r + shift_j, k]
-// grid = (ceil(K/64) * taps, ceil(N/64), row splits); fp32 atomicAdd into a zeroed buffer.
+// CTA tile: 128 n x 64 k for one tap, a slice of the rows; grid = (ceil(K/64) * taps, ceil(N/128),
+// row splits); fp32 atomicAdd into a zeroed buffer.  Same micro-kernel (m = n of G, n = k of A).
 // ------------------------------------------------------------------------------------------
 struct WGrad {
   const float* G; int ldg;
@@ -174,55 +261,79 @@ struct WGrad {
 };
 
 __global__ void __launch_bounds__(256) wgrad_kernel(const WGrad g) {
-  __shared__ float Gs[16][64 + 4];
-  __shared__ float As[16][64 + 4];
+  __shared__ __align__(16) float Gs[kGK][kGM + 4];       // [row][n]
+  __shared__ __align__(16) float2 As[kGK][kGN];          // [row][k] duplicated
   const int tid = threadIdx.x;
-  const int tx = tid & 15, ty = tid >> 4;          // thread -> n = ty*4.., k = tx*4..
+  const int tx = tid & 15, ty = tid >> 4;                // thread -> n = ty*8.., k = tx*4..
   const int j = blockIdx.x / g.k_tiles;
-  const int k0 = (blockIdx.x - j * g.k_tiles) * 64;
-  const int n0 = blockIdx.y * 64;
+  const int k0 = (blockIdx.x - j * g.k_tiles) * kGN;
+  const int n0 = blockIdx.y * kGM;
   const int shift = g.shift0 + j * g.shift_step;
   const int r_begin = blockIdx.z * g.rows_per_split;
   const int r_end = min(g.R, r_begin + g.rows_per_split);
-  float acc[4][4];
+  unsigned long long acc[4][4];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
-    for (int q = 0; q < 4; ++q) acc[i][q] = 0.f;
-  const int l_r = tid >> 4, l_c = (tid & 15) * 4;    // 16 rows x 64 cols per tile, 4 cols per thread
-  for (int r0 = r_begin; r0 < r_end; r0 += 16) {
-    const int r = r0 + l_r;
+    for (int q = 0; q < 4; ++q) acc[i][q] = 0ull;
+  // loaders: G tile 16 rows x 128 n -> 2 float4 per thread; A tile 16 rows x 64 k -> 1 float4 per thread
+  const int g_r = tid >> 4, g_c = (tid & 15) * 4;        // + 64 for the second half
+  const int a_r = tid >> 4, a_c = (tid & 15) * 4;
+  const bool g_vec = (g.ldg & 3) == 0 && (reinterpret_cast<uintptr_t>(g.G) & 15) == 0;
+  const bool a_vec = (g.lda & 3) == 0 && (reinterpret_cast<uintptr_t>(g.A) & 15) == 0;
+  float4 rg[2], ra;
+  auto fetch = [&](int r0) {
+    const int r = r0 + g_r;
     const bool r_ok = r < r_end;
-    const int t = r_ok ? r % g.T : 0;
-    const bool a_ok = r_ok && (t + shift) >= 0 && (t + shift) < g.T;
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int n = n0 + l_c + q, k = k0 + l_c + q;
-      Gs[l_r][l_c + q] = (r_ok && n < g.N) ? __ldg(g.G + (long long)r * g.ldg + n) : 0.f;
-      As[l_r][l_c + q] = (a_ok && k < g.K) ? __ldg(g.A + (long long)(r + shift) * g.lda + k) : 0.f;
+    for (int h = 0; h < 2; ++h) {
+      const int n = n0 + g_c + 64 * h;
+      const float* q = g.G + (long long)r * g.ldg + n;
+      if (r_ok && g_vec && n + 3 < g.N) rg[h] = __ldg(reinterpret_cast<const float4*>(q));
+      else {
+        rg[h].x = (r_ok && n + 0 < g.N) ? __ldg(q + 0) : 0.f;
+        rg[h].y = (r_ok && n + 1 < g.N) ? __ldg(q + 1) : 0.f;
+        rg[h].z = (r_ok && n + 2 < g.N) ? __ldg(q + 2) : 0.f;
+        rg[h].w = (r_ok && n + 3 < g.N) ? __ldg(q + 3) : 0.f;
+      }
     }
+    const int t = r_ok ? r % g.T : -(1 << 30);
+    const bool ok = (t + shift) >= 0 && (t + shift) < g.T;
+    const int k = k0 + a_c;
+    const float* q = g.A + (long long)(r + shift) * g.lda + k;
+    if (ok && a_vec && k + 3 < g.K) ra = __ldg(reinterpret_cast<const float4*>(q));
+    else {
+      ra.x = (ok && k + 0 < g.K) ? __ldg(q + 0) : 0.f;
+      ra.y = (ok && k + 1 < g.K) ? __ldg(q + 1) : 0.f;
+      ra.z = (ok && k + 2 < g.K) ? __ldg(q + 2) : 0.f;
+      ra.w = (ok && k + 3 < g.K) ? __ldg(q + 3) : 0.f;
+    }
+  };
+  if (r_begin < r_end) fetch(r_begin);
+  for (int r0 = r_begin; r0 < r_end; r0 += kGK) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) *reinterpret_cast<float4*>(&Gs[g_r][g_c + 64 * h]) = rg[h];
+    As[a_r][a_c + 0] = make_float2(ra.x, ra.x); As[a_r][a_c + 1] = make_float2(ra.y, ra.y);
+    As[a_r][a_c + 2] = make_float2(ra.z, ra.z); As[a_r][a_c + 3] = make_float2(ra.w, ra.w);
     __syncthreads();
+    if (r0 + kGK < r_end) fetch(r0 + kGK);
 #pragma unroll
-    for (int rr = 0; rr < 16; ++rr) {
-      const float4 a = *reinterpret_cast<const float4*>(&Gs[rr][ty * 4]);
-      const float4 b = *reinterpret_cast<const float4*>(&As[rr][tx * 4]);
-      const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int q = 0; q < 4; ++q) acc[i][q] = fmaf(av[i], bv[q], acc[i][q]);
-    }
+    for (int rr = 0; rr < kGK; ++rr) micro_step<kGM>(Gs, As, rr, ty, tx, acc);
     __syncthreads();
   }
   float* wp = g.dW + j * g.w_tap_stride;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const int n = n0 + ty * 4 + i;
-    if (n >= g.N) continue;
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int k = k0 + tx * 4 + q;
-      if (k < g.K) atomicAdd(wp + (long long)n * g.K + k, acc[i][q]);
+    for (int half = 0; half < 2; ++half) {
+      const int n = n0 + ty * 8 + 2 * i + half;
+      if (n >= g.N) continue;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int k = k0 + tx * 4 + q;
+        const float2 pr = unpack2(acc[i][q]);
+        if (k < g.K) atomicAdd(wp + (long long)n * g.K + k, half ? pr.y : pr.x);
+      }
     }
   }
 }
@@ -646,25 +757,34 @@ struct ModalBuf {
   float* z;                       // [R][C] (modality 0: inside `cat`, leading dimension ld_z)
   int ld_z;
   float *qkv, *gqkv;              // [R][3*md]
+  float *ga, *gb, *gc, *gd;       // backward ping-pong [R][max C of this modality] (modalities run concurrently)
 };
 
 inline size_t align_up(size_t x) { return (x + 255) & ~size_t(255); }
 
 int launch_row_gemm(const RowGemm& g, bool b_kn, cudaStream_t st) {
-  dim3 grid((g.N + 63) / 64, (g.R + 63) / 64);
-  if (b_kn) row_gemm_kernel<true><<<grid, 256, 0, st>>>(g);
-  else row_gemm_kernel<false><<<grid, 256, 0, st>>>(g);
+  const int nt = (g.N + kGN - 1) / kGN;
+  const bool big = (long long)((g.R + 127) / 128) * nt >= 2 * 148;      // enough 128-row tiles for two waves
+  if (big) {
+    dim3 grid(nt, (g.R + 127) / 128);
+    if (b_kn) row_gemm_kernel<true, 128><<<grid, 256, 0, st>>>(g);
+    else row_gemm_kernel<false, 128><<<grid, 256, 0, st>>>(g);
+  } else {
+    dim3 grid(nt, (g.R + 63) / 64);
+    if (b_kn) row_gemm_kernel<true, 64><<<grid, 128, 0, st>>>(g);
+    else row_gemm_kernel<false, 64><<<grid, 128, 0, st>>>(g);
+  }
   CER_CUDA(cudaGetLastError());
   return CER_OK;
 }
 
 int launch_wgrad(WGrad g, int num_sms, cudaStream_t st) {
-  g.k_tiles = (g.K + 63) / 64;
-  const int tiles = g.k_tiles * g.taps * ((g.N + 63) / 64);
-  int splits = std::max(1, std::min((4 * num_sms + tiles - 1) / tiles, (g.R + 255) / 256));
+  g.k_tiles = (g.K + kGN - 1) / kGN;
+  const int tiles = g.k_tiles * g.taps * ((g.N + kGM - 1) / kGM);
+  int splits = std::max(1, std::min((3 * num_sms + tiles - 1) / tiles, (g.R + 255) / 256));
   g.rows_per_split = (((g.R + splits - 1) / splits) + 15) / 16 * 16;
   splits = (g.R + g.rows_per_split - 1) / g.rows_per_split;
-  dim3 grid(g.k_tiles * g.taps, (g.N + 63) / 64, splits);
+  dim3 grid(g.k_tiles * g.taps, (g.N + kGM - 1) / kGM, splits);
   wgrad_kernel<<<grid, 256, 0, st>>>(g);
   CER_CUDA(cudaGetLastError());
   return CER_OK;
@@ -696,7 +816,8 @@ struct cer_head_train {
   int B, T, R, E, md3, num_sms;
   std::vector<ModalBuf> mod;
   float *vals, *o, *ln_mean, *ln_rstd, *cat, *gcat, *go, *gvals;
-  float *ga, *gb, *gc, *gd;       // backward ping-pong [R][max C]
+  cudaStream_t side[CER_MAX_MODALS];      // modality m > 0 runs on side[m]; modality 0 on the caller's stream
+  cudaEvent_t ev_fork, ev_join[CER_MAX_MODALS];
   float* scratch_zero; size_t scratch_zero_bytes;    // all dw_eff buffers, zeroed per backward
   uint32_t seed;                  // seed of the last forward (backward re-derives the masks)
   int ld_cat;
@@ -750,13 +871,15 @@ static size_t plan_layout(const cer_head_train_spec* s, int64_t B, int64_t T, ce
     mb.bn_mean = take(C); mb.bn_invstd = take(C);
     if (m == 0) { mb.z = cat; mb.ld_z = c0 + E; } else { mb.z = take(R * C); mb.ld_z = C; }
     mb.qkv = take(R * md3); mb.gqkv = take(R * md3);
+    int mc = md3;
+    for (int i = 0; i < s->modal[m].n_blocks; ++i) mc = std::max(mc, std::max(s->modal[m].blocks[i].c_in, s->modal[m].blocks[i].c_out));
+    mb.ga = take(R * mc); mb.gb = take(R * mc); mb.gc = take(R * mc); mb.gd = take(R * mc);
     if (p) p->mod[m] = mb;
   }
   float* vals = take(R * E); float* o = take(R * E); float* lm = take(R); float* lr = take(R);
   float* gcat = take(R * (c0 + E)); float* go = take(R * E); float* gvals = take(R * E);
-  float* ga = take(R * maxc); float* gb = take(R * maxc); float* gc = take(R * maxc); float* gd = take(R * maxc);
-  if (p) { p->vals = vals; p->o = o; p->ln_mean = lm; p->ln_rstd = lr; p->gcat = gcat; p->go = go; p->gvals = gvals;
-           p->ga = ga; p->gb = gb; p->gc = gc; p->gd = gd; }
+  (void)maxc;
+  if (p) { p->vals = vals; p->o = o; p->ln_mean = lm; p->ln_rstd = lr; p->gcat = gcat; p->go = go; p->gvals = gvals; }
   return off + 256;
 }
 
@@ -784,11 +907,26 @@ extern "C" int cer_head_train_create(cer_head_train** out, const cer_head_train_
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(workspace_dev) + 255) & ~uintptr_t(255));
   plan_layout(s, batch, length, p, base);
   p->seed = 0;
+  for (int m = 0; m < CER_MAX_MODALS; ++m) { p->side[m] = nullptr; p->ev_join[m] = nullptr; }
+  p->ev_fork = nullptr;
+  CER_CUDA(cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming));
+  for (int m = 1; m < s->n_modals; ++m) {
+    CER_CUDA(cudaStreamCreateWithFlags(&p->side[m], cudaStreamNonBlocking));
+    CER_CUDA(cudaEventCreateWithFlags(&p->ev_join[m], cudaEventDisableTiming));
+  }
   *out = p;
   return CER_OK;
 }
 
-extern "C" void cer_head_train_destroy(cer_head_train* p) { delete p; }
+extern "C" void cer_head_train_destroy(cer_head_train* p) {
+  if (!p) return;
+  for (int m = 1; m < CER_MAX_MODALS; ++m) {
+    if (p->side[m]) cudaStreamDestroy(p->side[m]);
+    if (p->ev_join[m]) cudaEventDestroy(p->ev_join[m]);
+  }
+  if (p->ev_fork) cudaEventDestroy(p->ev_fork);
+  delete p;
+}
 
 #define RC(x) do { int _rc = (x); if (_rc) return _rc; } while (0)
 
@@ -798,11 +936,17 @@ extern "C" int cer_head_train_forward(cer_head_train* p, const float* const* fea
   const cer_head_train_spec& s = p->s;
   const int R = p->R, T = p->T, k = s.kernel_size;
   p->seed = seed;
+  cudaStream_t main_st = st;
+  // the modalities are independent until the attention: run them concurrently (each TCN alone has too
+  // few tiles to fill 148 SMs), modality 0 on the caller's stream, the others on side streams
+  CER_CUDA(cudaEventRecord(p->ev_fork, main_st));
   for (int m = 0; m < s.n_modals; ++m) {
     const cer_train_modal& M = s.modal[m];
     ModalBuf& mb = p->mod[m];
     const float* x = feats[m];
     if (!x) return set_error(CER_ERR_INVALID, "cer_head_train_forward: null feature pointer");
+    st = m == 0 ? main_st : p->side[m];
+    if (m > 0) CER_CUDA(cudaStreamWaitEvent(st, p->ev_fork, 0));
     for (int i = 0; i < M.n_blocks; ++i) {
       const cer_train_block& b = M.blocks[i];
       BlockBuf& bb = mb.blk[i];
@@ -841,7 +985,10 @@ extern "C" int cer_head_train_forward(cer_head_train* p, const float* const* fea
     q.R = R; q.T = T; q.taps = 1; q.A = mb.z; q.lda = mb.ld_z; q.K = C; q.B = M.wqkv; q.C = mb.qkv; q.ldc = p->md3;
     q.N = p->md3; q.bias = M.bqkv; q.epi = EPI_LINEAR;
     RC(launch_row_gemm(q, false, st));
+    if (m > 0) CER_CUDA(cudaEventRecord(p->ev_join[m], st));
   }
+  st = main_st;
+  for (int m = 1; m < s.n_modals; ++m) CER_CUDA(cudaStreamWaitEvent(st, p->ev_join[m], 0));
   AttnArgs a{};
   for (int m = 0; m < s.n_modals; ++m) a.qkv[m] = p->mod[m].qkv;
   a.vals = p->vals; a.R = R; a.M = s.n_modals; a.H = s.num_heads; a.hd = s.modal_dim / s.num_heads;
@@ -895,31 +1042,35 @@ extern "C" int cer_head_train_backward(cer_head_train* p, const float* const* fe
     attn_bwd_kernel<<<(R * a.H + 127) / 128, 128, 0, st>>>(a);
     CER_CUDA(cudaGetLastError()); }
 
+  cudaStream_t main_st = st;
+  CER_CUDA(cudaEventRecord(p->ev_fork, main_st));
   for (int m = 0; m < s.n_modals; ++m) {
     const cer_train_modal& M = s.modal[m];
     ModalBuf& mb = p->mod[m];
     const int C = M.blocks[M.n_blocks - 1].c_out;
+    st = m == 0 ? main_st : p->side[m];
+    if (m > 0) CER_CUDA(cudaStreamWaitEvent(st, p->ev_fork, 0));
     // qkv projection
     { WGrad w{}; w.G = mb.gqkv; w.ldg = p->md3; w.A = mb.z; w.lda = mb.ld_z; w.dW = M.dwqkv; w.R = R; w.T = T; w.N = p->md3;
       w.K = C; w.taps = 1; RC(launch_wgrad(w, sms, st)); }
     RC(launch_colsum(mb.gqkv, p->md3, R, p->md3, M.dbqkv, st));
-    float* gz = p->ga;        // [R][C]
+    float* gz = mb.ga;        // [R][C]
     { RowGemm g{}; g.R = R; g.T = T; g.taps = 1; g.A = mb.gqkv; g.lda = p->md3; g.K = p->md3; g.B = M.wqkv; g.C = gz; g.ldc = C;
       g.N = C; g.epi = EPI_LINEAR;
       if (m == 0) { g.addend = p->gcat; g.ld_add = p->ld_cat; }        // the leader also feeds the classifier directly
       RC(launch_row_gemm(g, true, st)); }
     // BatchNorm1d
-    float* gy = p->gb;
+    float* gy = mb.gb;
     bn_train_bwd_kernel<<<(C + 31) / 32, dim3(32, 8), 0, st>>>(gz, C, mb.blk[M.n_blocks - 1].y, C, R, C, M.bn_w, mb.bn_mean,
                                                                 mb.bn_invstd, gy, C, M.dbn_w, M.dbn_b);
     CER_CUDA(cudaGetLastError());
-    float* spare = p->ga;     // gz is dead from here on
+    float* spare = mb.ga;     // gz is dead from here on
     for (int i = M.n_blocks - 1; i >= 0; --i) {
       const cer_train_block& b = M.blocks[i];
       BlockBuf& bb = mb.blk[i];
       const float* x = i == 0 ? feats[m] : mb.blk[i - 1].y;
-      float* gpre = p->gc;
-      float* ga2 = p->gd;
+      float* gpre = mb.gc;
+      float* ga2 = mb.gd;
       const long long tot = (long long)R * b.c_out;
       block_bwd_pre_kernel<<<(int)std::min<long long>((tot + 255) / 256, 8LL * sms), 256, 0, st>>>(
           gy, bb.y, bb.h2d, gpre, ga2, tot, make_drop(s.p_tcn, seed, m * 16 + i * 2 + 1));
@@ -968,7 +1119,9 @@ extern "C" int cer_head_train_backward(cer_head_train* p, const float* const* fe
       spare = gy;              // ga1's buffer is free again after the next block's pre-stage reads gx
       gy = gx;
     }
+    if (m > 0) CER_CUDA(cudaEventRecord(p->ev_join[m], st));
   }
+  for (int m = 1; m < s.n_modals; ++m) CER_CUDA(cudaStreamWaitEvent(main_st, p->ev_join[m], 0));
   return CER_OK;
 }
 
