@@ -130,6 +130,10 @@ SIGNATURES = {
     "cer_preproc_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_size_t]),
     "cer_preproc_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "cer_preproc_destroy": (None, [C.c_void_p]),
+    "cer_logmel_num_frames": (C.c_int64, [C.c_int64, C.c_int32, C.c_int32]),
+    "cer_logmel_forward": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_double,
+                                     C.c_void_p, C.c_void_p]),
+    "cer_frame_examples": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "cer_stitch_windows": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int64,
                                      C.c_void_p, C.c_void_p]),
 }

@@ -309,6 +309,47 @@ class PreprocEngine:
             self._h = None
 
 
+class LogMelEngine:
+    """Waveform -> VGGish input examples on the device (cer_logmel_forward + cer_frame_examples).
+    ``examples(wave, window_sec, hop_sec)`` mirrors vggish_input.waveform_to_examples for mono
+    16 kHz input (hop_sec = 1/fps gives one [96,64] example per video frame, audio.py:126-127)."""
+
+    def __init__(self, device: torch.device, cfg: Optional[dict] = None):
+        _capi.require_gpu()
+        from . import packing
+        self.cfg = dict(cfg or packing.LOGMEL)
+        self.device = torch.device(device)
+        self._tables = packing.logmel_tables(self.cfg).to(self.device)
+
+    def log_mel(self, wave: torch.Tensor) -> torch.Tensor:
+        """wave fp32 [n_samples] on the device -> log-mel fp32 [n_frames, n_mel]."""
+        if wave.dim() != 1 or wave.dtype != torch.float32 or wave.device != self.device:
+            raise ValueError("wave must be a 1-D fp32 tensor on the engine's CUDA device")
+        wave = wave.contiguous()
+        c = self.cfg
+        n = int(lib().cer_logmel_num_frames(wave.numel(), c["win"], c["hop"]))
+        out = torch.empty(n, c["n_mel"], dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            check(lib().cer_logmel_forward(wave.data_ptr(), wave.numel(), self._tables.data_ptr(), c["win"], c["hop"], c["fft"],
+                                           c["n_mel"], c["log_offset"], out.data_ptr(), _capi.current_stream_ptr()),
+                  "cer_logmel_forward")
+        return out
+
+    def examples(self, wave: torch.Tensor, window_sec: float = 0.96, hop_sec: float = 0.96) -> torch.Tensor:
+        lm = self.log_mel(wave)
+        rate = 1.0 / (self.cfg["hop"] / self.cfg["sample_rate"])
+        win = int(round(window_sec * rate))
+        hop = hop_sec * rate
+        import math
+        n = 1 + int(math.floor((lm.shape[0] - win) / hop)) if lm.shape[0] >= win else 0
+        starts = torch.tensor([round(hop * i) for i in range(n)], dtype=torch.int32).to(self.device)   # Python round, as my_frame
+        out = torch.empty(n, win, self.cfg["n_mel"], dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            check(lib().cer_frame_examples(lm.data_ptr(), starts.data_ptr(), n, win, self.cfg["n_mel"], out.data_ptr(),
+                                           _capi.current_stream_ptr()), "cer_frame_examples")
+        return out
+
+
 def stitch_windows(win_logits: torch.Tensor, win_start: torch.Tensor, length: int) -> torch.Tensor:
     """win_logits [n_win, win_len, n_out] fp32, win_start int32 [n_win] -> [length, n_out] mean over
     the windows covering each frame (trainer.py:864-890)."""

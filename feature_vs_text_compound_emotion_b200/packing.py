@@ -216,3 +216,28 @@ def pack_vggish(sd: Dict[str, torch.Tensor], prefix: str = "", in_hw=(96, 64),
     width = max([c["cout"] for c in convs] + [f["out_dim"] for f in fcs])
     return {"in_h": in_hw[0], "in_w": in_hw[1], "c1": int(conv1[0].shape[1]), "conv1_w": conv1[0], "conv1_bias": conv1[1],
             "convs": convs, "fcs": fcs, "zeros": torch.zeros(width), "emb_dim": fcs[-1]["out_dim"]}
+
+
+# VGGish front-end parameters (abaw5_pre_processing/base/vggish/vggish_params.py)
+LOGMEL = {"sample_rate": 16000, "win": 400, "hop": 160, "fft": 512, "n_mel": 64, "mel_lo": 125.0, "mel_hi": 7500.0,
+          "log_offset": 0.01}
+
+
+def logmel_tables(cfg: dict = None) -> torch.Tensor:
+    """fp64 [win | fft | fft | (fft/2+1)*n_mel]: periodic Hann window, cos/sin twiddles and the HTK
+    mel matrix (mel_features.py:66-90, :129-204) for cer_logmel_forward."""
+    import numpy as np
+    c = cfg or LOGMEL
+    win, fft, n_mel = c["win"], c["fft"], c["n_mel"]
+    hann = 0.5 - 0.5 * np.cos(2 * np.pi / win * np.arange(win))
+    ang = 2 * np.pi * np.arange(fft) / fft
+    bins = fft // 2 + 1
+    mel = lambda f: 1127.0 * np.log(1.0 + f / 700.0)
+    bins_mel = mel(np.linspace(0.0, c["sample_rate"] / 2.0, bins))
+    edges = np.linspace(mel(c["mel_lo"]), mel(c["mel_hi"]), n_mel + 2)
+    m = np.empty((bins, n_mel))
+    for i in range(n_mel):
+        lo, ce, up = edges[i:i + 3]
+        m[:, i] = np.maximum(0.0, np.minimum((bins_mel - lo) / (ce - lo), (up - bins_mel) / (up - ce)))
+    m[0, :] = 0.0
+    return torch.from_numpy(np.concatenate([hann, np.cos(ang), np.sin(ang), m.reshape(-1)]))

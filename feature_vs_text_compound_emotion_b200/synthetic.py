@@ -227,3 +227,17 @@ def raw_frames_u8(n: int, seed: int = 1234, h: int = 256, w: int = 256) -> torch
     base = 127.5 + 80 * torch.sin(yy * fy + xx * fx + ph)
     noise = torch.randint(-40, 41, (n, h, w, 3), generator=g).float()
     return (base + noise).clamp(0, 255).to(torch.uint8)
+
+
+def waveform(seconds: float, seed: int = 1234, sample_rate: int = 16000) -> torch.Tensor:
+    """Mono speech-like test signal in [-1, 1]: a few drifting harmonics, an amplitude envelope with
+    pauses, and noise.  fp32 [seconds * sample_rate]."""
+    g = torch.Generator().manual_seed(seed)
+    n = int(round(seconds * sample_rate))
+    t = torch.arange(n, dtype=torch.float64) / sample_rate
+    f0 = 120.0 + 40.0 * torch.sin(2 * torch.pi * 0.7 * t)
+    phase = 2 * torch.pi * torch.cumsum(f0, 0) / sample_rate
+    sig = sum(a * torch.sin(h * phase) for h, a in ((1, 0.35), (2, 0.2), (3, 0.12), (5, 0.06), (9, 0.03)))
+    env = (torch.sin(2 * torch.pi * 1.3 * t) > -0.3).double() * (0.6 + 0.4 * torch.sin(2 * torch.pi * 0.21 * t))
+    noise = 0.02 * torch.randn(n, generator=g, dtype=torch.float64)
+    return (sig * env + noise).clamp(-1, 1).float()

@@ -46,6 +46,22 @@ def preprocess_frames(model, frames_u8: torch.Tensor, resize: int = 48, crop: in
     return cache[key].forward(frames_u8)
 
 
+def wave_to_examples(model, wave: torch.Tensor, n_frames: int, fps: float = 30.0) -> torch.Tensor:
+    """Mono 16 kHz waveform on the GPU -> [n_frames, 96, 64] VGGish examples, one per video frame
+    (0.96 s window, hop 1/fps; vggish_input.py:37-95 incl. the one second of edge padding :93; the
+    last example is repeated if the audio track is shorter than the video)."""
+    from .engine import LogMelEngine
+    eng = model.__dict__.get("_logmel")
+    if eng is None or eng.device != wave.device:
+        eng = model.__dict__["_logmel"] = LogMelEngine(wave.device)
+    sr = eng.cfg["sample_rate"]
+    wave = torch.cat([wave.float(), wave[-1:].float().expand(sr)])
+    ex = eng.examples(wave, 0.96, 1.0 / fps)
+    if ex.shape[0] < n_frames:
+        ex = torch.cat([ex, ex[-1:].expand(n_frames - ex.shape[0], -1, -1)])
+    return ex[:n_frames].contiguous()
+
+
 def video_level_prediction(frame_logits: torch.Tensor, ignore_last_class: bool = False) -> Dict[str, int]:
     """The three video-level decision rules of metrics.py:88-145 (format_trg_pred_video) on
     per-frame logits [T, n_cls]: FRAMES_VOTE (majority of per-frame argmax; ties go to the class
@@ -66,12 +82,13 @@ def video_level_prediction(frame_logits: torch.Tensor, ignore_last_class: bool =
 
 @torch.no_grad()
 def infer_video(model, video: torch.Tensor, feats: Dict[str, torch.Tensor], window_length: int = 300,
-                hop_length: int = 200) -> torch.Tensor:
+                hop_length: int = 200, fps: float = 30.0) -> torch.Tensor:
     """One whole video through the LFAN mirror.
 
     video: [T,3,40,40] fp32 on the GPU (post eval-transform) or the stored uint8 [T,H,W,3] crops
     (then base/dataset.py:503-510 runs on the device, engine.PreprocEngine); feats[m]: [T, D_m] for
-    the non-visual modalities ('logmel': [T,96,64] examples, encoded by the VGGish kernels).  Returns per-frame logits [T, n_out] = the reference's stitched output.
+    the non-visual modalities ('logmel': [T,96,64] examples, encoded by the VGGish kernels; or
+    'wave': the mono 16 kHz waveform, turned into one example per frame at ``fps`` on the device).  Returns per-frame logits [T, n_out] = the reference's stitched output.
     """
     from .engine import stitch_windows
     T = video.shape[0]
@@ -84,7 +101,8 @@ def infer_video(model, video: torch.Tensor, feats: Dict[str, torch.Tensor], wind
         if m == "video":
             src = emb
         elif m == "logmel":
-            src = model.spatial["audio"](feats[m])              # one example per frame (audio.py:126-127)
+            ex = feats[m] if m in feats else wave_to_examples(model, feats["wave"], T, fps)
+            src = model.spatial["audio"](ex)                    # one example per frame (audio.py:126-127)
         else:
             src = feats[m]
         batch[m] = gather_windows(src, starts, window_length).contiguous()

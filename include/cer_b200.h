@@ -140,6 +140,23 @@ int64_t cer_vggish_launches(const cer_vggish* plan, int64_t n_patches);
 void cer_vggish_destroy(cer_vggish* plan);
 
 /* ------------------------------------------------------------------------------------------
+ * Log-mel front end of the inline-VGGish modality.   Replaces log_mel_spectrogram /
+ * stft_magnitude / periodic_hann / spectrogram_to_mel_matrix (abaw5_pre_processing/base/vggish/
+ * mel_features.py:92-236) and the example framing my_frame (:21-46; vggish_input.py:70-79).
+ * fp64 arithmetic like the numpy reference, fp32 output.
+ * wave_dev: fp32 mono samples at the VGGish rate (16 kHz); tables_dev: fp64
+ *   [win] periodic Hann | [fft] cos(2 pi i/fft) | [fft] sin(2 pi i/fft) | [fft/2+1][n_mel] mel matrix
+ *   (built on the host by packing.logmel_tables with the reference's formulas);
+ * logmel_out_dev: fp32 [cer_logmel_num_frames(n_samples, win, hop)][n_mel] = log(mel + log_offset).
+ * cer_frame_examples: out[e][t][:] = logmel[starts[e] + t][:], e < n_examples, t < frames_per_example.
+ * ------------------------------------------------------------------------------------------ */
+int64_t cer_logmel_num_frames(int64_t n_samples, int32_t win, int32_t hop);
+int cer_logmel_forward(const float* wave_dev, int64_t n_samples, const double* tables_dev, int32_t win, int32_t hop,
+                       int32_t fft, int32_t n_mel, double log_offset, float* logmel_out_dev, void* stream);
+int cer_frame_examples(const float* logmel_dev, const int32_t* starts_dev, int32_t n_examples, int32_t frames_per_example,
+                       int32_t n_mel, float* out_dev, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * One TemporalBlock, fused.   Replaces TemporalBlock.forward
  * (models/temporal_convolutional_model.py:21-54): weight-normed dilated Conv1d + Chomp1d +
  * LeakyReLU, twice, plus identity / 1x1 residual and the final LeakyReLU.  Optionally applies a

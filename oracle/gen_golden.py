@@ -13,6 +13,7 @@ reference modules, imported as they are, are the source of truth):
   * lfan_logmel_b1.pt -- LFAN(video,logmel,bert) forward from pixels and log-mel, B=1 x T=40
   * train_b2.pt     -- two SGD-nesterov steps of the head in train mode (Dropout p=0): loss, gradients, BN stats
   * eval_transform.pt -- the reference's eval transform classes (PIL resize 48, crop 40, normalise) on seeded uint8 frames
+  * logmel.pt       -- mel_features.log_mel_spectrogram + my_frame (the reference code) on a seeded 3 s waveform
   * windowing.json  -- Trainer.windowing outputs for a set of lengths
 Weights are NOT stored: they are regenerated from the seed by
 feature_vs_text_compound_emotion_b200.synthetic (identical on every machine), and are loaded
@@ -185,6 +186,20 @@ def main():
     import PIL
     torch.save({"cases": cases, "pillow": PIL.__version__}, os.path.join(OUT, "eval_transform.pt"))
     print("eval transform", {k: tuple(v["out"].shape) for k, v in cases.items()}, "Pillow", PIL.__version__)
+
+    # ---- log-mel front end (abaw5_pre_processing/base/vggish/mel_features.py), reference code itself ----
+    sys.path.insert(0, os.path.join(REF, "abaw5_pre_processing"))
+    from base.vggish import mel_features as MF
+    wave = synthetic.waveform(3.0, seed=601)
+    lm = MF.log_mel_spectrogram(wave.double().numpy(), audio_sample_rate=16000, log_offset=0.01, window_length_secs=0.025,
+                                hop_length_secs=0.010, num_mel_bins=64, lower_edge_hertz=125, upper_edge_hertz=7500)
+    hop_sec = 1.0 / 30.0                                   # one example per video frame at 30 fps (audio.py:126-127)
+    ex = MF.my_frame(lm, window_length=96, hop_length=hop_sec * 100.0)
+    torch.save({"seconds": 3.0, "seed": 601, "hop_sec": hop_sec, "log_mel": torch.from_numpy(lm).float(),
+                "n_examples": int(ex.shape[0]), "example_sum": torch.from_numpy(ex.sum(axis=(1, 2))),
+                "example_7": torch.from_numpy(ex[7]).float(), "example_last": torch.from_numpy(ex[-1]).float()},
+               os.path.join(OUT, "logmel.pt"))
+    print("logmel", lm.shape, ex.shape)
 
     # ---- windowing (trainer.py imports pynvml/munch, absent here: exec the one function) ----
     src = open(os.path.join(REF, "trainer.py")).read()

@@ -510,3 +510,55 @@ def video_level_prediction(logits: np.ndarray, ignore_last_class: bool = False) 
     probs = e / np.sum(e, axis=1).reshape((-1, 1))
     return {"FRAMES_VOTE": int(vote), "FRAMES_AVG_LOGITS": int(np.argmax(lg.mean(axis=0))),
             "FRAMES_AVG_PROBS": int(np.argmax(probs.mean(axis=0)))}
+
+
+# --------------------------------------------------------------------------------------
+# Log-mel front end of the inline-VGGish modality
+# (abaw5_pre_processing/base/vggish/mel_features.py:92-236, vggish_input.py:37-95,
+#  vggish_params.py: 16 kHz, 25 ms periodic-Hann window, 10 ms hop, 512-point FFT, 64 mel bands
+#  125-7500 Hz (HTK), log(mel + 0.01), examples of 96 frames)
+# --------------------------------------------------------------------------------------
+VGGISH_SR, VGGISH_WIN, VGGISH_HOP, VGGISH_FFT = 16000, 400, 160, 512
+VGGISH_MEL_BINS, VGGISH_MEL_LO, VGGISH_MEL_HI, VGGISH_LOG_OFFSET = 64, 125.0, 7500.0, 0.01
+
+
+def mel_matrix(num_mel_bins=VGGISH_MEL_BINS, num_spectrogram_bins=VGGISH_FFT // 2 + 1, sample_rate=VGGISH_SR,
+               lower_hz=VGGISH_MEL_LO, upper_hz=VGGISH_MEL_HI) -> np.ndarray:
+    """spectrogram_to_mel_matrix (mel_features.py:129-204): triangular bands, linear in HTK-mel
+    (1127 ln(1 + f/700)), DC bin zeroed.  float64 [bins, mel]."""
+    mel = lambda f: 1127.0 * np.log(1.0 + f / 700.0)
+    bins_mel = mel(np.linspace(0.0, sample_rate / 2.0, num_spectrogram_bins))
+    edges = np.linspace(mel(lower_hz), mel(upper_hz), num_mel_bins + 2)
+    m = np.empty((num_spectrogram_bins, num_mel_bins))
+    for i in range(num_mel_bins):
+        lo, ce, up = edges[i:i + 3]
+        m[:, i] = np.maximum(0.0, np.minimum((bins_mel - lo) / (ce - lo), (up - bins_mel) / (up - ce)))
+    m[0, :] = 0.0
+    return m
+
+
+def log_mel_spectrogram(wave: np.ndarray) -> np.ndarray:
+    """log_mel_spectrogram (mel_features.py:207-236) with the VGGish parameters: complete frames
+    only (no padding), periodic Hann, |rfft(512)|, mel matrix, log(. + 0.01).  float64 [frames, 64]."""
+    wave = np.asarray(wave, dtype=np.float64)
+    n_frames = 1 + int(np.floor((wave.shape[0] - VGGISH_WIN) / VGGISH_HOP))
+    idx = np.arange(VGGISH_WIN)[None, :] + VGGISH_HOP * np.arange(n_frames)[:, None]
+    window = 0.5 - 0.5 * np.cos(2 * np.pi / VGGISH_WIN * np.arange(VGGISH_WIN))
+    spec = np.abs(np.fft.rfft(wave[idx] * window, VGGISH_FFT))
+    return np.log(spec @ mel_matrix() + VGGISH_LOG_OFFSET)
+
+
+def example_starts(n_logmel_frames: int, window_sec: float, hop_sec: float):
+    """my_frame's indexing (mel_features.py:21-46, vggish_input.py:70-79): examples of
+    round(window_sec*100) frames, example i starts at Python-round(hop_sec*100 * i)."""
+    win = int(round(window_sec * (1.0 / 0.010)))
+    hop = hop_sec * (1.0 / 0.010)
+    n = 1 + int(np.floor((n_logmel_frames - win) / hop))
+    return [round(hop * i) for i in range(n)], win
+
+
+def waveform_to_examples(wave: np.ndarray, window_sec: float = 0.96, hop_sec: float = 0.96) -> np.ndarray:
+    """waveform_to_examples (vggish_input.py:37-82) for mono 16 kHz input: [n_examples, 96, 64]."""
+    lm = log_mel_spectrogram(wave)
+    starts, win = example_starts(lm.shape[0], window_sec, hop_sec)
+    return np.stack([lm[s:s + win] for s in starts])

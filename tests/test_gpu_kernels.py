@@ -217,3 +217,25 @@ def test_preprocess_many_frames_vs_oracle():
     out = PreprocEngine(256, 256, dev).forward(raw.to(dev)).cpu()
     assert torch.equal(out, O.eval_transform(raw.numpy()))
     assert out[0].eq(-1).all() and out[1].eq(1).all()
+
+
+def test_logmel_front_end_vs_reference_golden(golden_dir):
+    """Waveform -> log-mel -> VGGish examples on the device (fp64 DFT) against the reference's
+    numpy code: 2e-5 absolute on log-mel values (fp32 output, fp32 fixture)."""
+    import os
+    from feature_vs_text_compound_emotion_b200.engine import LogMelEngine
+    dev = _dev()
+    g = torch.load(os.path.join(golden_dir, "logmel.pt"))
+    wave = synthetic.waveform(g["seconds"], seed=g["seed"])
+    eng = LogMelEngine(dev)
+    lm = eng.log_mel(wave.to(dev)).cpu()
+    assert lm.shape == g["log_mel"].shape
+    assert (lm - g["log_mel"]).abs().max().item() < 2e-5
+    ex = eng.examples(wave.to(dev), 0.96, g["hop_sec"]).cpu()
+    assert ex.shape == (g["n_examples"], 96, 64)
+    assert (ex[7] - g["example_7"]).abs().max().item() < 2e-5
+    assert (ex[-1] - g["example_last"]).abs().max().item() < 2e-5
+    assert (ex.double().sum(dim=(1, 2)) - g["example_sum"]).abs().max().item() < 5e-2
+    # the examples feed VGGish directly
+    want = torch.from_numpy(O.waveform_to_examples(wave.double().numpy(), 0.96, g["hop_sec"])).float()
+    assert (ex - want).abs().max().item() < 2e-5

@@ -149,3 +149,14 @@ def test_eval_transform_matches_reference(golden_dir):
         raw = synthetic.raw_frames_u8(c["n"], seed=c["seed"], h=c["h"], w=c["w"]).numpy()
         out = O.eval_transform(raw)
         assert torch.equal(out, c["out"]), name
+
+
+def test_logmel_front_end_matches_reference(golden_dir):
+    g = torch.load(os.path.join(golden_dir, "logmel.pt"))
+    wave = synthetic.waveform(g["seconds"], seed=g["seed"]).double().numpy()
+    lm = O.log_mel_spectrogram(wave)
+    assert np.abs(lm - g["log_mel"].double().numpy()).max() < 1e-5        # the fixture is stored in fp32
+    ex = O.waveform_to_examples(wave, 0.96, g["hop_sec"])
+    assert ex.shape == (g["n_examples"], 96, 64)
+    assert np.abs(ex.sum(axis=(1, 2)) - g["example_sum"].numpy()).max() < 1e-6
+    assert np.abs(ex[7] - g["example_7"].double().numpy()).max() < 1e-5
