@@ -23,10 +23,15 @@ class HostPrefetcher:
         self._free = [None] * depth                   # recorded on the compute stream after a slot was consumed
 
     def _stage(self, slot: int, host: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
-        bufs = self._slots[slot]
-        if bufs is None or any(k not in bufs or bufs[k].shape != v.shape or bufs[k].dtype != v.dtype for k, v in host.items()):
-            bufs = {k: torch.empty(v.shape, dtype=v.dtype, device=self.device) for k, v in host.items()}
-            self._slots[slot] = bufs
+        flat = self._slots[slot]
+        if flat is None:
+            flat = self._slots[slot] = {}
+        bufs = {}
+        for k, v in host.items():                      # grow-only flat device buffers, viewed at the batch's shape
+            f = flat.get(k)
+            if f is None or f.dtype != v.dtype or f.numel() < v.numel():
+                f = flat[k] = torch.empty(max(v.numel(), 1), dtype=v.dtype, device=self.device)
+            bufs[k] = f[:v.numel()].view(v.shape)
         with torch.cuda.stream(self.copy_stream):
             if self._free[slot] is not None:
                 self.copy_stream.wait_event(self._free[slot])      # the previous user of this slot is done
