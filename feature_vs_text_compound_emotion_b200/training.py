@@ -36,6 +36,20 @@ def head_parameters(model) -> List[tuple]:
     return [(k, p) for k, p in model.named_parameters() if not k.startswith("spatial.")]
 
 
+def all_reduce_flat(flat: torch.Tensor, group=None) -> float:
+    """ONE collective for the whole head: SUM all-reduce of the flat gradient bucket (any backend:
+    nccl on the GPUs, gloo in the CPU tests).  Returns 1/world, the scale the optimizer kernel
+    applies to turn the sum into the data-parallel mean; 1.0 when no process group is up."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()):
+        return 1.0
+    world = dist.get_world_size(group)
+    if world == 1:
+        return 1.0
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    return 1.0 / world
+
+
 class HeadTrainer:
     def __init__(self, model, batch: int, length: Optional[int] = None, optimizer: Optional[dict] = None,
                  seed: int = 0, process_group=None):
@@ -207,14 +221,7 @@ class HeadTrainer:
 
     def all_reduce_grads(self) -> float:
         """SUM all-reduce of the flat gradient buffer; returns the scale that makes it a mean."""
-        import torch.distributed as dist
-        if not (dist.is_available() and dist.is_initialized()):
-            return 1.0
-        world = dist.get_world_size(self.group)
-        if world == 1:
-            return 1.0
-        dist.all_reduce(self.grads, op=dist.ReduceOp.SUM, group=self.group)
-        return 1.0 / world
+        return all_reduce_flat(self.grads, self.group)
 
     def apply_optimizer(self, grad_scale: float = 1.0) -> None:
         o = self.opt

@@ -225,3 +225,41 @@ def test_host_prefetcher_matches_direct_calls():
     assert n == 5
     for i in range(5):
         assert torch.equal(got[i], want[i]), i
+
+
+def test_empty_ragged_and_short_inputs():
+    """Edge cases of the entry points: zero frames, a ragged second pass, a video shorter than one
+    window (padded by repeating its last frame, base/dataset.py:570-582), a single-frame video."""
+    dev = _dev()
+    from feature_vs_text_compound_emotion_b200 import windowing
+    from feature_vs_text_compound_emotion_b200.engine import PreprocEngine
+    from feature_vs_text_compound_emotion_b200.models.arcface_model import Backbone
+    mods = ["video", "vggish", "bert"]
+    m = _lfan(mods, dev, seed=7)
+    sd = synthetic.lfan_state_dict(7, mods)
+    vb = m.spatial["visual"]
+    assert vb(torch.empty(0, 3, 40, 40, device=dev)).shape == (0, 512)
+    assert PreprocEngine(256, 256, dev).forward(torch.empty(0, 256, 256, 3, dtype=torch.uint8, device=dev)).shape == (0, 3, 40, 40)
+    # ragged passes: 2 full passes of 16 frames + 1 frame
+    old = Backbone.frames_per_pass
+    Backbone.frames_per_pass = 16
+    try:
+        vb.backbone.repack()
+        x = synthetic.frames(33, seed=71)
+        emb = vb(x.to(dev)).cpu()
+    finally:
+        Backbone.frames_per_pass = old
+        vb.backbone.repack()
+    ref = O.ir50_forward(sd, x, "spatial.visual.backbone.")
+    assert F.cosine_similarity(emb, ref, dim=1).min().item() >= 0.999
+    # short videos
+    for L in (1, 7, 299):
+        vid = synthetic.frames(L, seed=72 + L)
+        g = torch.Generator().manual_seed(73 + L)
+        feats = {"vggish": torch.randn(L, 128, generator=g), "bert": torch.randn(L, 768, generator=g)}
+        out = windowing.infer_video(m, vid.to(dev), {k: v.to(dev) for k, v in feats.items()}).cpu()
+        assert out.shape == (L, 7)
+        emb = O.ir50_forward(sd, vid, "spatial.visual.backbone.")
+        pad = lambda t: torch.cat([t, t[-1:].expand(300 - L, -1)]).unsqueeze(0)
+        want = O.head_forward(sd, {"video": pad(emb), "vggish": pad(feats["vggish"]), "bert": pad(feats["bert"])}, mods)[0, :L]
+        assert (out - want).abs().max().item() <= 2e-2, L

@@ -83,3 +83,32 @@ def test_video_level_decision_rules_match_reference_semantics():
     for t, c in enumerate((5, 2, 2, 5)):
         lg[t, c] = 1.0
     assert windowing.video_level_prediction(lg)["FRAMES_VOTE"] == 5 == O.video_level_prediction(lg.numpy())["FRAMES_VOTE"]
+
+
+def _ar_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from feature_vs_text_compound_emotion_b200.training import all_reduce_flat
+        flat = torch.arange(1000, dtype=torch.float32) * (rank + 1)
+        scale = all_reduce_flat(flat)
+        q.put((rank, scale, bool(torch.equal(flat, torch.arange(1000, dtype=torch.float32) * 3))))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_flat_gradient_bucket_all_reduce_world_size_2_gloo():
+    """The training step's only collective: SUM over the flat bucket, 1/world returned as the scale."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_ar_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+    assert res == [(0, 0.5, True), (1, 0.5, True)]
+    from feature_vs_text_compound_emotion_b200.training import all_reduce_flat
+    assert all_reduce_flat(torch.ones(4)) == 1.0          # no process group: nothing to do
