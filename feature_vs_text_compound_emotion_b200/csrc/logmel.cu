@@ -8,7 +8,8 @@
 // 1.7 GFLOP per example) and agrees with numpy to ~1e-12 before the final cast to fp32.
 //   DFT by definition: X[k] = sum_n x[n] w[n] (cos, -sin)(2 pi k n / fft), twiddles from a table of
 //   fft entries indexed (k*n) mod fft; |X| -> mel matrix [bins][mel] -> log(. + offset).
-// One CTA per STFT frame; thread k owns spectrogram bin k, then thread j owns mel band j.
+// One CTA per 4 STFT frames (each twiddle read feeds 4 frames); thread k owns spectrogram bin k,
+// then one thread per (frame, mel band).
 #include <cuda_runtime.h>
 #include <cstdint>
 
@@ -17,40 +18,55 @@
 
 namespace cer {
 
+constexpr int kLmFrames = 4;      // STFT frames per CTA: every twiddle read from smem feeds 4 frames
+
 __global__ void __launch_bounds__(288) logmel_kernel(const float* __restrict__ wave, long long n_samples,
                                                      const double* __restrict__ tables, int win, int hop, int fft, int n_mel,
                                                      double log_offset, float* __restrict__ out, int n_frames) {
   extern __shared__ __align__(16) double sm_d[];
-  double* s_x = sm_d;                 // [win] windowed samples
-  double* s_cos = s_x + win;          // [fft]
-  double* s_sin = s_cos + fft;        // [fft]
-  double* s_mag = s_sin + fft;        // [fft/2 + 1]
+  double* s_x = sm_d;                            // [win][kLmFrames] windowed samples, frame-minor
+  double* s_cos = s_x + win * kLmFrames;         // [fft]
+  double* s_sin = s_cos + fft;                   // [fft]
+  double* s_mag = s_sin + fft;                   // [kLmFrames][fft/2 + 1]
   const int bins = fft / 2 + 1;
   const double* hann = tables;        // [win]
   const double* tcos = tables + win;  // [fft]
   const double* tsin = tcos + fft;    // [fft]
   const double* mel = tsin + fft;     // [bins][n_mel]
-  const int f = blockIdx.x;
-  const long long s0 = (long long)f * hop;
-  for (int i = threadIdx.x; i < win; i += blockDim.x) s_x[i] = (double)wave[s0 + i] * hann[i];
+  const int f0 = blockIdx.x * kLmFrames;
+  for (int i = threadIdx.x; i < win * kLmFrames; i += blockDim.x) {
+    const int n = i / kLmFrames, q = i - n * kLmFrames;
+    const int f = f0 + q;
+    s_x[i] = f < n_frames ? (double)wave[(long long)f * hop + n] * hann[n] : 0.0;
+  }
   for (int i = threadIdx.x; i < fft; i += blockDim.x) { s_cos[i] = tcos[i]; s_sin[i] = tsin[i]; }
   __syncthreads();
   for (int k = threadIdx.x; k < bins; k += blockDim.x) {
-    double re = 0.0, im = 0.0;
+    double re[kLmFrames], im[kLmFrames];
+#pragma unroll
+    for (int q = 0; q < kLmFrames; ++q) { re[q] = 0.0; im[q] = 0.0; }
     int idx = 0;                                   // (k * n) mod fft, fft is a power of two
     for (int n = 0; n < win; ++n) {
-      const double x = s_x[n];
-      re = fma(x, s_cos[idx], re);
-      im = fma(x, s_sin[idx], im);
+      const double c = s_cos[idx], sn = s_sin[idx];
+      const double2 x01 = *reinterpret_cast<const double2*>(&s_x[n * kLmFrames]);
+      const double2 x23 = *reinterpret_cast<const double2*>(&s_x[n * kLmFrames + 2]);
+      re[0] = fma(x01.x, c, re[0]); im[0] = fma(x01.x, sn, im[0]);
+      re[1] = fma(x01.y, c, re[1]); im[1] = fma(x01.y, sn, im[1]);
+      re[2] = fma(x23.x, c, re[2]); im[2] = fma(x23.x, sn, im[2]);
+      re[3] = fma(x23.y, c, re[3]); im[3] = fma(x23.y, sn, im[3]);
       idx = (idx + k) & (fft - 1);
     }
-    s_mag[k] = sqrt(re * re + im * im);
+#pragma unroll
+    for (int q = 0; q < kLmFrames; ++q) s_mag[q * bins + k] = sqrt(re[q] * re[q] + im[q] * im[q]);
   }
   __syncthreads();
-  for (int j = threadIdx.x; j < n_mel; j += blockDim.x) {
+  for (int i = threadIdx.x; i < n_mel * kLmFrames; i += blockDim.x) {
+    const int q = i / n_mel, j = i - q * n_mel;
+    if (f0 + q >= n_frames) continue;
     double acc = 0.0;
-    for (int k = 0; k < bins; ++k) acc = fma(s_mag[k], mel[(long long)k * n_mel + j], acc);
-    out[(long long)f * n_mel + j] = (float)log(acc + log_offset);
+    const double* mg = s_mag + q * bins;
+    for (int k = 0; k < bins; ++k) acc = fma(mg[k], mel[(long long)k * n_mel + j], acc);
+    out[(long long)(f0 + q) * n_mel + j] = (float)log(acc + log_offset);
   }
 }
 
@@ -83,12 +99,12 @@ extern "C" int cer_logmel_forward(const float* wave_dev, int64_t n_samples, cons
   const int64_t n_frames = cer_logmel_num_frames(n_samples, win, hop);
   if (n_frames <= 0) return CER_OK;
   if (n_frames > (1ll << 30)) return set_error(CER_ERR_INVALID, "cer_logmel_forward: too many frames");
-  const size_t smem = (size_t)(win + 2 * fft + fft / 2 + 1) * sizeof(double);
+  const size_t smem = (size_t)(win * kLmFrames + 2 * fft + kLmFrames * (fft / 2 + 1)) * sizeof(double);
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(logmel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return set_error(CER_ERR_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
   }
-  logmel_kernel<<<(int)n_frames, 288, smem, static_cast<cudaStream_t>(stream)>>>(wave_dev, n_samples, tables_dev, win, hop, fft,
+  logmel_kernel<<<(int)((n_frames + kLmFrames - 1) / kLmFrames), 288, smem, static_cast<cudaStream_t>(stream)>>>(wave_dev, n_samples, tables_dev, win, hop, fft,
                                                                                 n_mel, log_offset, logmel_out_dev, (int)n_frames);
   CER_CUDA(cudaGetLastError());
   return CER_OK;
