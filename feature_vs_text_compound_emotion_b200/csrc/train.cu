@@ -24,6 +24,7 @@
 
 #include "../../include/cer_b200.h"
 #include "common.h"
+#include "row_gemm.h"
 
 namespace cer {
 
@@ -31,15 +32,6 @@ constexpr float kLeaky = 0.01f;
 constexpr float kBnEps = 1e-5f;
 constexpr float kLnEps = 1e-5f;
 
-__host__ __device__ __forceinline__ uint32_t fmix32(uint32_t x) {
-  x ^= x >> 16; x *= 0x85EBCA6Bu; x ^= x >> 13; x *= 0xC2B2AE35u; x ^= x >> 16;
-  return x;
-}
-struct Drop {            // p == 0 <=> thr == 0 (everything kept, scale 1)
-  uint32_t key;          // seed + stream * 0x85EBCA6B
-  uint32_t thr;          // keep iff hash >= thr
-  float scale;           // 1 / (1 - p)
-};
 __device__ __forceinline__ float drop_factor(const Drop& d, uint32_t idx) {
   if (d.thr == 0) return 1.f;
   return fmix32(idx * 0x9E3779B1u + d.key) >= d.thr ? d.scale : 0.f;
@@ -55,22 +47,6 @@ __device__ __forceinline__ float lrelu_grad(float saved) { return saved > 0.f ? 
 //   B_KN = true : B_j is [K][N] row-major (the same storage read transposed: dgrad).
 // 64x64 tile, BK = 16, 256 threads, 4x4 outputs per thread.
 // ------------------------------------------------------------------------------------------
-enum Epi { EPI_LINEAR = 0, EPI_LRELU_DROP = 1, EPI_BLOCK_OUT = 2, EPI_DGRAD_ACT = 3 };
-
-struct RowGemm {
-  const float* A; int lda;
-  const float* B; long long b_tap_stride;   // elements between consecutive taps' matrices
-  float* C; int ldc;
-  int R, T, N, K;
-  int taps, shift0, shift_step;             // shift_j = shift0 + j*shift_step (rows)
-  const float* bias;                        // [N] or null
-  const float* addend; int ld_add;          // [R][N] added before the activation, or null
-  int accumulate;                           // C += result (EPI_LINEAR only)
-  int epi;
-  float* aux; int ld_aux;                   // BLOCK_OUT: h2d out; DGRAD_ACT: saved activation in
-  Drop drop;
-};
-
 // ---- shared micro-kernel: 128 x 64 outputs per CTA, 256 threads, 8 x 4 per thread, packed FP32 FMAs ----
 // Blackwell issues two fp32 FMAs per instruction (fma.rn.f32x2).  The "m" operand comes from shared
 // memory as natural pairs (rows 2i, 2i+1); the "n" operand is stored DUPLICATED ({b, b}) so that no
@@ -229,6 +205,8 @@ __global__ void __launch_bounds__(2 * BM) row_gemm_kernel(const RowGemm g) {
           if (g.addend) v += g.addend[(long long)r * g.ld_add + n];
           if (g.accumulate) v += *cp;
           *cp = v;
+        } else if (g.epi == EPI_RELU) {
+          *cp = fmaxf(v, 0.f);
         } else if (g.epi == EPI_LRELU_DROP) {
           *cp = lrelu(v) * drop_factor(g.drop, idx);
         } else if (g.epi == EPI_BLOCK_OUT) {
@@ -762,7 +740,8 @@ struct ModalBuf {
 
 inline size_t align_up(size_t x) { return (x + 255) & ~size_t(255); }
 
-int launch_row_gemm(const RowGemm& g, bool b_kn, cudaStream_t st) {
+}  // namespace
+int cer::launch_row_gemm(const RowGemm& g, bool b_kn, cudaStream_t st) {
   const int nt = (g.N + kGN - 1) / kGN;
   const bool big = (long long)((g.R + 127) / 128) * nt >= 2 * 148;      // enough 128-row tiles for two waves
   if (big) {
@@ -777,6 +756,7 @@ int launch_row_gemm(const RowGemm& g, bool b_kn, cudaStream_t st) {
   CER_CUDA(cudaGetLastError());
   return CER_OK;
 }
+namespace {
 
 int launch_wgrad(WGrad g, int num_sms, cudaStream_t st) {
   g.k_tiles = (g.K + kGN - 1) / kGN;

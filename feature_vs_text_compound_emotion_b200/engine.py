@@ -380,3 +380,57 @@ def conv_forward(src: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, ks
                                      cout, ksize, stride, pad, bias.data_ptr(), bias.shape[0], _ptr(alpha), _ptr(res),
                                      dst.data_ptr(), int(out_fp32), _capi.current_stream_ptr()), "cer_conv_forward")
     return dst
+
+
+# ----------------------------------------------------------------------------------------------
+# fp32 building blocks of the CAN / JMT / MT heads (cer_linear_forward, cer_softmax_gate,
+# cer_sdpa_forward, cer_add_layernorm).  All tensors are row-major 2-D views [rows, features].
+# ----------------------------------------------------------------------------------------------
+ACT = {None: 0, "leaky_relu": 1, "relu": 2}
+
+
+def linear(x: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor], act: Optional[str] = None,
+           out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """y = act(x W^T + b).  x [rows, in] (row stride may exceed in), w [out, in] contiguous; ``out`` may be
+    a column slice of a wider buffer (concat without a copy)."""
+    rows, k = x.shape
+    n = w.shape[0]
+    if x.stride(1) != 1 or w.stride() != (k, 1) or w.shape[1] != k:
+        raise ValueError("linear: x must be unit-stride in features and w contiguous [out, in]")
+    if out is None:
+        out = torch.empty(rows, n, dtype=torch.float32, device=x.device)
+    if out.stride(1) != 1 or out.shape != (rows, n):
+        raise ValueError("linear: bad output view")
+    with torch.cuda.device(x.device):
+        check(lib().cer_linear_forward(x.data_ptr(), rows, k, x.stride(0), w.data_ptr(), _ptr(b), n, ACT[act], out.data_ptr(),
+                                       out.stride(0), _capi.current_stream_ptr()), "cer_linear_forward")
+    return out
+
+
+def softmax_gate(gate: torch.Tensor, feat: torch.Tensor) -> torch.Tensor:
+    out = torch.empty_like(feat)
+    with torch.cuda.device(feat.device):
+        check(lib().cer_softmax_gate(gate.contiguous().data_ptr(), feat.contiguous().data_ptr(), feat.shape[0], feat.shape[1],
+                                     out.data_ptr(), _capi.current_stream_ptr()), "cer_softmax_gate")
+    return out
+
+
+def sdpa(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, batch: int, len_q: int, len_k: int) -> torch.Tensor:
+    """Single-head attention.  q [batch*len_q, E], k / v [batch*len_k, E] (column slices of a packed
+    projection are fine) -> [batch*len_q, E]."""
+    e = q.shape[1]
+    out = torch.empty(batch * len_q, e, dtype=torch.float32, device=q.device)
+    with torch.cuda.device(q.device):
+        check(lib().cer_sdpa_forward(q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), v.data_ptr(), v.stride(0), batch,
+                                     len_q, len_k, e, out.data_ptr(), e, _capi.current_stream_ptr()), "cer_sdpa_forward")
+    return out
+
+
+def add_layernorm(x: torch.Tensor, res: Optional[torch.Tensor], gamma: torch.Tensor, beta: torch.Tensor,
+                  eps: float = 1e-5) -> torch.Tensor:
+    out = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        check(lib().cer_add_layernorm(x.contiguous().data_ptr(), None if res is None else res.contiguous().data_ptr(),
+                                      x.shape[0], x.shape[1], gamma.data_ptr(), beta.data_ptr(), eps, out.data_ptr(),
+                                      _capi.current_stream_ptr()), "cer_add_layernorm")
+    return out

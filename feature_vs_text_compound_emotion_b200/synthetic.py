@@ -241,3 +241,115 @@ def waveform(seconds: float, seed: int = 1234, sample_rate: int = 16000) -> torc
     env = (torch.sin(2 * torch.pi * 1.3 * t) > -0.3).double() * (0.6 + 0.4 * torch.sin(2 * torch.pi * 0.21 * t))
     noise = 0.02 * torch.randn(n, generator=g, dtype=torch.float64)
     return (sig * env + noise).clamp(-1, 1).float()
+
+
+# configs.py:79-126 (tcn_settings used by CAN / JMT / MT)
+TCN_SETTINGS = {
+    "video": {"input_dim": 512, "channel": [256, 256, 128, 128, 128], "kernel_size": 5},
+    "cnn_res50": {"input_dim": 512, "channel": [256, 256, 128, 128], "kernel_size": 5},
+    "vggish": {"input_dim": 128, "channel": [128, 128, 64, 64], "kernel_size": 5},
+    "logmel": {"input_dim": 128, "channel": [128, 128, 64, 64, 64], "kernel_size": 5},
+    "bert": {"input_dim": 768, "channel": [256, 256, 128, 128], "kernel_size": 5},
+}
+
+
+def _tcn(sd, prefix, cin, channels, k, g):
+    """``TemporalConvNet.state_dict()`` keys under ``prefix`` (temporal_convolutional_model.py:21-75)."""
+    for i, cout in enumerate(channels):
+        p = f"{prefix}network.{i}."
+        made = {}
+        for name, ci in (("conv1", cin), ("conv2", cout)):
+            v = _uniform(g, (cout, ci, k), (ci * k) ** -0.5)
+            gn = v.reshape(cout, -1).norm(dim=1).view(cout, 1, 1) * (torch.rand(cout, 1, 1, generator=g) + 0.5)
+            made[name] = (_uniform(g, (cout,), (ci * k) ** -0.5), gn, v)
+        for nm, src in (("conv1", "conv1"), ("conv2", "conv2"), ("net.0", "conv1"), ("net.4", "conv2")):
+            sd[p + nm + ".bias"], sd[p + nm + ".weight_g"], sd[p + nm + ".weight_v"] = made[src]
+        if cin != cout:
+            sd[p + "downsample.weight"] = _uniform(g, (cout, cin, 1), cin ** -0.5)
+            sd[p + "downsample.bias"] = _uniform(g, (cout,), cin ** -0.5)
+        cin = cout
+
+
+def _linear(sd, p, fout, fin, g):
+    sd[p + ".weight"] = _uniform(g, (fout, fin), (3.0 / fin) ** 0.5)
+    sd[p + ".bias"] = 0.1 * torch.randn(fout, generator=g)
+
+
+def _mha(sd, p, e, g):
+    """nn.MultiheadAttention(e, 1): in_proj_weight [3e, e], in_proj_bias, out_proj.{weight,bias}."""
+    sd[p + ".in_proj_weight"] = _uniform(g, (3 * e, e), (3.0 / e) ** 0.5)
+    sd[p + ".in_proj_bias"] = 0.1 * torch.randn(3 * e, generator=g)
+    _linear(sd, p + ".out_proj", e, e, g)
+
+
+def _encoder_block(sd, p, e, hidden, g):
+    """TransformerEncoderBlock(e, 1, hidden, 1) (models/model.py:716-750)."""
+    q = p + ".layers.0"
+    _mha(sd, q + ".attention", e, g)
+    _linear(sd, q + ".feed_forward.0", hidden, e, g)
+    _linear(sd, q + ".feed_forward.2", e, hidden, g)
+    for n in ("layer_norm1", "layer_norm2"):
+        sd[f"{q}.{n}.weight"] = torch.rand(e, generator=g) + 0.5
+        sd[f"{q}.{n}.bias"] = 0.1 * torch.randn(e, generator=g)
+
+
+def _head_common(sd, modalities, settings, g):
+    for m in modalities:
+        _tcn(sd, f"temporal.{m}.", settings[m]["input_dim"], settings[m]["channel"], settings[m]["kernel_size"], g)
+    for m in modalities:
+        _bn(sd, f"bn.{m}", settings[m]["channel"][-1], g)
+
+
+def _spatial(sd, modalities, seed):
+    if "video" in modalities:
+        for k, v in visual_backbone_state_dict(seed).items():
+            sd["spatial.visual." + k] = v
+    if "logmel" in modalities:
+        for k, v in vggish_state_dict(seed).items():
+            sd["spatial.audio.backbone." + k] = v
+
+
+def can_state_dict(seed: int = 0, modalities: Sequence[str] = ("video", "vggish", "bert"), output_dim: int = 7,
+                   settings: Dict[str, dict] = None) -> "OrderedDict[str, torch.Tensor]":
+    """``CAN.state_dict()`` layout (models/model.py:571-622): temporal, bn, spatial, fuse.attn.<i>,
+    fuse.weights, conv_c (unused by forward), bn1, fc1, fc2."""
+    settings = settings or TCN_SETTINGS
+    g = torch.Generator().manual_seed(seed + 104729)
+    sd: "OrderedDict[str, torch.Tensor]" = OrderedDict()
+    _head_common(sd, modalities, settings, g)
+    _spatial(sd, modalities, seed)
+    n = len(modalities)
+    for i, m in enumerate(modalities):
+        _linear(sd, f"fuse.attn.{i}", 128, settings[m]["channel"][-1], g)
+    _linear(sd, "fuse.weights", 128 * n, 128 * n, g)
+    sd["conv_c.weight"] = _uniform(g, (128, 128 * n, 1), (128 * n) ** -0.5)
+    sd["conv_c.bias"] = 0.1 * torch.randn(128, generator=g)
+    _bn(sd, "bn1", 128 * n, g)
+    _linear(sd, "fc1", 128 * n, 128 * n, g)
+    _linear(sd, "fc2", output_dim, 128 * n, g)
+    return sd
+
+
+def jmt_state_dict(seed: int = 0, modalities: Sequence[str] = ("video", "vggish"), output_dim: int = 7,
+                   model_name: str = "JMT", settings: Dict[str, dict] = None) -> "OrderedDict[str, torch.Tensor]":
+    """``JMT.state_dict()`` layout for model_name 'JMT' or 'MT' (models/model.py:895-1105)."""
+    settings = settings or TCN_SETTINGS
+    g = torch.Generator().manual_seed(seed + 1299709)
+    sd: "OrderedDict[str, torch.Tensor]" = OrderedDict()
+    _head_common(sd, modalities, settings, g)
+    _spatial(sd, modalities, seed)
+    f = "fuse."
+    encs = ("visual_encoder", "audio_encoder", "jr_encoder", "final_encoder") if model_name == "JMT" else \
+        ("visual_encoder", "audio_encoder", "final_encoder")
+    for e in encs:
+        _encoder_block(sd, f + e, 128, 128, g)
+    cas = ("CA_va", "CA_av", "CA_jra", "CA_ajr", "CA_vjr", "CA_jrv") if model_name == "JMT" else ("CA_va", "CA_av")
+    for c in cas:
+        _mha(sd, f + c, 128, g)
+    _linear(sd, f + "reduce_feats_dim", 128, 256, g)
+    _linear(sd, f + "augment_audio_feats_dim", 128, 64, g)
+    _mha(sd, f + "final_self_attention", 128, g)
+    _bn(sd, "bn1", 128, g)
+    _linear(sd, "fc1", 128, 128, g)
+    _linear(sd, "fc2", output_dim, 128, g)
+    return sd

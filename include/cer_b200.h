@@ -298,6 +298,25 @@ int cer_preproc_forward(cer_preproc* plan, const uint8_t* frames_dev, int64_t n_
 void cer_preproc_destroy(cer_preproc* plan);
 
 /* ------------------------------------------------------------------------------------------
+ * Building blocks of the alternative fusion heads CAN / JMT / MT (models/model.py:529-684,
+ * :709-750, :895-1167; selected by --model_name, experiment.py:317-347).  Exact fp32.
+ *   cer_linear_forward : y[r,:] = act(x[r,:] W^T + b), W [out_dim][in_dim] (nn.Linear layout);
+ *                        act 0 none, 1 LeakyReLU(0.01) (F.leaky_relu, model.py:680), 2 ReLU (:734).
+ *                        ldx / ldy: row pitches in floats (write into a slice of a concat buffer).
+ *   cer_softmax_gate   : out = softmax(gate, dim=-1) * feat        (AttentionFusion, :563-567)
+ *   cer_sdpa_forward   : out[b,i,:] = softmax_j(q[b,i,:].k[b,j,:] / sqrt(dim)) v[b,j,:] -- the core of
+ *                        nn.MultiheadAttention(dim, 1) (:731, :917-931) on batch-major [B][L][dim] rows
+ *   cer_add_layernorm  : out = LayerNorm(x + res) (res may be NULL)  (TransformerEncoderLayer, :740-750)
+ * ------------------------------------------------------------------------------------------ */
+int cer_linear_forward(const float* x_dev, int64_t rows, int32_t in_dim, int32_t ldx, const float* w_dev,
+                       const float* bias_dev /* or NULL */, int32_t out_dim, int32_t act, float* y_dev, int32_t ldy, void* stream);
+int cer_softmax_gate(const float* gate_dev, const float* feat_dev, int64_t rows, int32_t dim, float* out_dev, void* stream);
+int cer_sdpa_forward(const float* q_dev, int32_t ldq, const float* k_dev, int32_t ldk, const float* v_dev, int32_t ldv,
+                     int32_t batch, int32_t len_q, int32_t len_k, int32_t dim, float* out_dev, int32_t ldo, void* stream);
+int cer_add_layernorm(const float* x_dev, const float* res_dev, int64_t rows, int32_t dim, const float* gamma_dev,
+                      const float* beta_dev, float eps, float* out_dev, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Window stitching.   Replaces the sum / overlap-count / divide of
  * Trainer.inference_forward_windows (trainer.py:864-890) on device.
  * win_logits: fp32 [n_windows][win_len][n_out]; win_start: int32 [n_windows] first frame of each

@@ -14,6 +14,7 @@ reference modules, imported as they are, are the source of truth):
   * train_b2.pt     -- two SGD-nesterov steps of the head in train mode (Dropout p=0): loss, gradients, BN stats
   * eval_transform.pt -- the reference's eval transform classes (PIL resize 48, crop 40, normalise) on seeded uint8 frames
   * logmel.pt       -- mel_features.log_mel_spectrogram + my_frame (the reference code) on a seeded 3 s waveform
+  * heads.pt        -- CAN / JMT / MT forward from pixels (B=2 x T=24) and their state_dict key listings
   * windowing.json  -- Trainer.windowing outputs for a set of lengths
 Weights are NOT stored: they are regenerated from the seed by
 feature_vs_text_compound_emotion_b200.synthetic (identical on every machine), and are loaded
@@ -200,6 +201,37 @@ def main():
                 "example_7": torch.from_numpy(ex[7]).float(), "example_last": torch.from_numpy(ex[-1]).float()},
                os.path.join(OUT, "logmel.pt"))
     print("logmel", lm.shape, ex.shape)
+
+    # ---- alternative heads CAN / JMT / MT (models/model.py:529-684, :895-1167) ------------------
+    from models.model import CAN, JMT
+    ts = ref_configs.config["tcn_settings"]
+    assert {k: ts[k] for k in synthetic.TCN_SETTINGS} == synthetic.TCN_SETTINGS
+    TH, heads = 24, {}
+    cmods = ["video", "vggish", "bert"]
+    can = CAN(task="CLASSIFICATION", modalities=cmods, tcn_settings=ts, backbone_settings=ref_configs.config["backbone_settings"],
+              output_dim=7, root_dir=tmp, device="cpu")
+    csd = synthetic.can_state_dict(0, cmods)
+    assert list(can.state_dict()) == list(csd)
+    can.load_state_dict(csd, strict=True)
+    can.eval()
+    fh = synthetic.feature_windows(2, TH, seed=705, modalities=["vggish", "bert"])
+    Xc = {"video": synthetic.frames(2 * TH, seed=706).view(2, TH, 3, 40, 40), "vggish": fh["vggish"], "bert": fh["bert"]}
+    heads["CAN"] = {"modalities": cmods, "feat_seed": 705, "frame_seed": 706, "T": TH, "out": can({k: v.clone() for k, v in Xc.items()}),
+                    "keys": {k: list(v.shape) for k, v in can.state_dict().items()}}
+    for name in ("JMT", "MT"):
+        jmods = ["video", "vggish"]
+        jm = JMT(task="CLASSIFICATION", modalities=jmods, tcn_settings=ts, backbone_settings=ref_configs.config["backbone_settings"],
+                 output_dim=7, root_dir=tmp, device="cpu", model_name=name)
+        jsd = synthetic.jmt_state_dict(0, jmods, model_name=name)
+        assert list(jm.state_dict()) == list(jsd)
+        jm.load_state_dict(jsd, strict=True)
+        jm.eval()
+        Xj = {"video": synthetic.frames(2 * TH, seed=707).view(2, TH, 3, 40, 40),
+              "vggish": synthetic.feature_windows(2, TH, seed=708, modalities=["vggish"])["vggish"]}
+        heads[name] = {"modalities": jmods, "feat_seed": 708, "frame_seed": 707, "T": TH, "out": jm({k: v.clone() for k, v in Xj.items()}),
+                       "keys": {k: list(v.shape) for k, v in jm.state_dict().items()}}
+    torch.save(heads, os.path.join(OUT, "heads.pt"))
+    print("heads", {k: (tuple(v["out"].shape), len(v["keys"])) for k, v in heads.items()})
 
     # ---- windowing (trainer.py imports pynvml/munch, absent here: exec the one function) ----
     src = open(os.path.join(REF, "trainer.py")).read()

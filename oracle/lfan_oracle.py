@@ -562,3 +562,96 @@ def waveform_to_examples(wave: np.ndarray, window_sec: float = 0.96, hop_sec: fl
     lm = log_mel_spectrogram(wave)
     starts, win = example_starts(lm.shape[0], window_sec, hop_sec)
     return np.stack([lm[s:s + win] for s in starts])
+
+
+
+# --------------------------------------------------------------------------------------
+# Alternative fusion heads: CAN (models/model.py:529-684), JMT / MT (:709-750, :895-1167)
+# --------------------------------------------------------------------------------------
+def _tcn_levels(sd: SD, prefix: str) -> int:
+    n = 0
+    while f"{prefix}network.{n}.conv1.weight_v" in sd:
+        n += 1
+    return n
+
+
+def _encode_modalities(sd: SD, X: Dict[str, Tensor], modalities: Sequence[str]) -> Dict[str, Tensor]:
+    """The part CAN.forward and JMT.forward share (model.py:655-676, :1138-1159): backbones, then
+    TemporalConvNet + BatchNorm1d per modality.  Returns x[m]: [B, C_m, T] as the reference keeps it."""
+    x = {}
+    for m in modalities:
+        if m == "video":
+            B, T = X[m].shape[:2]
+            f = ir50_forward(sd, X[m].reshape(B * T, *X[m].shape[2:]), "spatial.visual.backbone.").view(B, T, -1)
+        elif m == "logmel":
+            B, hh, T, ww = X[m].shape
+            f = vggish_forward(sd, X[m].permute(0, 2, 3, 1).contiguous().view(-1, ww, hh), "spatial.audio.backbone.").view(B, T, -1)
+        else:
+            f = X[m].squeeze(1)
+        h = tcn_forward(sd, f"temporal.{m}.", f.transpose(1, 2), _tcn_levels(sd, f"temporal.{m}."))
+        x[m] = _bn_eval(sd, f"bn.{m}", h)
+    return x
+
+
+def _head_tail(sd: SD, c: Tensor) -> Tensor:
+    """fc1 -> BatchNorm1d (eval) over the feature axis -> F.leaky_relu -> fc2 (model.py:678-681, :1161-1164)."""
+    c = F.linear(c, sd["fc1.weight"], sd["fc1.bias"]).transpose(1, 2)
+    c = _bn_eval(sd, "bn1", c).transpose(1, 2)
+    return F.linear(F.leaky_relu(c, LEAKY_SLOPE), sd["fc2.weight"], sd["fc2.bias"])
+
+
+def can_forward(sd: SD, X: Dict[str, Tensor], modalities: Sequence[str]) -> Tensor:
+    """CAN.forward (model.py:651-684) with AttentionFusion (:552-568): per-modality Linear to 128,
+    concat, softmax(Linear(concat)) as an element-wise gate.  Returns [B, T, output_dim]."""
+    x = _encode_modalities(sd, X, modalities)
+    proj = [F.linear(x[m].transpose(1, 2), sd[f"fuse.attn.{i}.weight"], sd[f"fuse.attn.{i}.bias"])
+            for i, m in enumerate(modalities)]
+    cat = torch.cat(proj, -1)
+    gate = torch.softmax(F.linear(cat, sd["fuse.weights.weight"], sd["fuse.weights.bias"]), dim=-1)
+    return _head_tail(sd, gate * cat)
+
+
+def mha1(sd: SD, p: str, q_in: Tensor, k_in: Tensor, v_in: Tensor) -> Tensor:
+    """nn.MultiheadAttention(E, num_heads=1), sequence-first inputs [L, N, E] (model.py:731, :917-931)."""
+    W, b = sd[p + ".in_proj_weight"], sd[p + ".in_proj_bias"]
+    E = W.shape[1]
+    q = F.linear(q_in, W[:E], b[:E]).transpose(0, 1)
+    k = F.linear(k_in, W[E:2 * E], b[E:2 * E]).transpose(0, 1)
+    v = F.linear(v_in, W[2 * E:], b[2 * E:]).transpose(0, 1)
+    att = torch.softmax(q @ k.transpose(1, 2) / math.sqrt(E), dim=-1)
+    return F.linear((att @ v).transpose(0, 1), sd[p + ".out_proj.weight"], sd[p + ".out_proj.bias"])
+
+
+def encoder_block(sd: SD, p: str, x: Tensor) -> Tensor:
+    """TransformerEncoderBlock with one TransformerEncoderLayer (model.py:716-750): post-norm."""
+    q = p + ".layers.0"
+    x = x + mha1(sd, q + ".attention", x, x, x)
+    x = F.layer_norm(x, (x.shape[-1],), sd[q + ".layer_norm1.weight"], sd[q + ".layer_norm1.bias"], LN_EPS)
+    ff = F.linear(F.relu(F.linear(x, sd[q + ".feed_forward.0.weight"], sd[q + ".feed_forward.0.bias"])),
+                  sd[q + ".feed_forward.2.weight"], sd[q + ".feed_forward.2.bias"])
+    return F.layer_norm(x + ff, (x.shape[-1],), sd[q + ".layer_norm2.weight"], sd[q + ".layer_norm2.bias"], LN_EPS)
+
+
+def jmt_forward(sd: SD, X: Dict[str, Tensor], modalities: Sequence[str], model_name: str = "JMT") -> Tensor:
+    """JMT.forward (model.py:1134-1167) with JMTFusion (:933-979) or MTFusion (:1015-1048).
+    Note the reference's final stage: the stacked cross-attention outputs [L, B, S, E] are viewed
+    as [L*B, S, E] and fed to sequence-first attention modules, so the final encoder and
+    self-attention attend over all L*B positions, with the S stack slots as the batch."""
+    x = _encode_modalities(sd, X, modalities)
+    f = "fuse."
+    vis = x["video"].permute(2, 0, 1)
+    aud = F.linear(x["vggish"].permute(2, 0, 1), sd[f + "augment_audio_feats_dim.weight"], sd[f + "augment_audio_feats_dim.bias"])
+    ev, ea = encoder_block(sd, f + "visual_encoder", vis), encoder_block(sd, f + "audio_encoder", aud)
+    if model_name == "JMT":
+        jr = F.linear(torch.cat((vis, aud), dim=2), sd[f + "reduce_feats_dim.weight"], sd[f + "reduce_feats_dim.bias"])
+        ej = encoder_block(sd, f + "jr_encoder", jr)
+        stack = [mha1(sd, f + "CA_va", ev, ea, ea), mha1(sd, f + "CA_av", ea, ev, ev), mha1(sd, f + "CA_jrv", ej, ev, ev),
+                 mha1(sd, f + "CA_vjr", ev, ej, ej), mha1(sd, f + "CA_jra", ej, ea, ea), mha1(sd, f + "CA_ajr", ea, ej, ej)]
+    else:
+        stack = [mha1(sd, f + "CA_va", ev, ea, ea), mha1(sd, f + "CA_av", ea, ev, ev)]
+    st = torch.stack(stack, dim=2)
+    L, B, S, E = st.shape
+    st = st.view(-1, S, E)
+    enc = encoder_block(sd, f + "final_encoder", st)
+    out = mha1(sd, f + "final_self_attention", enc, enc, enc).view(L, B, S, E)[:, :, -1, :].permute(1, 0, 2)
+    return _head_tail(sd, out)

@@ -120,3 +120,20 @@ def test_struct_sizes_match_header_layout():
     assert ctypes.sizeof(_capi.IrUnit) == 16 + 5 * 8
     assert ctypes.sizeof(_capi.TcnBlock) == 16 + 8 * 8
     assert ctypes.sizeof(_capi.Ir50Weights) == 8 + 3 * 8 + 8 + 8 + 8 + 2 * 8
+
+
+def test_alternative_head_layouts_equal_reference(golden_dir):
+    from feature_vs_text_compound_emotion_b200.models.model import CAN, JMT
+    g = torch.load(os.path.join(golden_dir, "heads.pt"))
+    vsd = synthetic.visual_backbone_state_dict(0)
+    can = CAN(task="CLASSIFICATION", modalities=g["CAN"]["modalities"], tcn_settings=synthetic.TCN_SETTINGS, backbone_settings=BS,
+              output_dim=7, root_dir="", device="cpu", visual_state_dict=vsd)
+    assert {k: list(v.shape) for k, v in can.state_dict().items()} == g["CAN"]["keys"]
+    assert list(can.state_dict()) == list(g["CAN"]["keys"])
+    can.load_state_dict(synthetic.can_state_dict(0, g["CAN"]["modalities"]), strict=True)
+    for name in ("JMT", "MT"):
+        jm = JMT(task="CLASSIFICATION", modalities=g[name]["modalities"], tcn_settings=synthetic.TCN_SETTINGS, backbone_settings=BS,
+                 output_dim=7, root_dir="", device="cpu", model_name=name, visual_state_dict=vsd)
+        assert list(jm.state_dict()) == list(g[name]["keys"]), name
+        assert {k: list(v.shape) for k, v in jm.state_dict().items()} == g[name]["keys"], name
+        jm.load_state_dict(synthetic.jmt_state_dict(0, g[name]["modalities"], model_name=name), strict=True)

@@ -263,3 +263,31 @@ def test_empty_ragged_and_short_inputs():
         pad = lambda t: torch.cat([t, t[-1:].expand(300 - L, -1)]).unsqueeze(0)
         want = O.head_forward(sd, {"video": pad(emb), "vggish": pad(feats["vggish"]), "bert": pad(feats["bert"])}, mods)[0, :L]
         assert (out - want).abs().max().item() <= 2e-2, L
+
+
+@pytest.mark.parametrize("name", ["CAN", "JMT", "MT"])
+def test_alternative_heads_vs_golden(golden_dir, name):
+    """CAN / JMT / MT drop-ins from pixels vs the reference's outputs (same tolerances as LFAN)."""
+    dev = _dev()
+    from feature_vs_text_compound_emotion_b200.models.model import CAN, JMT
+    g = torch.load(os.path.join(golden_dir, "heads.pt"))[name]
+    mods, T = g["modalities"], g["T"]
+    vsd = synthetic.visual_backbone_state_dict(0)
+    if name == "CAN":
+        m = CAN(task="CLASSIFICATION", modalities=mods, tcn_settings=synthetic.TCN_SETTINGS, backbone_settings=BS, output_dim=7,
+                root_dir="", device=dev, visual_state_dict=vsd)
+        m.load_state_dict(synthetic.can_state_dict(0, mods), strict=True)
+    else:
+        m = JMT(task="CLASSIFICATION", modalities=mods, tcn_settings=synthetic.TCN_SETTINGS, backbone_settings=BS, output_dim=7,
+                root_dir="", device=dev, model_name=name, visual_state_dict=vsd)
+        m.load_state_dict(synthetic.jmt_state_dict(0, mods, model_name=name), strict=True)
+    m = m.to(dev).eval()
+    X = {"video": synthetic.frames(2 * T, seed=g["frame_seed"]).view(2, T, 3, 40, 40).to(dev)}
+    for k, v in synthetic.feature_windows(2, T, seed=g["feat_seed"], modalities=[x for x in mods if x != "video"]).items():
+        X[k] = v.to(dev)
+    out = m(X).cpu()
+    assert out.shape == g["out"].shape
+    err = (out - g["out"]).abs().max().item()
+    agree = (out.argmax(-1) == g["out"].argmax(-1)).float().mean().item()
+    assert err <= 2e-2 * max(1.0, g["out"].abs().max().item()), err
+    assert agree >= 0.95, agree          # 48 frames: at most two flips

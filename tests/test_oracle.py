@@ -160,3 +160,26 @@ def test_logmel_front_end_matches_reference(golden_dir):
     assert ex.shape == (g["n_examples"], 96, 64)
     assert np.abs(ex.sum(axis=(1, 2)) - g["example_sum"].numpy()).max() < 1e-6
     assert np.abs(ex[7] - g["example_7"].double().numpy()).max() < 1e-5
+
+
+def _head_inputs(g, name):
+    c = g[name]
+    T = c["T"]
+    X = {"video": synthetic.frames(2 * T, seed=c["frame_seed"]).view(2, T, 3, 40, 40)}
+    f = synthetic.feature_windows(2, T, seed=c["feat_seed"], modalities=[m for m in c["modalities"] if m != "video"])
+    X.update(f)
+    return X
+
+
+def test_alternative_heads_match_reference(golden_dir):
+    """CAN, JMT and MT (models/model.py:529-684, :895-1167) from pixels, oracle vs the reference."""
+    g = torch.load(os.path.join(golden_dir, "heads.pt"))
+    sd = synthetic.can_state_dict(0, g["CAN"]["modalities"])
+    assert {k: list(v.shape) for k, v in sd.items()} == g["CAN"]["keys"] and list(sd) == list(g["CAN"]["keys"])
+    out = O.can_forward(sd, _head_inputs(g, "CAN"), g["CAN"]["modalities"])
+    assert (out - g["CAN"]["out"]).abs().max().item() < 2e-5
+    for name in ("JMT", "MT"):
+        sd = synthetic.jmt_state_dict(0, g[name]["modalities"], model_name=name)
+        assert {k: list(v.shape) for k, v in sd.items()} == g[name]["keys"] and list(sd) == list(g[name]["keys"])
+        out = O.jmt_forward(sd, _head_inputs(g, name), g[name]["modalities"], name)
+        assert (out - g[name]["out"]).abs().max().item() < 2e-5, name
