@@ -25,6 +25,19 @@ namespace cer {
 // One thread = one output pixel, all 64 channels; weights [27][64] broadcast from smem.
 // Reference: Backbone.input_layer, models/arcface_model.py:130-132.
 // ------------------------------------------------------------------------------------------
+// v2: one thread = TWO horizontally adjacent output pixels (a 3 x 4 x 3 input patch in registers,
+// duplicated into {x, x} pairs once), channel PAIRS on packed fp32 FMAs (fma.rn.f32x2): per tap and
+// 8 channels, 2 x LDS.128 of weights feed 8 FFMA2 = 16 FMAs (v1: 2 x LDS.128 per 8 FMAs).
+__device__ __forceinline__ void stem_ffma2(unsigned long long& d, unsigned long long a, unsigned long long b) {
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(d) : "l"(a), "l"(b));
+}
+__device__ __forceinline__ unsigned long long stem_dup(float x) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %1};" : "=l"(r) : "f"(x));
+  return r;
+}
+struct alignas(16) StemW2 { unsigned long long p0, p1; };     // channels (c, c+1), (c+2, c+3)
+
 __global__ void __launch_bounds__(128) stem_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                    const float* __restrict__ bias, const float* __restrict__ alpha,
                                                    __nv_bfloat16* __restrict__ out, int n_frames, int H, int W) {
@@ -38,43 +51,68 @@ __global__ void __launch_bounds__(128) stem_kernel(const float* __restrict__ x, 
   }
   __syncthreads();
   const int hw = H * W;
-  const long long total = static_cast<long long>(n_frames) * hw;
-  for (long long pix = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; pix < total;
-       pix += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int n = static_cast<int>(pix / hw);
-    const int rem = static_cast<int>(pix - static_cast<long long>(n) * hw);
-    const int oh = rem / W, ow = rem - oh * W;
-    float in[27];
+  const int W2 = (W + 1) >> 1;
+  const long long total = static_cast<long long>(n_frames) * H * W2;           // pixel pairs
+  for (long long pp = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; pp < total;
+       pp += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int n = static_cast<int>(pp / (H * W2));
+    const int rem = static_cast<int>(pp - static_cast<long long>(n) * H * W2);
+    const int oh = rem / W2, ow = (rem - oh * W2) * 2;
+    const bool has_b = ow + 1 < W;
+    // patch[r][cc][c], cc = 0..3 <-> input column ow - 1 + cc, duplicated for the packed FMAs
+    unsigned long long in2[3][4][3];
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
+      const int ih = oh + r - 1;
 #pragma unroll
-      for (int s = 0; s < 3; ++s) {
-        const int ih = oh + r - 1, iw = ow + s - 1;
+      for (int cc = 0; cc < 4; ++cc) {
+        const int iw = ow + cc - 1;
         const bool ok = ih >= 0 && ih < H && iw >= 0 && iw < W;
 #pragma unroll
         for (int c = 0; c < 3; ++c)
-          in[(r * 3 + s) * 3 + c] = ok ? __ldg(x + (static_cast<size_t>(n) * 3 + c) * hw + ih * W + iw) : 0.f;
+          in2[r][cc][c] = stem_dup(ok ? __ldg(x + (static_cast<size_t>(n) * 3 + c) * hw + ih * W + iw) : 0.f);
       }
     }
-    uint4* op = reinterpret_cast<uint4*>(out + static_cast<size_t>(pix) * 64);
+    const size_t pix = (static_cast<size_t>(n) * H + oh) * W + ow;
+    uint4* opa = reinterpret_cast<uint4*>(out + pix * 64);
+    uint4* opb = reinterpret_cast<uint4*>(out + (pix + 1) * 64);
 #pragma unroll
     for (int cg = 0; cg < 8; ++cg) {
-      float acc[8];
+      unsigned long long accA[4], accB[4];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[j] = bs[cg * 8 + j];
-#pragma unroll
-      for (int t = 0; t < 27; ++t) {
-        const float4 w0 = *reinterpret_cast<const float4*>(&ws[t * 64 + cg * 8]);
-        const float4 w1 = *reinterpret_cast<const float4*>(&ws[t * 64 + cg * 8 + 4]);
-        acc[0] = fmaf(in[t], w0.x, acc[0]); acc[1] = fmaf(in[t], w0.y, acc[1]);
-        acc[2] = fmaf(in[t], w0.z, acc[2]); acc[3] = fmaf(in[t], w0.w, acc[3]);
-        acc[4] = fmaf(in[t], w1.x, acc[4]); acc[5] = fmaf(in[t], w1.y, acc[5]);
-        acc[6] = fmaf(in[t], w1.z, acc[6]); acc[7] = fmaf(in[t], w1.w, acc[7]);
+      for (int j = 0; j < 4; ++j) {
+        const unsigned long long b2 = *reinterpret_cast<const unsigned long long*>(&bs[cg * 8 + 2 * j]);
+        accA[j] = b2; accB[j] = b2;
       }
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[j] = acc[j] >= 0.f ? acc[j] : acc[j] * as[cg * 8 + j];
-      op[cg] = make_uint4(pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]), pack_bf16x2(acc[4], acc[5]),
-                          pack_bf16x2(acc[6], acc[7]));
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int s2 = 0; s2 < 3; ++s2)
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            const int t = (r * 3 + s2) * 3 + c;
+            const StemW2 w01 = *reinterpret_cast<const StemW2*>(&ws[t * 64 + cg * 8]);
+            const StemW2 w23 = *reinterpret_cast<const StemW2*>(&ws[t * 64 + cg * 8 + 4]);
+            const unsigned long long ia = in2[r][s2][c], ib = in2[r][s2 + 1][c];
+            stem_ffma2(accA[0], ia, w01.p0); stem_ffma2(accA[1], ia, w01.p1);
+            stem_ffma2(accA[2], ia, w23.p0); stem_ffma2(accA[3], ia, w23.p1);
+            stem_ffma2(accB[0], ib, w01.p0); stem_ffma2(accB[1], ib, w01.p1);
+            stem_ffma2(accB[2], ib, w23.p0); stem_ffma2(accB[3], ib, w23.p1);
+          }
+      uint32_t pa[4], pb[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float a0, a1, b0, b1;
+        asm("mov.b64 {%0, %1}, %2;" : "=f"(a0), "=f"(a1) : "l"(accA[j]));
+        asm("mov.b64 {%0, %1}, %2;" : "=f"(b0), "=f"(b1) : "l"(accB[j]));
+        const float s0 = as[cg * 8 + 2 * j], s1 = as[cg * 8 + 2 * j + 1];
+        a0 = a0 >= 0.f ? a0 : a0 * s0; a1 = a1 >= 0.f ? a1 : a1 * s1;
+        b0 = b0 >= 0.f ? b0 : b0 * s0; b1 = b1 >= 0.f ? b1 : b1 * s1;
+        pa[j] = pack_bf16x2(a0, a1);
+        pb[j] = pack_bf16x2(b0, b1);
+      }
+      opa[cg] = make_uint4(pa[0], pa[1], pa[2], pa[3]);
+      if (has_b) opb[cg] = make_uint4(pb[0], pb[1], pb[2], pb[3]);
     }
   }
 }
@@ -531,7 +569,7 @@ extern "C" int cer_ir50_create(cer_ir50** out, const cer_ir50_weights* w, int64_
 
 static int run_pass(cer_ir50* p, const float* x, int frames, int last_unit, float* emb_out, cudaStream_t st) {
   const int H = p->w.in_h, W = p->w.in_w;
-  const long long pix = (long long)frames * H * W;
+  const long long pix = (long long)frames * H * ((W + 1) / 2);      // one thread per pixel pair
   const int blocks = (int)std::min<long long>((pix + 127) / 128, (long long)p->num_sms * 16);
   stem_kernel<<<blocks, 128, 0, st>>>(x, p->w.stem_w, p->w.stem_bias, p->w.stem_alpha,
                                       reinterpret_cast<__nv_bfloat16*>(p->buf[0]), frames, H, W);

@@ -50,32 +50,41 @@ __global__ void __launch_bounds__(128) vgg_stem_pool_kernel(const float* __restr
         in[r][c] = (ih >= 0 && ih < H && iw >= 0 && iw < W) ? __ldg(xp + ih * W + iw) : 0.f;
       }
     }
+    // packed fp32 FMAs on channel pairs (fma.rn.f32x2): the 16 inputs are duplicated into {x, x} once
+    unsigned long long in2[4][4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) asm("mov.b64 %0, {%1, %1};" : "=l"(in2[r][c]) : "f"(in[r][c]));
     uint4* op = reinterpret_cast<uint4*>(out + static_cast<size_t>(pix) * 64);
 #pragma unroll
     for (int cg = 0; cg < 8; ++cg) {
-      float a[4][8];      // [pool position][channel]
+      unsigned long long a[4][4];      // [pool position][channel pair]
 #pragma unroll
       for (int q = 0; q < 4; ++q)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) a[q][j] = 0.f;
+        for (int j = 0; j < 4; ++j) a[q][j] = 0ull;
 #pragma unroll
       for (int t = 0; t < 9; ++t) {
         const int r = t / 3, s = t - 3 * (t / 3);
-        const float4 w0 = *reinterpret_cast<const float4*>(&ws[t * 64 + cg * 8]);
-        const float4 w1 = *reinterpret_cast<const float4*>(&ws[t * 64 + cg * 8 + 4]);
-        const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+        const ulonglong2 w01 = *reinterpret_cast<const ulonglong2*>(&ws[t * 64 + cg * 8]);
+        const ulonglong2 w23 = *reinterpret_cast<const ulonglong2*>(&ws[t * 64 + cg * 8 + 4]);
+        const unsigned long long wv[4] = {w01.x, w01.y, w23.x, w23.y};
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          const float v = in[(q >> 1) + r][(q & 1) + s];
+          const unsigned long long v = in2[(q >> 1) + r][(q & 1) + s];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) a[q][j] = fmaf(v, wv[j], a[q][j]);
+          for (int j = 0; j < 4; ++j) asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(a[q][j]) : "l"(v), "l"(wv[j]));
         }
       }
       float m[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float mx = fmaxf(fmaxf(a[0][j], a[1][j]), fmaxf(a[2][j], a[3][j])) + bs[cg * 8 + j];
-        m[j] = fmaxf(mx, 0.f);
+      for (int j = 0; j < 4; ++j) {
+        float lo[4], hi[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) asm("mov.b64 {%0, %1}, %2;" : "=f"(lo[q]), "=f"(hi[q]) : "l"(a[q][j]));
+        m[2 * j] = fmaxf(fmaxf(fmaxf(lo[0], lo[1]), fmaxf(lo[2], lo[3])) + bs[cg * 8 + 2 * j], 0.f);
+        m[2 * j + 1] = fmaxf(fmaxf(fmaxf(hi[0], hi[1]), fmaxf(hi[2], hi[3])) + bs[cg * 8 + 2 * j + 1], 0.f);
       }
       op[cg] = make_uint4(pack_bf16x2(m[0], m[1]), pack_bf16x2(m[2], m[3]), pack_bf16x2(m[4], m[5]),
                           pack_bf16x2(m[6], m[7]));
