@@ -170,8 +170,10 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
       if (p.bias_classes == 9)
         cls = (oh == 0 ? 0 : (oh == p.Hout - 1 ? 2 : 1)) * 3 + (ow == 0 ? 0 : (ow == p.Wout - 1 ? 2 : 1));
       const size_t m = (static_cast<size_t>(n) * p.Hout + oh) * p.Wout + ow;
+      const bool pool_store = p.pool_xor && valid && !(oh & 1) && !(ow & 1);
+      const size_t pool_off = ((static_cast<size_t>(n) * (p.Hout >> 1) + (oh >> 1)) * (p.Wout >> 1) + (ow >> 1)) * p.Cout + n0;
       conv_epilogue_core<BN>(p, s_bias, s_alpha, tmem_base + acc * BN, n0, warp, tfull0 + acc * 8, acc_phase, valid, cls,
-                             m * p.Cout + n0);
+                             m * p.Cout + n0, pool_store, pool_off);
       tc_fence_before();
       asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tempty0 + acc * 8) : "memory");
     }

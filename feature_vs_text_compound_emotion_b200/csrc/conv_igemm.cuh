@@ -41,6 +41,8 @@ struct alignas(64) ConvKernelParams {
   int bias_classes;      // 1 or 9
   int out_fp32;          // 0: bf16 output, 1: fp32 output
   int halo_frames, halo_bands, halo_cts;   // conv_halo_kernel only: frames, 16-row bands and 8-column tiles per frame
+  int pool_xor;          // 0: no pooling; else fused MaxPool2d(2,2): the vertical pool partner is lane ^ pool_xor
+                         // (8 or 16 = pixels per tile row), the horizontal one lane ^ 1; output is [M/4][Cout]
   const float* bias;     // [bias_classes][Cout]
   const float* alpha;    // [Cout] PReLU slopes or nullptr
   const __nv_bfloat16* res;  // [M][Cout] residual or nullptr
@@ -88,7 +90,8 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
 template <int BN>
 __device__ __forceinline__ void conv_epilogue_core(const ConvKernelParams& p, const float* s_bias, const float* s_alpha,
                                                    uint32_t tmem_acc, int n0, int warp, uint32_t tfull, uint32_t parity,
-                                                   bool valid, int cls, size_t out_off);
+                                                   bool valid, int cls, size_t out_off, bool pool_store = false,
+                                                   size_t pool_off = 0);
 
 template <int BN>
 __device__ __forceinline__ void conv_epilogue_tile(const ConvKernelParams& p, const float* s_bias, const float* s_alpha,
@@ -109,14 +112,22 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvKernelParams& p, co
     const int ow = rem - oh * p.Wout;
     cls = (oh == 0 ? 0 : (oh == p.Hout - 1 ? 2 : 1)) * 3 + (ow == 0 ? 0 : (ow == p.Wout - 1 ? 2 : 1));
   }
+  bool pool_store = false;
+  size_t pool_off = 0;
+  if (p.pool_xor) {      // fused 2x2 max-pool: the lane at even (oh, ow) stores the window's maximum
+    const int rem = m % hw;
+    const int oh = rem / p.Wout, ow = rem - oh * p.Wout;
+    pool_store = valid && !(oh & 1) && !(ow & 1);
+    pool_off = ((static_cast<size_t>(m / hw) * (p.Hout >> 1) + (oh >> 1)) * (p.Wout >> 1) + (ow >> 1)) * p.Cout + n0;
+  }
   conv_epilogue_core<BN>(p, s_bias, s_alpha, tmem_acc, n0, warp, tfull, parity, valid, cls,
-                         static_cast<size_t>(m) * p.Cout + n0);
+                         static_cast<size_t>(m) * p.Cout + n0, pool_store, pool_off);
 }
 
 template <int BN>
 __device__ __forceinline__ void conv_epilogue_core(const ConvKernelParams& p, const float* s_bias, const float* s_alpha,
                                                    uint32_t tmem_acc, int n0, int warp, uint32_t tfull, uint32_t parity,
-                                                   bool valid, int cls, size_t out_off) {
+                                                   bool valid, int cls, size_t out_off, bool pool_store, size_t pool_off) {
   constexpr int kHalf = BN / 2;
   const int quarter = warp & 3;
   const int half = warp >> 2;
@@ -181,7 +192,27 @@ __device__ __forceinline__ void conv_epilogue_core(const ConvKernelParams& p, co
         }
       }
     }
-    if (valid) {
+    if (p.pool_xor) {
+      // MaxPool2d(2,2) across the four lanes of the window (all 32 lanes take part in the shuffles);
+      // max of the bf16-rounded values == bf16 rounding of the max, i.e. identical to pooling the stored tensor
+      uint32_t h[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) h[j] = pack_bf16x2(f[2 * j], f[2 * j + 1]);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        uint32_t o = __shfl_xor_sync(0xffffffffu, h[j], 1);
+        __nv_bfloat162 mx = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&h[j]), *reinterpret_cast<__nv_bfloat162*>(&o));
+        h[j] = *reinterpret_cast<uint32_t*>(&mx);
+        o = __shfl_xor_sync(0xffffffffu, h[j], p.pool_xor);
+        mx = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&h[j]), *reinterpret_cast<__nv_bfloat162*>(&o));
+        h[j] = *reinterpret_cast<uint32_t*>(&mx);
+      }
+      if (pool_store) {
+        uint4* op = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + pool_off + c0);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) op[j] = make_uint4(h[4 * j], h[4 * j + 1], h[4 * j + 2], h[4 * j + 3]);
+      }
+    } else if (valid) {
       if (p.out_fp32) {
         float4* op = reinterpret_cast<float4*>(static_cast<float*>(p.out) + out_off + c0);
 #pragma unroll

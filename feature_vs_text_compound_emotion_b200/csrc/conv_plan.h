@@ -23,9 +23,12 @@ struct ConvGeom {
   const void* src2; int H2, W2, Cin2, stride2;       // fused shortcut operand (Cin2 = 0: none)
   const void* weight; const float* bias; int bias_classes; const float* alpha;
   const __nv_bfloat16* res; void* dst; int Cout; int out_fp32;
+  int pool;        // 1: fuse MaxPool2d(2,2) into the epilogue (dst is the pooled tensor); see conv_can_pool()
 };
 
 int load_driver_entry_points();
+// can a 3x3/s1/p1 conv over an H x W map with these channels fuse the 2x2 max-pool into its epilogue?
+bool conv_can_pool(int H, int W, int Cin, int Cout);
 // n_cap: frames the activation allocation holds (tensor-map N extent)
 int build_conv_op(ConvOp* op, const ConvGeom& g, int n_cap);
 int launch_conv(const ConvOp& op, int frames, int num_sms, cudaStream_t st);

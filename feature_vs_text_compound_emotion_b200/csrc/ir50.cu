@@ -270,6 +270,15 @@ int make_tiled2d_map_generic(CUtensorMap* map, CUtensorMapDataType dt, int elem_
 
 static int pick_bn(int cout) { return cout % 256 == 0 ? 256 : (cout % 128 == 0 ? 128 : 64); }
 
+// Fused pooling needs every 2x2 window inside one warp of the epilogue: 32 consecutive tile rows must
+// cover whole pairs of map rows (halo tiles: always; im2col tiles: W in {8, 16}, H*W a multiple of 32
+// so that frames start on even rows of a 128-pixel tile).
+bool conv_can_pool(int H, int W, int Cin, int Cout) {
+  if ((H & 1) || (W & 1) || Cout % 64) return false;
+  if (Cin == 64) return W % kHaloTileW == 0 && (Cout == 64 || Cout == 128);
+  return (W == 8 || W == 16) && (H * W) % 32 == 0 && Cin % 64 == 0;
+}
+
 int build_conv_op(ConvOp* op, const ConvGeom& g, int n_cap) {
   if (g.Cin % kBlockK || g.Cin2 % kBlockK || g.Cout % 64) return set_error(CER_ERR_INVALID, "channels must be multiples of 64");
   memset(op, 0, sizeof *op);
@@ -307,6 +316,12 @@ int build_conv_op(ConvOp* op, const ConvGeom& g, int n_cap) {
   p.bias_classes = g.bias_classes;
   p.out_fp32 = g.out_fp32;
   p.bias = g.bias; p.alpha = g.alpha; p.res = g.res; p.out = g.dst;
+  p.pool_xor = 0;
+  if (g.pool) {
+    if (!conv_can_pool(g.H, g.W, g.Cin, g.Cout) || g.ksize != 3 || g.stride != 1 || g.pad != 1 || g.res || g.out_fp32 || g.Cin2)
+      return set_error(CER_ERR_INVALID, "conv: this layer cannot fuse the max-pool");
+    p.pool_xor = (g.Cin == 64) ? kHaloTileW : g.W;        // halo tiles are 8 pixels wide; im2col tiles follow the map width
+  }
   op->halo_ok = g.ksize == 3 && g.stride == 1 && g.pad == 1 && g.Cin == 64 && g.Cin2 == 0 && (g.Cout == 64 || g.Cout == 128) &&
                 g.W % kHaloTileW == 0 && !g.out_fp32;
   if (op->halo_ok) {
@@ -414,7 +429,7 @@ int launch_conv(const ConvOp& op, int frames, int num_sms, cudaStream_t st) {
   p.num_m_tiles = (p.M + kBlockM - 1) / kBlockM;
   const int tiles = p.num_m_tiles * p.num_n_tiles;
   if (tiles == 0) return CER_OK;
-  if (op.halo_ok && halo_mode() != 0 && tiles >= 2 * num_sms) {
+  if (op.halo_ok && ((halo_mode() != 0 && tiles >= 2 * num_sms) || (p.pool_xor && p.cin_chunks == 1))) {
     p.tmap_a = op.tmap_halo;
     p.halo_frames = frames;
     p.halo_bands = (p.Hout + kHaloTileH - 1) / kHaloTileH;

@@ -7,6 +7,7 @@
 #include <cuda_bf16.h>
 #include <algorithm>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -201,6 +202,8 @@ extern "C" int cer_vggish_create(cer_vggish** out, const cer_vggish_weights* w, 
     g.src = p->buf[cur]; g.H = H; g.W = W; g.Cin = c.cin; g.ksize = 3; g.stride = 1; g.pad = 1;
     g.weight = c.w; g.bias = c.bias; g.bias_classes = 1; g.alpha = w->zeros;      // PReLU slope 0 == ReLU
     g.dst = p->buf[cur ^ 1]; g.Cout = c.cout; g.out_fp32 = 0;
+    const bool fuse_pool = c.pool_after && conv_can_pool(H, W, c.cin, c.cout) && !getenv("CER_NO_POOL_FUSION");
+    g.pool = fuse_pool ? 1 : 0;
     cer_vggish::Step s{};
     s.kind = 0;
     rc = build_conv_op(&s.op, g, p->n_cap);
@@ -208,7 +211,9 @@ extern "C" int cer_vggish_create(cer_vggish** out, const cer_vggish_weights* w, 
     p->steps.push_back(s);
     cur ^= 1;
     C = c.cout;
-    if (c.pool_after) {
+    if (fuse_pool) {          // the conv already wrote the pooled tensor
+      H /= 2; W /= 2;
+    } else if (c.pool_after) {
       if ((H & 1) || (W & 1) || (C % 8)) { delete p; return set_error(CER_ERR_INVALID, "vggish: pool needs even H, W and C % 8 == 0"); }
       cer_vggish::Step ps{};
       ps.kind = 1; ps.H = H; ps.W = W; ps.C = C; ps.src = p->buf[cur]; ps.dst = p->buf[cur ^ 1];

@@ -291,3 +291,19 @@ def test_alternative_heads_vs_golden(golden_dir, name):
     agree = (out.argmax(-1) == g["out"].argmax(-1)).float().mean().item()
     assert err <= 2e-2 * max(1.0, g["out"].abs().max().item()), err
     assert agree >= 0.95, agree          # 48 frames: at most two flips
+
+
+def test_vggish_fused_pool_equals_separate_pool_kernel(monkeypatch):
+    """The max-pool fused into the conv epilogue (shuffles over bf16-rounded values) must be
+    bit-identical to pooling the stored bf16 tensor with the stand-alone kernel."""
+    dev = _dev()
+    from feature_vs_text_compound_emotion_b200 import packing
+    from feature_vs_text_compound_emotion_b200.engine import VggishEngine
+    pk = packing.pack_vggish(synthetic.vggish_state_dict(2))
+    x = synthetic.logmel_patches(45, seed=21).to(dev)
+    fused = VggishEngine(pk, dev, patches_per_pass=64).forward(x).cpu()
+    monkeypatch.setenv("CER_NO_POOL_FUSION", "1")
+    plain_eng = VggishEngine(pk, dev, patches_per_pass=64)
+    assert plain_eng.launches(45) == 12 and True
+    plain = plain_eng.forward(x).cpu()
+    assert torch.equal(fused, plain)
