@@ -170,6 +170,21 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
       if (p.bias_classes == 9)
         cls = (oh == 0 ? 0 : (oh == p.Hout - 1 ? 2 : 1)) * 3 + (ow == 0 ? 0 : (ow == p.Wout - 1 ? 2 : 1));
       const size_t m = (static_cast<size_t>(n) * p.Hout + oh) * p.Wout + ow;
+      if (p.res != nullptr) {
+        // the residual read is the epilogue's only long-latency load: pull the NEXT tile's line into L2 now,
+        // a whole tile ahead of the __ldg that needs it
+        const int nt = tile + gridDim.x;
+        if (nt < total_tiles) {
+          const int n2 = nt / tiles_per_frame;
+          const int rem2 = nt - n2 * tiles_per_frame;
+          const int band2 = rem2 / p.halo_cts, ct2 = rem2 - band2 * p.halo_cts;
+          const int oh2 = band2 * kHaloTileH + ty, ow2 = ct2 * kHaloTileW + tx;
+          if (oh2 < p.Hout) {
+            const __nv_bfloat16* rp = p.res + ((static_cast<size_t>(n2) * p.Hout + oh2) * p.Wout + ow2) * p.Cout + n0;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(rp));
+          }
+        }
+      }
       const bool pool_store = p.pool_xor && valid && !(oh & 1) && !(ow & 1);
       const size_t pool_off = ((static_cast<size_t>(n) * (p.Hout >> 1) + (oh >> 1)) * (p.Wout >> 1) + (ow >> 1)) * p.Cout + n0;
       conv_epilogue_core<BN>(p, s_bias, s_alpha, tmem_base + acc * BN, n0, warp, tfull0 + acc * 8, acc_phase, valid, cls,
