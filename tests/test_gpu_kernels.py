@@ -239,3 +239,31 @@ def test_logmel_front_end_vs_reference_golden(golden_dir):
     # the examples feed VGGish directly
     want = torch.from_numpy(O.waveform_to_examples(wave.double().numpy(), 0.96, g["hop_sec"])).float()
     assert (ex - want).abs().max().item() < 2e-5
+
+
+def test_c_abi_error_paths_report_status_and_message():
+    """Bad arguments come back as negative cer_status + cer_last_error(), never as a crash or a silent
+    fallback (include/cer_b200.h conventions)."""
+    import ctypes as C
+    from feature_vs_text_compound_emotion_b200 import _capi
+    from feature_vs_text_compound_emotion_b200.engine import Ir50Engine, conv_forward
+    dev = _dev()
+    lib = _capi.lib()
+    x = torch.zeros(2, 8, 8, 32, dtype=torch.bfloat16, device=dev)            # Cin = 32: not a multiple of 64
+    w = torch.zeros(64, 9 * 32, dtype=torch.bfloat16, device=dev)
+    with pytest.raises(_capi.CerError, match="multiples of 64"):
+        conv_forward(x, w, torch.zeros(1, 64, device=dev), 3, 1, 1)
+    assert lib.cer_ce_loss(None, None, 10, 7, None, None, None) == -1 and b"cer_ce_loss" in lib.cer_last_error()
+    assert lib.cer_optimizer_step(5, None, None, None, None, 0, 0.1, 0.0, 0.9, 0.0, 1e-8, 0, 1, 1.0, None) == -1
+    # workspace too small
+    pk = packing.pack_ir50(synthetic.visual_backbone_state_dict(0))
+    eng = Ir50Engine(pk, dev, frames_per_pass=8)
+    h = C.c_void_p()
+    ws = torch.empty(1024, dtype=torch.uint8, device=dev)
+    rc = lib.cer_ir50_create(C.byref(h), C.byref(eng._w), 8, ws.data_ptr(), 1024)
+    assert rc == -4 and b"workspace" in lib.cer_last_error()
+    # shape checks of the Python mirrors
+    with pytest.raises(ValueError):
+        eng.forward(torch.zeros(2, 3, 32, 32, device=dev))
+    with pytest.raises(ValueError):
+        eng.forward(torch.zeros(2, 3, 40, 40))                               # CPU tensor
