@@ -246,4 +246,165 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm2_kernel(const __gr
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// Weights-resident CTA-pair variant (IR-50 stage 2: 128 -> 128 @20x20, 18 k-steps, one n-tile).
+// The streaming pair kernel needs 16 KB of A + 8 KB of B per 256-cycle k-step = 96 B/cycle/SM, above
+// the ~80 B/cycle the TMA path delivers (tools/tma_probe.cu; ncu: tensor pipe 58 %).  Here each CTA
+// keeps ITS HALF of the whole weight matrix (ksteps x 64 rows x 128 B = 144 KB) in shared memory for
+// the life of the CTA and the ring carries only A (64 B/cycle/SM).  Four A stages fit beside it, so
+// the ring is walked with run-time stage indices (a k-step is 256 tensor cycles at N = 128: the few
+// extra issue instructions do not matter).
+// ------------------------------------------------------------------------------------------
+template <int BN, int STAGES, int KSTEPS>
+struct Conv2BresSmem {
+  static constexpr int kBBytes = (BN / 2) * 128;             // this CTA's half of one k-step of B
+  static constexpr int kBOffset = STAGES * kABytes;
+  static constexpr int kBarOffset = kBOffset + KSTEPS * kBBytes;
+  static constexpr int kNumBars = 2 * STAGES + 5;            // full, empty, tfull[2], tempty[2], bres
+  static constexpr int kTableOffset = (kBarOffset + kNumBars * 8 + 16 + 15) & ~15;
+  static constexpr int kTableFloats = 10 * BN;
+  static constexpr int kTotal = kTableOffset + kTableFloats * 4 + 1024;
+};
+
+template <int BN, int STAGES, int KSTEPS>
+__global__ void __launch_bounds__(kConvThreads, 1) conv_igemm2_bres_kernel(const __grid_constant__ ConvKernelParams p) {
+  using L = Conv2BresSmem<BN, STAGES, KSTEPS>;
+  static_assert(KSTEPS % 2 == 0, "the two A producers split the k-steps evenly");
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOffset);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint64_t* bres_bar = tempty_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bres_bar + 1);
+  float* s_bias = reinterpret_cast<float*>(smem + L::kTableOffset);
+  float* s_alpha = s_bias + p.bias_classes * p.Cout;
+
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+  const int total_ptiles = (p.num_m_tiles + 1) >> 1;          // one n-tile
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 2 * kEpiWarps); }
+    mbar_init(bres_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == kProdWarp0 && lane == 0) tma_prefetch_desc(&p.tmap_a);
+  if (warp == kProdWarp0 + 2 && lane == 0) tma_prefetch_desc(&p.tmap_b);
+  if (warp == kMmaWarp) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(2 * BN)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  if (warp < kEpiWarps) {
+    for (int i = threadIdx.x; i < p.bias_classes * p.Cout; i += kEpiWarps * 32) s_bias[i] = __ldg(p.bias + i);
+    if (p.alpha != nullptr)
+      for (int i = threadIdx.x; i < p.Cout; i += kEpiWarps * 32) s_alpha[i] = __ldg(p.alpha + i);
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();
+  pdl_wait();
+
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar);
+  const uint32_t tfull0 = smem_u32(tfull_bar), tempty0 = smem_u32(tempty_bar);
+
+  if (warp == kProdWarp0 + 2) {
+    // ---- resident weights: every CTA loads its 64 output channels of all k-steps, once
+    if (elect_one()) {
+      const uint32_t bar = smem_u32(bres_bar) & kPeerBitMask;            // the leader's barrier
+      if (rank == 0) mbar_expect_tx_a(bar, 2 * KSTEPS * L::kBBytes);
+      for (int ks = 0; ks < KSTEPS; ++ks)
+        tma2_load_2d(&p.tmap_b, bar, smem_base + L::kBOffset + ks * L::kBBytes, ks * kBlockK, (int)rank * (BN / 2));
+    }
+    __syncwarp();
+  } else if (warp == kProdWarp0 || warp == kProdWarp0 + 1) {
+    // ---- A producers: warp q takes the k-steps g = q (mod 2), g counted across all tiles of this pair
+    const int q = warp - kProdWarp0;
+    const int hw = p.Hout * p.Wout;
+    uint32_t g = q;
+    for (int pt = pair; pt < total_ptiles; pt += num_pairs) {
+      const int m0 = (2 * pt + (int)rank) * kBlockM;
+      const int n_img = m0 / hw;
+      const int rem = m0 - n_img * hw;
+      const int oh = rem / p.Wout, ow = rem - oh * p.Wout;
+      const int cw = ow * p.stride - p.pad, ch = oh * p.stride - p.pad;
+      for (int ks = q; ks < KSTEPS; ks += 2, g += 2) {
+        const uint32_t stage = g % STAGES, phase = (g / STAGES) & 1;
+        mbar_wait_a(empty0 + stage * 8, phase ^ 1);
+        int tap = 0, chunk = ks;
+        if (p.ksize == 3) { tap = ks >> p.cin_shift; chunk = ks & (p.cin_chunks - 1); }
+        const int rr = (tap * 11) >> 5, ss = tap - rr * 3;
+        if (elect_one()) {
+          const uint32_t fb = (full0 + stage * 8) & kPeerBitMask;
+          if (rank == 0) mbar_expect_tx_a(fb, 2 * kABytes);
+          tma2_load_im2col_4d(&p.tmap_a, fb, smem_base + stage * kABytes, chunk * kBlockK, cw, ch, n_img, (uint16_t)ss,
+                              (uint16_t)rr);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == kMmaWarp) {
+    if (rank == 0) {
+      constexpr uint32_t idesc = umma_idesc(2 * kBlockM, BN, /*bf16*/ 1);
+      const uint32_t a_lo0 = umma_desc_lo(smem_base);
+      const uint32_t b_lo0 = umma_desc_lo(smem_base + L::kBOffset);
+      mbar_wait_a(smem_u32(bres_bar), 0);
+      uint32_t g = 0;
+      int it = 0;
+      for (int pt = pair; pt < total_ptiles; pt += num_pairs, ++it) {
+        const uint32_t acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait_a(tempty0 + acc * 8, acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * BN;
+        for (int ks = 0; ks < KSTEPS; ++ks, ++g) {
+          const uint32_t stage = g % STAGES, phase = (g / STAGES) & 1;
+          mbar_wait_a(full0 + stage * 8, phase);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t a_lo = a_lo0 + stage * (kABytes >> 4);
+            const uint32_t b_lo = b_lo0 + ks * (L::kBBytes >> 4);
+            umma2_f16(tmem_d, umma_desc_from_lo(a_lo), umma_desc_from_lo(b_lo), idesc, ks != 0 ? 1u : 0u);
+            umma2_f16(tmem_d, umma_desc_from_lo(a_lo + 2), umma_desc_from_lo(b_lo + 2), idesc, 1u);
+            umma2_f16(tmem_d, umma_desc_from_lo(a_lo + 4), umma_desc_from_lo(b_lo + 4), idesc, 1u);
+            umma2_f16(tmem_d, umma_desc_from_lo(a_lo + 6), umma_desc_from_lo(b_lo + 6), idesc, 1u);
+            umma2_commit_mc(empty0 + stage * 8);
+            if (ks == KSTEPS - 1) umma2_commit_mc(tfull0 + acc * 8);
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else if (warp < kEpiWarps) {
+    const uint32_t tempty_leader = tempty0 & kPeerBitMask;
+    int it = 0;
+    for (int pt = pair; pt < total_ptiles; pt += num_pairs, ++it) {
+      const uint32_t acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      conv_epilogue_tile<BN>(p, s_bias, s_alpha, tmem_base + acc * BN, 2 * pt + (int)rank, 0, warp, lane, tfull0 + acc * 8,
+                             acc_phase);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(tempty_leader + acc * 8);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == kMmaWarp) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * BN) : "memory");
+  }
+}
+
 }  // namespace cer

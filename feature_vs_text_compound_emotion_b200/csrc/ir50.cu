@@ -417,6 +417,27 @@ static int launch_conv2_inst(const ConvKernelParams& p, int num_sms, cudaStream_
   return launch_conv_kernel(conv_igemm2_kernel<BN, STAGES>, 2 * pairs, kConvThreads, L::kTotal, st, 2, p);
 }
 
+template <int BN, int STAGES, int KSTEPS>
+static int launch_conv2_bres_inst(const ConvKernelParams& p, int num_sms, cudaStream_t st) {
+  using L = Conv2BresSmem<BN, STAGES, KSTEPS>;
+  static_assert(L::kTotal <= 232448, "resident-weights pair conv kernel shared memory exceeds 227 KB");
+  static bool configured = false;
+  if (!configured) {
+    CER_CUDA(cudaFuncSetAttribute(conv_igemm2_bres_kernel<BN, STAGES, KSTEPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
+    configured = true;
+  }
+  if ((p.bias_classes + 1) * p.Cout > L::kTableFloats) return set_error(CER_ERR_INVALID, "conv: Cout too large for the epilogue table");
+  const int pairs = std::min((p.num_m_tiles + 1) / 2, num_sms / 2);
+  return launch_conv_kernel(conv_igemm2_bres_kernel<BN, STAGES, KSTEPS>, 2 * pairs, kConvThreads, L::kTotal, st, 2, p);
+}
+
+// CER_PAIR_BRES=0 disables the weights-resident pair variant (A/B timing).
+static bool pair_bres_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("CER_PAIR_BRES"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v == 1;
+}
+
 static bool pair_mode_enabled() {
   static int v = -1;
   if (v < 0) { const char* e = getenv("CER_NO_PAIR"); v = (e && e[0] == '1') ? 0 : 1; }
@@ -442,6 +463,8 @@ int launch_conv(const ConvOp& op, int frames, int num_sms, cudaStream_t st) {
   // number of times and that have at least two waves of pair tiles
   if (pair_mode_enabled() && p.ksteps2 == 0 && ksteps % 6 == 0 && tiles >= 4 * num_sms && op.bn >= 128) {
     p.tmap_b = op.tmap_b_half;
+    if (op.bn == 128 && p.num_n_tiles == 1 && ksteps == 18 && pair_bres_enabled())      // stage 2: weights stay in smem
+      return launch_conv2_bres_inst<128, 4, 18>(p, num_sms, st);
     return op.bn == 256 ? launch_conv2_inst<256, 6>(p, num_sms, st) : launch_conv2_inst<128, 6>(p, num_sms, st);
   }
   // weights-resident variants when the whole layer's B fits (Cin = 64 layers: 9 k-steps, one n-tile)
