@@ -44,6 +44,9 @@ class _PackedModule(nn.Module):
 
     def _apply(self, fn, *a, **kw):
         self.__dict__["_engine"] = None
+        self.__dict__.pop("_trainer", None)      # a training plan holds raw pointers into the old parameter storage
+        self.__dict__.pop("_preproc", None)
+        self.__dict__.pop("_logmel", None)
         return super()._apply(fn, *a, **kw)
 
     def _device(self) -> torch.device:
