@@ -51,6 +51,8 @@ def test_ir50_library_bar():
         res["eager_tf32_ms"] = _time(lambda: O.ir50_forward(sd_dev, x, "backbone."))
         with torch.autocast("cuda", dtype=torch.bfloat16):
             res["eager_bf16_autocast_ms"] = _time(lambda: O.ir50_forward(sd_dev, x, "backbone."))
+        with torch.autocast("cuda", dtype=torch.float16):          # the reference's --amp True (trainer.py:367,478)
+            res["eager_fp16_autocast_ms"] = _time(lambda: O.ir50_forward(sd_dev, x, "backbone."))
     finally:
         torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
     vb = VisualBackbone(use_pretrained=False)
