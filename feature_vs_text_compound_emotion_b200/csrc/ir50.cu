@@ -285,6 +285,16 @@ int build_conv_op(ConvOp* op, const ConvGeom& g, int n_cap) {
   const int Hout = (g.H + 2 * g.pad - g.ksize) / g.stride + 1;
   const int Wout = (g.W + 2 * g.pad - g.ksize) / g.stride + 1;
   op->bn = pick_bn(g.Cout);
+  {
+    // few output rows (the 12800 -> 512 FC: M = frames): 128 x 256 tiles would occupy a quarter of the SMs;
+    // narrower N tiles trade L2 re-reads of A for parallelism
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const long long m_tiles = ((long long)n_cap * Hout * Wout + kBlockM - 1) / kBlockM;
+    while (op->bn > 64 && m_tiles * (g.Cout / op->bn) < sms / 2 && (g.bias_classes + 1) * g.Cout <= 10 * (op->bn / 2))
+      op->bn /= 2;          // the epilogue table of the narrower instantiation must still hold [classes + 1][Cout]
+  }
   op->hw_out = Hout * Wout;
   ConvKernelParams& p = op->kp;
   int rc = make_im2col_map(&p.tmap_a, g.src, n_cap, g.H, g.W, g.Cin, g.ksize, g.stride, g.pad);
