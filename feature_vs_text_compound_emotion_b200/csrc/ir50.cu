@@ -21,8 +21,8 @@ namespace cer {
 
 // ------------------------------------------------------------------------------------------
 // Stem: conv3x3(3->64, pad 1) + BN + PReLU, fp32 NCHW in -> bf16 NHWC out.  K = 27 is not a
-// tensor-core shape; this kernel is bound by its 128 B/pixel output stream (HBM roofline).
-// One thread = one output pixel, all 64 channels; weights [27][64] broadcast from smem.
+// tensor-core shape; the kernel is bound by fp32 FMA issue (1728 FMAs per pixel), not by its
+// 128 B/pixel output stream (ncu: DRAM 10 %).  Weights [27][64] are broadcast from smem.
 // Reference: Backbone.input_layer, models/arcface_model.py:130-132.
 // ------------------------------------------------------------------------------------------
 // v2: one thread = TWO horizontally adjacent output pixels (a 3 x 4 x 3 input patch in registers,
