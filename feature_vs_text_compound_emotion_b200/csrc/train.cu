@@ -537,6 +537,18 @@ __global__ void attn_fwd_kernel(const AttnArgs a) {
   }
 }
 
+// attention probabilities only: maps[r][h][m][n] (MultimodalMultiheadAttention(return_attention=True))
+__global__ void attn_maps_kernel(const AttnArgs a, float* __restrict__ maps) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.R * a.H) return;
+  const int r = i / a.H, h = i - r * a.H;
+  float att[CER_MAX_MODALS][CER_MAX_MODALS];
+  attn_probs(a, r, h, att);
+  float* o = maps + (long long)i * a.M * a.M;
+  for (int m = 0; m < a.M; ++m)
+    for (int n = 0; n < a.M; ++n) o[m * a.M + n] = att[m][n];
+}
+
 __global__ void attn_bwd_kernel(const AttnArgs a) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= a.R * a.H) return;
@@ -1132,6 +1144,23 @@ extern "C" int cer_optimizer_step(int32_t kind, float* params, const float* grad
   const int blocks = (int)std::min<int64_t>((n + 255) / 256, 148 * 16);
   optimizer_kernel<<<blocks, 256, 0, st>>>(kind, params, grads, state_m, state_v, (long long)n, lr, weight_decay,
                                            beta1_or_momentum, beta2_or_dampening, eps, nesterov, step, bc1, bc2s, grad_scale);
+  CER_CUDA(cudaGetLastError());
+  return CER_OK;
+}
+
+extern "C" int cer_modal_attention_maps(const float* const* qkv_dev, int64_t rows, int32_t n_modals, int32_t num_heads,
+                                        int32_t head_dim, float* maps_out_dev, void* stream) {
+  if (!qkv_dev || !maps_out_dev || rows < 0 || n_modals < 1 || n_modals > CER_MAX_MODALS || num_heads < 1 || head_dim < 1 ||
+      rows > (1 << 24))
+    return set_error(CER_ERR_INVALID, "cer_modal_attention_maps: bad argument");
+  if (rows == 0) return CER_OK;
+  AttnArgs a{};
+  for (int m = 0; m < n_modals; ++m) {
+    if (!qkv_dev[m]) return set_error(CER_ERR_INVALID, "cer_modal_attention_maps: null qkv pointer");
+    a.qkv[m] = qkv_dev[m];
+  }
+  a.R = (int)rows; a.M = n_modals; a.H = num_heads; a.hd = head_dim;
+  attn_maps_kernel<<<(int)((rows * num_heads + 127) / 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(a, maps_out_dev);
   CER_CUDA(cudaGetLastError());
   return CER_OK;
 }

@@ -401,7 +401,24 @@ class MultimodalTransformerEncoder(_PackedModule):
         return fused.view(B, T, -1)
 
     def get_attention_maps(self, x, mask=None):
-        raise NotImplementedError("attention-map export is a visualisation helper outside the inference path")
+        """transformer.py:211-215: ``[attention]`` with attention [B, num_heads, T, M, M] (the softmax
+        of the modality-by-modality scores, one 3x3 map per frame and head)."""
+        import ctypes as C
+        from . import _capi, engine as E
+        if mask is not None:
+            raise NotImplementedError("mask is never passed on the LFAN path (model.py:517)")
+        B, T, _ = x[self.modalities[0]].shape
+        rows = B * T
+        attn = self.layers.self_attn
+        qkv = [E.linear(x[m].float().reshape(rows, -1).contiguous(), attn.qkv_proj[m].weight, attn.qkv_proj[m].bias)
+               for m in self.modalities]
+        ptrs = (C.c_void_p * len(qkv))(*[t.data_ptr() for t in qkv])
+        M, H = len(self.modalities), self.num_heads
+        maps = torch.empty(rows, H, M, M, dtype=torch.float32, device=qkv[0].device)
+        with torch.cuda.device(maps.device):
+            _capi.check(_capi.lib().cer_modal_attention_maps(ptrs, rows, M, H, self.modal_dim // H, maps.data_ptr(),
+                                                             _capi.current_stream_ptr()), "cer_modal_attention_maps")
+        return [maps.view(B, T, H, M, M).permute(0, 2, 1, 3, 4)]
 
 
 # ----------------------------------------------------------------------------------------------

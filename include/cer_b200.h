@@ -210,6 +210,12 @@ typedef struct cer_fusion_weights {
   const float* br;                  /* fp32 [n_out]                                               */
 } cer_fusion_weights;
 
+/* Attention probabilities of the cross-modal attention (MultimodalTransformerEncoder.get_attention_maps,
+ * transformer.py:211-215 -> scaled_dot_product :11-19).  qkv_dev[m]: fp32 [rows][3*modal_dim] = qkv_proj.<m>(x_m)
+ * (cer_linear_forward), per head laid out q|k|v; maps_out_dev: fp32 [rows][num_heads][n_modals][n_modals]. */
+int cer_modal_attention_maps(const float* const* qkv_dev, int64_t rows, int32_t n_modals, int32_t num_heads, int32_t head_dim,
+                             float* maps_out_dev, void* stream);
+
 int cer_fusion_head_forward(const cer_fusion_weights* w, const float* const* feats_dev, int64_t rows,
                             float* logits_dev, float* fused_out_dev /* [rows][E] or NULL */, void* stream);
 

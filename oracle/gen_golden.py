@@ -15,6 +15,7 @@ reference modules, imported as they are, are the source of truth):
   * eval_transform.pt -- the reference's eval transform classes (PIL resize 48, crop 40, normalise) on seeded uint8 frames
   * logmel.pt       -- mel_features.log_mel_spectrogram + my_frame (the reference code) on a seeded 3 s waveform
   * heads.pt        -- CAN / JMT / MT forward from pixels (B=2 x T=24) and their state_dict key listings
+  * attention_maps.pt -- MultimodalTransformerEncoder.get_attention_maps on seeded encoder outputs
   * windowing.json  -- Trainer.windowing outputs for a set of lengths
 Weights are NOT stored: they are regenerated from the seed by
 feature_vs_text_compound_emotion_b200.synthetic (identical on every machine), and are loaded
@@ -232,6 +233,15 @@ def main():
                        "keys": {k: list(v.shape) for k, v in jm.state_dict().items()}}
     torch.save(heads, os.path.join(OUT, "heads.pt"))
     print("heads", {k: (tuple(v["out"].shape), len(v["keys"])) for k, v in heads.items()})
+
+    # ---- attention maps of the cross-modal encoder (transformer.py:211-215) ---------------------
+    from models.transformer import MultimodalTransformerEncoder
+    enc = MultimodalTransformerEncoder(modalities=mods3, input_dim={"video": 128, "vggish": 32, "bert": 128}, modal_dim=32,
+                                       num_heads=2, dropout=0.1)
+    enc.load_state_dict({k[len("fusion."):]: v for k, v in fsd.items() if k.startswith("fusion.")}, strict=True)
+    enc.eval()
+    xa_ = {m: torch.randn(2, 50, d, generator=torch.Generator().manual_seed(3)) for m, d in zip(mods3, (128, 32, 128))}
+    torch.save({"seed": 3, "T": 50, "maps": enc.get_attention_maps(xa_)[0]}, os.path.join(OUT, "attention_maps.pt"))
 
     # ---- windowing (trainer.py imports pynvml/munch, absent here: exec the one function) ----
     src = open(os.path.join(REF, "trainer.py")).read()

@@ -655,3 +655,21 @@ def jmt_forward(sd: SD, X: Dict[str, Tensor], modalities: Sequence[str], model_n
     enc = encoder_block(sd, f + "final_encoder", st)
     out = mha1(sd, f + "final_self_attention", enc, enc, enc).view(L, B, S, E)[:, :, -1, :].permute(1, 0, 2)
     return _head_tail(sd, out)
+
+
+
+def attention_maps(sd: SD, prefix: str, feats: Dict[str, Tensor], modalities: Sequence[str], modal_dim: int = 32,
+                   num_heads: int = 2) -> Tensor:
+    """MultimodalTransformerEncoder.get_attention_maps (transformer.py:211-215): softmax(QK^T/sqrt(hd))
+    over the modality tokens, [B, H, T, M, M]."""
+    hd = modal_dim // num_heads
+    a = prefix + "layers.self_attn."
+    qs, ks = [], []
+    for m in modalities:
+        qkv = F.linear(feats[m], sd[f"{a}qkv_proj.{m}.weight"], sd[f"{a}qkv_proj.{m}.bias"])
+        B, T, _ = qkv.shape
+        qkv = qkv.view(B, T, num_heads, 3, hd)
+        qs.append(qkv[:, :, :, 0]); ks.append(qkv[:, :, :, 1])
+    Q, K = torch.stack(qs, 3), torch.stack(ks, 3)
+    att = torch.softmax(torch.einsum("bthmd,bthnd->bthmn", Q, K) / math.sqrt(hd), dim=-1)
+    return att.permute(0, 2, 1, 3, 4)

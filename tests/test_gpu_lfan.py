@@ -307,3 +307,15 @@ def test_vggish_fused_pool_equals_separate_pool_kernel(monkeypatch):
     assert plain_eng.launches(45) == 12 and True
     plain = plain_eng.forward(x).cpu()
     assert torch.equal(fused, plain)
+
+
+def test_get_attention_maps_vs_golden(golden_dir):
+    dev = _dev()
+    g = torch.load(os.path.join(golden_dir, "attention_maps.pt"))
+    mods = ["video", "vggish", "bert"]
+    m = _lfan(mods, dev)
+    x = {k: torch.randn(2, g["T"], d, generator=torch.Generator().manual_seed(g["seed"])).to(dev) for k, d in zip(mods, (128, 32, 128))}
+    maps = m.fusion.get_attention_maps(x)
+    assert isinstance(maps, list) and len(maps) == 1 and maps[0].shape == (2, 2, g["T"], 3, 3)
+    assert (maps[0].cpu() - g["maps"]).abs().max().item() < 1e-5
+    assert torch.allclose(maps[0].sum(-1).cpu(), torch.ones(2, 2, g["T"], 3), atol=1e-5)

@@ -183,3 +183,12 @@ def test_alternative_heads_match_reference(golden_dir):
         assert {k: list(v.shape) for k, v in sd.items()} == g[name]["keys"] and list(sd) == list(g[name]["keys"])
         out = O.jmt_forward(sd, _head_inputs(g, name), g[name]["modalities"], name)
         assert (out - g[name]["out"]).abs().max().item() < 2e-5, name
+
+
+def test_attention_maps_match_reference(golden_dir):
+    g = torch.load(os.path.join(golden_dir, "attention_maps.pt"))
+    mods = ["video", "vggish", "bert"]
+    sd = synthetic.lfan_state_dict(0, mods)
+    x = {m: torch.randn(2, g["T"], d, generator=torch.Generator().manual_seed(g["seed"])) for m, d in zip(mods, (128, 32, 128))}
+    maps = O.attention_maps(sd, "fusion.", x, mods)
+    assert maps.shape == (2, 2, g["T"], 3, 3) and (maps - g["maps"]).abs().max().item() < 1e-6
