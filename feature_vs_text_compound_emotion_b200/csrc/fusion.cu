@@ -55,9 +55,19 @@ __global__ void __launch_bounds__(kFusThreads) fusion_head_kernel(cer_fusion_wei
   float* s_val = s_qkv + kFR * d.M * d.D3;
 
   const float* feats[CER_MAX_MODALS] = {f0, f1, f2, f3};
-  for (int m = 0; m < d.M; ++m)
-    for (int i = threadIdx.x; i < d.dim[m] * d.D3; i += kFusThreads) s_wqkv[d.doff[m] * d.D3 + i] = w.wqkv[m][i];
-  for (int i = threadIdx.x; i < d.E * d.E; i += kFusThreads) s_wo[i] = w.wo[i];
+  // weight staging dominates this kernel at small batches (150 KB per CTA for ~1 frame group per warp):
+  // 16-byte loads where the host verified alignment (D3 and E*E are multiples of 4 floats)
+  for (int m = 0; m < d.M; ++m) {
+    const int n4 = d.dim[m] * d.D3 / 4;
+    const float4* src = reinterpret_cast<const float4*>(w.wqkv[m]);
+    float4* dst = reinterpret_cast<float4*>(s_wqkv + d.doff[m] * d.D3);
+    for (int i = threadIdx.x; i < n4; i += kFusThreads) dst[i] = __ldg(src + i);
+  }
+  {
+    const float4* src = reinterpret_cast<const float4*>(w.wo);
+    float4* dst = reinterpret_cast<float4*>(s_wo);
+    for (int i = threadIdx.x; i < d.E * d.E / 4; i += kFusThreads) dst[i] = __ldg(src + i);
+  }
   for (int i = threadIdx.x; i < (d.dim[0] + d.E) * d.n_out; i += kFusThreads) s_wr[i] = w.wr[i];
   for (int m = 0; m < d.M; ++m)
     for (int i = threadIdx.x; i < d.D3; i += kFusThreads) s_bqkv[m * d.D3 + i] = w.bqkv[m][i];
@@ -267,6 +277,10 @@ extern "C" int cer_fusion_head_forward(const cer_fusion_weights* w, const float*
   }
   d.din_total = off;
   if (!w->wo || !w->bo || !w->ln_g || !w->ln_b || !w->wr || !w->br) return set_error(CER_ERR_INVALID, "fusion: null weight");
+  if (d.D3 % 4 || (d.E * d.E) % 4 || (reinterpret_cast<uintptr_t>(w->wo) & 15))
+    return set_error(CER_ERR_INVALID, "fusion: modal_dim must be a multiple of 4 and weights 16B aligned");
+  for (int m = 0; m < d.M; ++m)
+    if (reinterpret_cast<uintptr_t>(w->wqkv[m]) & 15) return set_error(CER_ERR_INVALID, "fusion: wqkv must be 16B aligned");
   const size_t floats = (size_t)d.din_total * d.D3 + (size_t)d.E * d.E + (size_t)(d.dim[0] + d.E) * d.n_out +
                         (size_t)d.M * d.D3 + 3 * (size_t)d.E + kMaxOut +
                         (size_t)kFusWarps * kFR * (d.din_total + d.M * d.D3 + d.E);
