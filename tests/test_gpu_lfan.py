@@ -319,3 +319,43 @@ def test_get_attention_maps_vs_golden(golden_dir):
     assert isinstance(maps, list) and len(maps) == 1 and maps[0].shape == (2, 2, g["T"], 3, 3)
     assert (maps[0].cpu() - g["maps"]).abs().max().item() < 1e-5
     assert torch.allclose(maps[0].sum(-1).cpu(), torch.ones(2, 2, g["T"], 3), atol=1e-5)
+
+
+def test_full_size_properties_config2():
+    """BASELINE configs[1] size (8 x 300 frames): properties that need no oracle run at that size --
+    unit-norm embeddings, bit-exact determinism, frame-permutation equivariance (every frame is
+    independent in eval mode, whatever tile it lands in), pass-size invariance, and causality /
+    window independence of the head."""
+    dev = _dev()
+    from feature_vs_text_compound_emotion_b200.models.arcface_model import Backbone
+    mods = ["video", "vggish", "bert"]
+    m = _lfan(mods, dev, seed=8)
+    vb = m.spatial["visual"]
+    n = 2400
+    x = synthetic.frames(n, seed=81).to(dev)
+    e1 = vb(x)
+    assert torch.allclose(e1.norm(dim=1), torch.ones(n, device=dev), atol=1e-4)
+    assert torch.equal(vb(x), e1)                                        # deterministic
+    perm = torch.randperm(n, generator=torch.Generator().manual_seed(82)).to(dev)
+    assert torch.equal(vb(x[perm]), e1[perm])                            # frames are independent
+    old = Backbone.frames_per_pass
+    Backbone.frames_per_pass = 700                                       # 3 full passes + a ragged one
+    try:
+        vb.backbone.repack()
+        e2 = vb(x)
+    finally:
+        Backbone.frames_per_pass = old
+        vb.backbone.repack()
+    assert torch.equal(e2, e1)
+    # head: logits of frame t depend only on frames <= t of the same window
+    f = synthetic.feature_windows(8, 300, seed=83, modalities=["vggish", "bert"])
+    X = {"video": e1.view(8, 300, 512), "vggish": f["vggish"].squeeze(1).to(dev), "bert": f["bert"].squeeze(1).to(dev)}
+    y0 = m.forward_features({k: v.clone() for k, v in X.items()})
+    X2 = {k: v.clone() for k, v in X.items()}
+    X2["bert"][:, 200:] += 1.0                                           # change the future of every window
+    X2["vggish"][3] = 0.0                                                # and all of window 3
+    y1 = m.forward_features(X2)
+    keep = [w for w in range(8) if w != 3]
+    assert torch.equal(y1[keep, :200], y0[keep, :200])
+    assert not torch.equal(y1[keep, 200:], y0[keep, 200:])
+    assert not torch.equal(y1[3], y0[3])
