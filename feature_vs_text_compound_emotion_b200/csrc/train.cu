@@ -1164,3 +1164,20 @@ extern "C" int cer_modal_attention_maps(const float* const* qkv_dev, int64_t row
   CER_CUDA(cudaGetLastError());
   return CER_OK;
 }
+
+extern "C" int cer_modal_attention_forward(const float* const* qkv_dev, int64_t rows, int32_t n_modals, int32_t num_heads,
+                                           int32_t head_dim, float* vals_out_dev, void* stream) {
+  if (!qkv_dev || !vals_out_dev || rows < 0 || n_modals < 1 || n_modals > CER_MAX_MODALS || num_heads < 1 || head_dim < 1 ||
+      rows > (1 << 24))
+    return set_error(CER_ERR_INVALID, "cer_modal_attention_forward: bad argument");
+  if (rows == 0) return CER_OK;
+  AttnArgs a{};
+  for (int m = 0; m < n_modals; ++m) {
+    if (!qkv_dev[m]) return set_error(CER_ERR_INVALID, "cer_modal_attention_forward: null qkv pointer");
+    a.qkv[m] = qkv_dev[m];
+  }
+  a.vals = vals_out_dev; a.R = (int)rows; a.M = n_modals; a.H = num_heads; a.hd = head_dim;
+  attn_fwd_kernel<<<(int)((rows * num_heads + 127) / 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  CER_CUDA(cudaGetLastError());
+  return CER_OK;
+}

@@ -247,6 +247,17 @@ class FusionEngine:
         self.dims = list(fw["dim"])
         self.n_out = fw["n_out"]
         self.E = fw["modal_dim"] * fw["n_modals"]
+        self.num_heads, self.head_dim = fw["num_heads"], fw["modal_dim"] // fw["num_heads"]
+        # the fused kernel stages every weight in shared memory (~150 KB at the reference's sizes);
+        # larger configurations run the same arithmetic as separate kernels
+        fused_floats = (sum(self.dims) * 3 * fw["modal_dim"] + self.E * self.E + (self.dims[0] + self.E) * self.n_out
+                        + fw["n_modals"] * 3 * fw["modal_dim"] + 3 * self.E + 16
+                        + 4 * 4 * (sum(self.dims) + fw["n_modals"] * 3 * fw["modal_dim"] + self.E))
+        self.composed = fused_floats * 4 > 227 * 1024 or self.E > 128 or self.n_out > 16
+        if self.composed:
+            d = lambda t: t.to(self.device).contiguous()
+            self._c = {"wqkv": [d(t) for t in fw["wqkv_oi"]], "bqkv": [d(t) for t in fw["bqkv"]], "wo": d(fw["wo_oi"]),
+                       "bo": d(fw["bo"]), "g": d(fw["ln_g"]), "b": d(fw["ln_b"]), "wr": d(fw["wr_oi"]), "br": d(fw["br"])}
 
     def forward(self, feats: Sequence[torch.Tensor], want_fused: bool = False):
         """feats[m]: [rows, D_m] fp32 -> logits [rows, n_out] (and fused [rows, E])."""
@@ -261,6 +272,8 @@ class FusionEngine:
             f = f.contiguous()
             keep.append(f)
             ptrs[i] = f.data_ptr()
+        if self.composed:
+            return self._forward_composed(keep, rows, want_fused)
         logits = torch.empty(rows, self.n_out, dtype=torch.float32, device=self.device)
         fused = torch.empty(rows, self.E, dtype=torch.float32, device=self.device) if want_fused else None
         with torch.cuda.device(self.device):
@@ -348,6 +361,26 @@ class LogMelEngine:
             check(lib().cer_frame_examples(lm.data_ptr(), starts.data_ptr(), n, win, self.cfg["n_mel"], out.data_ptr(),
                                            _capi.current_stream_ptr()), "cer_frame_examples")
         return out
+
+
+def _fusion_forward_composed(self, feats, rows, want_fused):
+    """qkv_proj -> modal attention -> o_proj -> LayerNorm -> cat -> regressor as separate kernels."""
+    c = self._c
+    qkv = [linear(f, c["wqkv"][i], c["bqkv"][i]) for i, f in enumerate(feats)]
+    ptrs = (C.c_void_p * len(qkv))(*[t.data_ptr() for t in qkv])
+    vals = torch.empty(rows, self.E, dtype=torch.float32, device=self.device)
+    with torch.cuda.device(self.device):
+        check(lib().cer_modal_attention_forward(ptrs, rows, len(qkv), self.num_heads, self.head_dim, vals.data_ptr(),
+                                                _capi.current_stream_ptr()), "cer_modal_attention_forward")
+    fused = add_layernorm(linear(vals, c["wo"], c["bo"]), None, c["g"], c["b"])
+    cat = torch.empty(rows, self.dims[0] + self.E, dtype=torch.float32, device=self.device)
+    cat[:, :self.dims[0]].copy_(feats[0])
+    cat[:, self.dims[0]:].copy_(fused)
+    logits = linear(cat, c["wr"], c["br"])
+    return (logits, fused) if want_fused else logits
+
+
+FusionEngine._forward_composed = _fusion_forward_composed
 
 
 def stitch_windows(win_logits: torch.Tensor, win_start: torch.Tensor, length: int) -> torch.Tensor:

@@ -176,7 +176,12 @@ def pack_fusion(sd: Dict[str, torch.Tensor], modalities: Sequence[str], modal_di
            "ln_g": sd[prefix + "layers.norm1.weight"].float().contiguous(),
            "ln_b": sd[prefix + "layers.norm1.bias"].float().contiguous(),
            "wr": sd[regressor + ".weight"].t().float().contiguous(),
-           "br": sd[regressor + ".bias"].float().contiguous()}
+           "br": sd[regressor + ".bias"].float().contiguous(),
+           # nn.Linear layout [out][in] for the composed path (cer_linear_forward) used when the fused
+           # kernel's shared-memory weight staging does not fit (large modal_dim)
+           "wqkv_oi": [sd[f"{a}qkv_proj.{m}.weight"].float().contiguous() for m in modalities],
+           "wo_oi": sd[a + "o_proj.weight"].float().contiguous(),
+           "wr_oi": sd[regressor + ".weight"].float().contiguous()}
     out["n_out"] = int(out["br"].shape[0])
     return out
 

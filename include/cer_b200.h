@@ -216,6 +216,12 @@ typedef struct cer_fusion_weights {
 int cer_modal_attention_maps(const float* const* qkv_dev, int64_t rows, int32_t n_modals, int32_t num_heads, int32_t head_dim,
                              float* maps_out_dev, void* stream);
 
+/* The attention itself for configurations whose weights do not fit the fused kernel's shared memory:
+ * vals_out_dev fp32 [rows][n_modals*num_heads*head_dim] = softmax(QK^T/sqrt(hd))V + V, packed (head, modal, dim)
+ * (transformer.py:150-159); combine with cer_linear_forward (qkv_proj, o_proj, regressor) and cer_add_layernorm. */
+int cer_modal_attention_forward(const float* const* qkv_dev, int64_t rows, int32_t n_modals, int32_t num_heads,
+                                int32_t head_dim, float* vals_out_dev, void* stream);
+
 int cer_fusion_head_forward(const cer_fusion_weights* w, const float* const* feats_dev, int64_t rows,
                             float* logits_dev, float* fused_out_dev /* [rows][E] or NULL */, void* stream);
 

@@ -359,3 +359,24 @@ def test_full_size_properties_config2():
     assert torch.equal(y1[keep, :200], y0[keep, :200])
     assert not torch.equal(y1[keep, 200:], y0[keep, 200:])
     assert not torch.equal(y1[3], y0[3])
+
+
+def test_lfan_variants_modalities_heads_regression():
+    """Other configurations the constructor allows: two modalities with another leader, 4 heads of 16,
+    REGRESSION task (tanh on the output, model.py:523) with 2 outputs."""
+    dev = _dev()
+    from feature_vs_text_compound_emotion_b200.models.model import LFAN
+    mods = ["vggish", "bert"]
+    kw = dict(modal_dim=64, tcn_channels=synthetic.TCN_CHANNELS)
+    sd = synthetic.head_state_dict(9, mods, output_dim=2, modal_dim=64)
+    m = LFAN(backbone_settings=BS, output_dim=2, task="REGRESSION", modality=mods, kernel_size=5, example_length=300,
+             tcn_channel=synthetic.TCN_CHANNELS, modal_dim=64, num_heads=4, root_dir="", device=dev)
+    m.init()
+    m.load_state_dict(sd, strict=True)
+    m = m.to(dev).eval()
+    X = synthetic.feature_windows(2, 300, seed=91, modalities=mods)
+    want = torch.tanh(O.lfan_forward(sd, {k: v.clone() for k, v in X.items()}, mods, modal_dim=64, num_heads=4))
+    out = m({k: v.to(dev) for k, v in X.items()}).cpu()
+    assert out.shape == (2, 300, 2)
+    assert (out - want).abs().max().item() <= 5e-3
+    del kw
