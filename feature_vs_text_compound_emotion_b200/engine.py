@@ -171,7 +171,7 @@ class TcnEngine:
         self.precision = precision
         self._keep: List[torch.Tensor] = []
         self.blocks: List[TcnBlock] = []
-        self.c_in = blocks[0]["c_in"]
+        self.c_in = blocks[0]["c_in"]                    # what the caller passes
         self.c_out = blocks[-1]["c_out"]
 
         def put(t):
@@ -195,6 +195,8 @@ class TcnEngine:
             raise ValueError(f"expected [B,T,{self.c_in}], got {tuple(x.shape)}")
         if x.device != self.device or x.dtype != torch.float32:
             raise ValueError("input must be fp32 on the engine's CUDA device")
+        if self.blocks[0].c_in != self.c_in:             # channels padded to the kernel's 32-channel chunks
+            x = torch.nn.functional.pad(x, (0, self.blocks[0].c_in - self.c_in))
         x = x.contiguous()
         B, T, _ = x.shape
         stream = _capi.current_stream_ptr()

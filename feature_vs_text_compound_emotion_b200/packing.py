@@ -125,10 +125,22 @@ def tcn_block_to_kmajor(blk: dict) -> dict:
     w1 [cout][k*cin] with K = (tap, ci); w2 [cout][k*cout (+ cin)] with the downsample appended."""
     out = dict(blk)
     k, cin, cout = blk["w1"].shape
-    out["w1"] = blk["w1"].permute(2, 0, 1).reshape(cout, k * cin).contiguous()
+    w1, wd = blk["w1"], blk["wd"]
+    if cin % 32:
+        # the tensor-core kernel moves 32-channel chunks: pad the input channels with zero weights
+        # (mfcc: 39 -> 64, egemaps: 88 -> 96); TcnEngine zero-pads the features to match
+        pad = 32 - cin % 32
+        w1 = torch.nn.functional.pad(w1, (0, 0, 0, pad))                     # [k][cin+pad][cout]
+        if wd is not None:
+            wd = torch.nn.functional.pad(wd, (0, 0, 0, pad))                 # [cin+pad][cout]
+        cin += pad
+        out["c_in"] = cin
+    if cout % 32:
+        raise ValueError("TemporalBlock output channels must be multiples of 32 for the tensor-core kernel")
+    out["w1"] = w1.permute(2, 0, 1).reshape(cout, k * cin).contiguous()
     w2 = blk["w2"].permute(2, 0, 1).reshape(cout, k * cout)
-    if blk["wd"] is not None:
-        w2 = torch.cat([w2, blk["wd"].t()], dim=1)
+    if wd is not None:
+        w2 = torch.cat([w2, wd.t()], dim=1)
     out["w2"] = w2.contiguous()
     out["layout"] = "k_major"
     return out

@@ -380,3 +380,22 @@ def test_lfan_variants_modalities_heads_regression():
     assert out.shape == (2, 300, 2)
     assert (out - want).abs().max().item() <= 5e-3
     del kw
+
+
+def test_lfan_odd_feature_widths_mfcc_egemaps():
+    """mfcc (39-d) and egemaps (88-d) inputs (model.py:388-393) are not multiples of the tensor-core
+    kernel's 32-channel chunks: weights and features are zero-padded, results unchanged."""
+    dev = _dev()
+    from feature_vs_text_compound_emotion_b200.models.model import LFAN
+    mods = ["mfcc", "egemaps", "bert"]
+    sd = synthetic.head_state_dict(10, mods)
+    m = LFAN(backbone_settings=BS, output_dim=7, task="CLASSIFICATION", modality=mods, kernel_size=5, example_length=300,
+             tcn_channel=synthetic.TCN_CHANNELS, modal_dim=32, num_heads=2, root_dir="", device=dev)
+    m.init()
+    m.load_state_dict(sd, strict=True)
+    m = m.to(dev).eval()
+    X = synthetic.feature_windows(2, 300, seed=92, modalities=mods)
+    want = O.lfan_forward(sd, {k: v.clone() for k, v in X.items()}, mods)
+    out = m({k: v.to(dev) for k, v in X.items()}).cpu()
+    assert (out - want).abs().max().item() <= 5e-3
+    assert (out.argmax(-1) == want.argmax(-1)).float().mean().item() >= 0.995
