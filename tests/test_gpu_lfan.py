@@ -399,3 +399,19 @@ def test_lfan_odd_feature_widths_mfcc_egemaps():
     out = m({k: v.to(dev) for k, v in X.items()}).cpu()
     assert (out - want).abs().max().item() <= 5e-3
     assert (out.argmax(-1) == want.argmax(-1)).float().mean().item() >= 0.995
+
+
+def test_backbone_standalone_7x7_head_56px():
+    """arcface_model.Backbone(50, ...) as the reference constructs it stand-alone: 7x7 output layer,
+    i.e. 56x56 inputs with this repo's stage-1 stride (arcface_model.py:98, :133-137)."""
+    dev = _dev()
+    from feature_vs_text_compound_emotion_b200.models.arcface_model import Backbone
+    sd = {k[len("backbone."):]: v for k, v in synthetic.visual_backbone_state_dict(11, spatial=7).items() if k.startswith("backbone.")}
+    bb = Backbone(50, 0.4, 3, 'ir')
+    bb.load_state_dict(sd, strict=True)
+    bb = bb.to(dev).eval()
+    x = synthetic.frames(6, seed=93, size=56)
+    emb = bb(x.to(dev)).cpu()
+    ref = O.ir50_forward(sd, x, "")
+    assert emb.shape == (6, 512)
+    assert F.cosine_similarity(emb, ref, dim=1).min().item() >= 0.999
