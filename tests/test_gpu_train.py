@@ -7,6 +7,7 @@ import warnings
 
 import pytest
 import torch
+import torch.nn.functional as F
 
 from feature_vs_text_compound_emotion_b200 import synthetic
 from oracle import lfan_oracle as O
@@ -204,3 +205,54 @@ def test_ce_loss_and_optimizer_entry_points():
                                         _capi.current_stream_ptr()))
     assert abs(loss.item() - ref.item()) < 1e-5
     assert (dl.cpu() - lg.grad).abs().max().item() < 1e-7
+
+
+def test_training_from_pixels_with_frozen_backbone_and_odd_widths():
+    """(1) LFAN(video, vggish, bert).train(): frames go through the frozen IR-50 kernels (eval mode,
+    see INTEGRATION.md), the head trains; compared with the oracle on the oracle's own embeddings.
+    (2) a head with 39-/88-wide inputs (mfcc, egemaps) through the training GEMMs' unaligned paths."""
+    dev = _dev()
+    from feature_vs_text_compound_emotion_b200.models.model import LFAN
+    from feature_vs_text_compound_emotion_b200.training import HeadTrainer
+    mods = ["video", "vggish", "bert"]
+    m = LFAN(backbone_settings=BS, output_dim=7, task="CLASSIFICATION", modality=mods, kernel_size=5, example_length=60,
+             tcn_channel=synthetic.TCN_CHANNELS, modal_dim=32, num_heads=2, root_dir="", device=dev)
+    m.init(visual_state_dict=synthetic.visual_backbone_state_dict(4))
+    sd = synthetic.lfan_state_dict(4, mods)
+    m.load_state_dict(sd, strict=True)
+    m = m.to(dev).train()
+    for mod in m.modules():
+        if isinstance(mod, torch.nn.Dropout):
+            mod.p = 0.0
+    f = synthetic.feature_windows(1, 60, seed=51, modalities=["vggish", "bert"])
+    vid = synthetic.frames(60, seed=52).view(1, 60, 3, 40, 40)
+    labels = torch.randint(0, 7, (1, 60, 1), generator=torch.Generator().manual_seed(53)).float()
+    with torch.enable_grad():
+        out = m({"video": vid.to(dev), "vggish": f["vggish"].to(dev), "bert": f["bert"].to(dev)})
+        loss = torch.nn.functional.cross_entropy(out.view(60, 7), labels.view(60).long().to(dev))
+        loss.backward()
+    assert all(p.grad is None for p in m.spatial.parameters())
+    # the head's gradients are checked on the embeddings the frozen kernels produced (with 60 rows the
+    # batch-statistics BatchNorm amplifies the backbone's bf16 noise, which is a property of the model)
+    with torch.no_grad():
+        emb = m.spatial["visual"](vid.view(60, 3, 40, 40).to(dev)).cpu().view(1, 60, 512)
+    assert F.cosine_similarity(emb[0], O.ir50_forward(sd, vid.view(60, 3, 40, 40), "spatial.visual.backbone."), dim=1).min() >= 0.999
+    ref_loss, grads, _, _ = O.train_step(sd, {"video": emb, "vggish": f["vggish"], "bert": f["bert"]}, labels, mods,
+                                         {"name": "sgd", "lr": 0.0}, None)
+    assert abs(loss.item() - float(ref_loss)) < 2e-5
+    named = dict(m.named_parameters())
+    for k, g in grads.items():
+        _grad_close(named[k].grad.cpu(), g)
+
+    mods2 = ["mfcc", "egemaps"]
+    m2 = _lfan(mods2, dev, seed=6, length=100, p_drop=0.0)
+    tr = HeadTrainer(m2, 2, 100)
+    sd2 = synthetic.lfan_state_dict(6, mods2)
+    X = synthetic.feature_windows(2, 100, seed=54, modalities=mods2)
+    y = torch.randint(0, 7, (2, 100, 1), generator=torch.Generator().manual_seed(55)).float()
+    logits = tr.forward({k: v.to(dev) for k, v in X.items()}, seed=1)
+    loss2, dl = tr.cross_entropy(logits, y.to(dev))
+    tr.backward(dl)
+    ref2, grads2, _, _ = O.train_step(sd2, X, y, mods2, {"name": "sgd", "lr": 0.0}, None)
+    assert abs(loss2.item() - float(ref2)) < 2e-5
+    _check_grads(tr, grads2)
