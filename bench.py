@@ -515,11 +515,13 @@ def main():
         from feature_vs_text_compound_emotion_b200 import synthetic
         threads = os.cpu_count() or 1
         sd = synthetic.lfan_state_dict(0, MODS)
-        cpu_reference_step(sd, 16, threads)
-        n = 96
-        dt = cpu_reference_step(sd, n, threads)
+        t_cal = cpu_reference_step(sd, 16, threads)
+        # ~10-30 s of CPU work: as much of one step (2400 frames) as fits, in chunks of 300 frames
+        n = int(max(96, min(frames, 300 * max(1, int(20.0 / max(t_cal * 300 / 16, 1e-3))))))
+        dt = sum(cpu_reference_step(sd, min(300, n - f0), threads) for f0 in range(0, n, 300))
         line["cpu_baseline"] = {"value": n / dt, "unit": "frames/s", "cores": threads, "kind": "port",
-                                "sample": f"{n} frames through IR-50 + one {LENGTH}-frame head window, oracle port fp32"}
+                                "sample": f"{n} frames through IR-50 (chunks of 300) + a {LENGTH}-frame head window per chunk, "
+                                          "oracle port fp32, torch CPU on all host threads"}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
