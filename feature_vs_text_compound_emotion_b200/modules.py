@@ -47,6 +47,7 @@ class _PackedModule(nn.Module):
         self.__dict__.pop("_trainer", None)      # a training plan holds raw pointers into the old parameter storage
         self.__dict__.pop("_preproc", None)
         self.__dict__.pop("_logmel", None)
+        self.__dict__.pop("_head_graphs", None)
         return super()._apply(fn, *a, **kw)
 
     def _device(self) -> torch.device:
@@ -526,8 +527,12 @@ class LFAN(_PackedModule):
         patches = logmel.permute(0, 2, 3, 1).contiguous().view(-1, ww, hh)
         return self.spatial["audio"](patches).view(B, T, -1)
 
-    def forward_features(self, feats: Dict[str, torch.Tensor]) -> torch.Tensor:
-        """feats[m]: [B,T,D_m] fp32 (visual = IR-50 embeddings) -> logits [B,T,output_dim]."""
+    # The head is 25 launches of 20-80 CTAs each: a launch-latency-bound chain.  With
+    # ``head_cuda_graph`` (default on) it is captured once per input shape into a CUDA graph over
+    # static buffers and replayed; CER_HEAD_GRAPH=0 or any capture failure keeps the eager launches.
+    head_cuda_graph = True
+
+    def _forward_features_eager(self, feats: Dict[str, torch.Tensor]) -> torch.Tensor:
         tcn, fus = self._head_engines()
         enc = []
         for m in self.modality:
@@ -536,6 +541,46 @@ class LFAN(_PackedModule):
         B, T, _ = enc[0].shape
         logits = fus.forward([e.view(B * T, -1) for e in enc])
         return logits.view(B, T, -1)
+
+    def forward_features(self, feats: Dict[str, torch.Tensor]) -> torch.Tensor:
+        """feats[m]: [B,T,D_m] fp32 (visual = IR-50 embeddings) -> logits [B,T,output_dim].
+        As in the reference, ``feats[m]`` is re-bound to the modality's encoded [B,T,C] features."""
+        if not self.head_cuda_graph or os.environ.get("CER_HEAD_GRAPH", "1") == "0" or torch.cuda.is_current_stream_capturing():
+            return self._forward_features_eager(feats)
+        self._head_engines()
+        x0 = feats[self.modality[0]]
+        key = (tuple(x0.shape[:2]), str(x0.device))
+        graphs = self.__dict__.setdefault("_head_graphs", {})
+        g = graphs.get(key)
+        if g is None:
+            ins = {m: feats[m].float().contiguous() for m in self.modality}
+            out = self._forward_features_eager(dict(ins))          # warm-up: one-time kernel attribute setup, workspaces
+            try:
+                static_in = {m: v.clone() for m, v in ins.items()}
+                graph = torch.cuda.CUDAGraph()
+                torch.cuda.synchronize(x0.device)
+                with torch.cuda.graph(graph):
+                    static_feats = dict(static_in)
+                    static_out = self._forward_features_eager(static_feats)
+                g = graphs[key] = (graph, static_in, static_feats, static_out)
+            except Exception:                                       # capture not possible here: stay eager for this shape
+                graphs[key] = False
+                g = False
+            if g is False:
+                return self._forward_features_eager(feats)
+        if g is False:
+            return self._forward_features_eager(feats)
+        graph, static_in, static_feats, static_out = g
+        for m in self.modality:
+            static_in[m].copy_(feats[m])
+        graph.replay()
+        for m in self.modality:
+            feats[m] = static_feats[m].clone()
+        return static_out.clone()
+
+    def repack(self):
+        self.__dict__.pop("_head_graphs", None)                     # graphs hold the old packed weights' pointers
+        super().repack()
 
     def _training_forward(self, X):
         """model.train() + grad enabled (trainer.py:365-391): the frozen backbones run their
