@@ -415,3 +415,29 @@ def test_backbone_standalone_7x7_head_56px():
     ref = O.ir50_forward(sd, x, "")
     assert emb.shape == (6, 512)
     assert F.cosine_similarity(emb, ref, dim=1).min().item() >= 0.999
+
+
+def test_infer_video_from_waveform():
+    """The audio branch from the raw 16 kHz waveform: edge padding (vggish_input.py:93), log-mel,
+    one 0.96 s example per video frame, VGGish, then the usual path."""
+    dev = _dev()
+    import numpy as np
+    from feature_vs_text_compound_emotion_b200 import windowing
+    mods = ["video", "logmel", "bert"]
+    m = _lfan(mods, dev, seed=12)
+    sd = synthetic.lfan_state_dict(12, mods)
+    L, fps = 45, 30.0
+    wave = synthetic.waveform(L / fps, seed=121)                 # exactly as long as the video: needs the padding
+    vid = synthetic.frames(L, seed=122)
+    bert = torch.randn(L, 768, generator=torch.Generator().manual_seed(123))
+    out = windowing.infer_video(m, vid.to(dev), {"wave": wave.to(dev), "bert": bert.to(dev)}, fps=fps).cpu()
+    assert out.shape == (L, 7)
+    w = wave.double().numpy()
+    w = np.pad(w, (0, 16000), "edge")
+    ex = torch.from_numpy(O.waveform_to_examples(w, 0.96, 1.0 / fps)).float()
+    assert ex.shape[0] >= L
+    aud = O.vggish_forward(sd, ex[:L], "spatial.audio.backbone.")
+    emb = O.ir50_forward(sd, vid, "spatial.visual.backbone.")
+    pad = lambda t: torch.cat([t, t[-1:].expand(300 - L, -1)]).unsqueeze(0)
+    want = O.head_forward(sd, {"video": pad(emb), "logmel": pad(aud), "bert": pad(bert)}, mods)[0, :L]
+    assert (out - want).abs().max().item() <= 2e-2
