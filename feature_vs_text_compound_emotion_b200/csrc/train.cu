@@ -19,6 +19,7 @@
 #include <algorithm>
 #include <cstdint>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -214,6 +215,191 @@ __global__ void __launch_bounds__(2 * BM) row_gemm_kernel(const RowGemm g) {
           g.aux[(long long)r * g.ld_aux + n] = h2d;
           *cp = lrelu(h2d + g.addend[(long long)r * g.ld_add + n]);
         } else {   // EPI_DGRAD_ACT: gradient w.r.t. the pre-activation of a LReLU+dropout site
+          if (g.addend) v += g.addend[(long long)r * g.ld_add + n];
+          const float saved = g.aux[(long long)r * g.ld_aux + n];
+          *cp = v * drop_factor(g.drop, idx) * lrelu_grad(saved);
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Intra-CTA split-K variant of the row GEMM for SMALL grids.  The head's GEMMs have only 75-300
+// 64x64 output tiles: with one 4-warp CTA per tile an SM holds 4-8 warps and every LDS->FFMA2
+// dependency is exposed (ncu: short_scoreboard stalls, sm active 65 %).  Here a CTA is four groups
+// of 128 threads; group g runs the same 64x64 micro-kernel over the (tap, k-tile) iterations
+// it = g (mod 4) on its own shared-memory tiles and its own named barrier, the four partial
+// accumulators are summed through shared memory, and group 0 runs the epilogue: 16 warps per SM
+// with the same register blocking.  Summation order differs from the 1-group kernel only in the
+// final 4-way add.
+// ------------------------------------------------------------------------------------------
+constexpr int kSplitG = 4;
+constexpr int kSplitSmemBytes = kSplitG * (kGK * (64 + 4) * 4 + kGK * kGN * 8);      // 4 x (4352 + 8192) = 50176
+
+__device__ __forceinline__ void group_sync(int g) { asm volatile("bar.sync %0, 128;" ::"r"(g + 1) : "memory"); }
+
+template <bool B_KN>
+__global__ void __launch_bounds__(128 * kSplitG) row_gemm_splitk_kernel(const RowGemm g) {
+  constexpr int BM = 64, NT = 128;
+  extern __shared__ __align__(16) uint8_t sk_smem[];
+  const int grp = threadIdx.x >> 7;
+  const int tid = threadIdx.x & 127;
+  float (*As)[BM + 4] = reinterpret_cast<float (*)[BM + 4]>(sk_smem + grp * (kGK * (BM + 4) * 4 + kGK * kGN * 8));
+  float2 (*Bs)[kGN] = reinterpret_cast<float2 (*)[kGN]>(reinterpret_cast<uint8_t*>(As) + kGK * (BM + 4) * 4);
+  const int tx = tid & 15, ty = tid >> 4;
+  const int row0 = blockIdx.y * BM, col0 = blockIdx.x * kGN;
+  unsigned long long acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0ull;
+
+  constexpr int AH = BM / 2;
+  const int a_r = tid >> 2, a_k = (tid & 3) * 4;
+  const bool a_vec = (g.lda & 3) == 0 && (g.K & 3) == 0 && (reinterpret_cast<uintptr_t>(g.A) & 15) == 0;
+  int a_t[2];
+#pragma unroll
+  for (int h = 0; h < 2; ++h) { const int r = row0 + a_r + AH * h; a_t[h] = r < g.R ? r % g.T : -(1 << 30); }
+  constexpr int BP = 256 / NT;
+  const int b_ld = B_KN ? g.N : g.K;
+  const bool b_vec = (b_ld & 3) == 0 && (reinterpret_cast<uintptr_t>(g.B) & 15) == 0 && (g.b_tap_stride & 3) == 0;
+  const int ksteps = (g.K + kGK - 1) / kGK;
+  const int total = g.taps * ksteps;
+  float4 ra[2], rbv[BP];
+  auto fetch = [&](int it) {
+    const int j = it / ksteps, k0 = (it - j * ksteps) * kGK;
+    const int shift = g.shift0 + j * g.shift_step;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int r = row0 + a_r + AH * h;
+      const bool ok = (a_t[h] + shift) >= 0 && (a_t[h] + shift) < g.T;
+      const float* ap = g.A + (long long)(r + shift) * g.lda + k0 + a_k;
+      if (ok && a_vec && k0 + a_k + 3 < g.K) ra[h] = __ldg(reinterpret_cast<const float4*>(ap));
+      else {
+        ra[h].x = (ok && k0 + a_k + 0 < g.K) ? __ldg(ap + 0) : 0.f;
+        ra[h].y = (ok && k0 + a_k + 1 < g.K) ? __ldg(ap + 1) : 0.f;
+        ra[h].z = (ok && k0 + a_k + 2 < g.K) ? __ldg(ap + 2) : 0.f;
+        ra[h].w = (ok && k0 + a_k + 3 < g.K) ? __ldg(ap + 3) : 0.f;
+      }
+    }
+    const float* bp = g.B + j * g.b_tap_stride;
+#pragma unroll
+    for (int u = 0; u < BP; ++u) {
+      const int slot = tid + u * NT;
+      const int b_a = B_KN ? (slot >> 4) : (slot >> 2);
+      const int b_b = B_KN ? (slot & 15) * 4 : (slot & 3) * 4;
+      float4& rb = rbv[u];
+      if (B_KN) {
+        const int k = k0 + b_a, n = col0 + b_b;
+        const float* q = bp + (long long)k * g.N + n;
+        if (k < g.K && b_vec && n + 3 < g.N) rb = __ldg(reinterpret_cast<const float4*>(q));
+        else {
+          rb.x = (k < g.K && n + 0 < g.N) ? __ldg(q + 0) : 0.f;
+          rb.y = (k < g.K && n + 1 < g.N) ? __ldg(q + 1) : 0.f;
+          rb.z = (k < g.K && n + 2 < g.N) ? __ldg(q + 2) : 0.f;
+          rb.w = (k < g.K && n + 3 < g.N) ? __ldg(q + 3) : 0.f;
+        }
+      } else {
+        const int n = col0 + b_a, k = k0 + b_b;
+        const float* q = bp + (long long)n * g.K + k;
+        if (n < g.N && b_vec && k + 3 < g.K) rb = __ldg(reinterpret_cast<const float4*>(q));
+        else {
+          rb.x = (n < g.N && k + 0 < g.K) ? __ldg(q + 0) : 0.f;
+          rb.y = (n < g.N && k + 1 < g.K) ? __ldg(q + 1) : 0.f;
+          rb.z = (n < g.N && k + 2 < g.K) ? __ldg(q + 2) : 0.f;
+          rb.w = (n < g.N && k + 3 < g.K) ? __ldg(q + 3) : 0.f;
+        }
+      }
+    }
+  };
+  auto stash = [&]() {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      As[a_k + 0][a_r + AH * h] = ra[h].x; As[a_k + 1][a_r + AH * h] = ra[h].y;
+      As[a_k + 2][a_r + AH * h] = ra[h].z; As[a_k + 3][a_r + AH * h] = ra[h].w;
+    }
+#pragma unroll
+    for (int u = 0; u < BP; ++u) {
+      const int slot = tid + u * NT;
+      const int b_a = B_KN ? (slot >> 4) : (slot >> 2);
+      const int b_b = B_KN ? (slot & 15) * 4 : (slot & 3) * 4;
+      const float4 rb = rbv[u];
+      if (B_KN) {
+        Bs[b_a][b_b + 0] = make_float2(rb.x, rb.x); Bs[b_a][b_b + 1] = make_float2(rb.y, rb.y);
+        Bs[b_a][b_b + 2] = make_float2(rb.z, rb.z); Bs[b_a][b_b + 3] = make_float2(rb.w, rb.w);
+      } else {
+        Bs[b_b + 0][b_a] = make_float2(rb.x, rb.x); Bs[b_b + 1][b_a] = make_float2(rb.y, rb.y);
+        Bs[b_b + 2][b_a] = make_float2(rb.z, rb.z); Bs[b_b + 3][b_a] = make_float2(rb.w, rb.w);
+      }
+    }
+  };
+  if (grp < total) fetch(grp);
+  for (int it = grp; it < total; it += kSplitG) {
+    stash();
+    group_sync(grp);
+    if (it + kSplitG < total) fetch(it + kSplitG);
+#pragma unroll
+    for (int kk = 0; kk < kGK; ++kk) micro_step<BM>(As, Bs, kk, ty, tx, acc);
+    group_sync(grp);
+  }
+  // ---- sum the four partial tiles through shared memory (the tiles are dead now)
+  __syncthreads();
+  float* red = reinterpret_cast<float*>(sk_smem);                 // [kSplitG - 1][128 threads][32] = 48 KB
+  if (grp > 0) {
+    float* dst = red + ((grp - 1) * 128 + tid) * 32;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        const float2 pr = unpack2(acc[i][jj]);
+        dst[(i * 4 + jj) * 2 + 0] = pr.x;
+        dst[(i * 4 + jj) * 2 + 1] = pr.y;
+      }
+  }
+  __syncthreads();
+  if (grp != 0) return;
+  float vals[4][4][2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) {
+      const float2 pr = unpack2(acc[i][jj]);
+      float lo = pr.x, hi = pr.y;
+#pragma unroll
+      for (int q = 0; q < kSplitG - 1; ++q) {
+        const float* src = red + (q * 128 + tid) * 32 + (i * 4 + jj) * 2;
+        lo += src[0]; hi += src[1];
+      }
+      vals[i][jj][0] = lo; vals[i][jj][1] = hi;
+    }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const int r = row0 + ty * 8 + 2 * i + half;
+      if (r >= g.R) continue;
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        const int n = col0 + tx * 4 + jj;
+        if (n >= g.N) continue;
+        float v = vals[i][jj][half];
+        if (g.bias) v += __ldg(g.bias + n);
+        const uint32_t idx = (uint32_t)r * (uint32_t)g.N + (uint32_t)n;
+        float* cp = g.C + (long long)r * g.ldc + n;
+        if (g.epi == EPI_LINEAR) {
+          if (g.addend) v += g.addend[(long long)r * g.ld_add + n];
+          if (g.accumulate) v += *cp;
+          *cp = v;
+        } else if (g.epi == EPI_RELU) {
+          *cp = fmaxf(v, 0.f);
+        } else if (g.epi == EPI_LRELU_DROP) {
+          *cp = lrelu(v) * drop_factor(g.drop, idx);
+        } else if (g.epi == EPI_BLOCK_OUT) {
+          const float h2d = lrelu(v) * drop_factor(g.drop, idx);
+          g.aux[(long long)r * g.ld_aux + n] = h2d;
+          *cp = lrelu(h2d + g.addend[(long long)r * g.ld_add + n]);
+        } else {
           if (g.addend) v += g.addend[(long long)r * g.ld_add + n];
           const float saved = g.aux[(long long)r * g.ld_aux + n];
           *cp = v * drop_factor(g.drop, idx) * lrelu_grad(saved);
@@ -762,7 +948,22 @@ int cer::launch_row_gemm(const RowGemm& g, bool b_kn, cudaStream_t st) {
     else row_gemm_kernel<false, 128><<<grid, 256, 0, st>>>(g);
   } else {
     dim3 grid(nt, (g.R + 63) / 64);
-    if (b_kn) row_gemm_kernel<true, 64><<<grid, 128, 0, st>>>(g);
+    static int split = -1;
+    if (split < 0) {
+      const char* e = getenv("CER_GEMM_SPLITK");
+      split = (e && e[0] == '0') ? 0 : 1;
+      if (split) {
+        CER_CUDA(cudaFuncSetAttribute(row_gemm_splitk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSplitSmemBytes));
+        CER_CUDA(cudaFuncSetAttribute(row_gemm_splitk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSplitSmemBytes));
+      }
+    }
+    const long long iters = (long long)g.taps * ((g.K + kGK - 1) / kGK);
+    if (split && (long long)grid.x * grid.y <= 148 && iters >= 2 * kSplitG) {
+      // at most one tile per SM and a long K: four K-groups per CTA (16 warps per SM instead of 4).  With more
+      // tiles than SMs the 512-thread CTAs (one per SM by registers) would run in waves and lose (measured)
+      if (b_kn) row_gemm_splitk_kernel<true><<<grid, 128 * kSplitG, kSplitSmemBytes, st>>>(g);
+      else row_gemm_splitk_kernel<false><<<grid, 128 * kSplitG, kSplitSmemBytes, st>>>(g);
+    } else if (b_kn) row_gemm_kernel<true, 64><<<grid, 128, 0, st>>>(g);
     else row_gemm_kernel<false, 64><<<grid, 128, 0, st>>>(g);
   }
   CER_CUDA(cudaGetLastError());
