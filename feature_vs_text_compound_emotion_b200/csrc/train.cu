@@ -234,12 +234,11 @@ __global__ void __launch_bounds__(2 * BM) row_gemm_kernel(const RowGemm g) {
 // with the same register blocking.  Summation order differs from the 1-group kernel only in the
 // final 4-way add.
 // ------------------------------------------------------------------------------------------
-constexpr int kSplitG = 4;
-constexpr int kSplitSmemBytes = kSplitG * (kGK * (64 + 4) * 4 + kGK * kGN * 8);      // 4 x (4352 + 8192) = 50176
+constexpr int kSplitGroupBytes = kGK * (64 + 4) * 4 + kGK * kGN * 8;                 // 4352 + 8192 per K-group
 
 __device__ __forceinline__ void group_sync(int g) { asm volatile("bar.sync %0, 128;" ::"r"(g + 1) : "memory"); }
 
-template <bool B_KN>
+template <bool B_KN, int kSplitG>
 __global__ void __launch_bounds__(128 * kSplitG) row_gemm_splitk_kernel(const RowGemm g) {
   constexpr int BM = 64, NT = 128;
   extern __shared__ __align__(16) uint8_t sk_smem[];
@@ -953,16 +952,20 @@ int cer::launch_row_gemm(const RowGemm& g, bool b_kn, cudaStream_t st) {
       const char* e = getenv("CER_GEMM_SPLITK");
       split = (e && e[0] == '0') ? 0 : 1;
       if (split) {
-        CER_CUDA(cudaFuncSetAttribute(row_gemm_splitk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSplitSmemBytes));
-        CER_CUDA(cudaFuncSetAttribute(row_gemm_splitk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSplitSmemBytes));
+        CER_CUDA(cudaFuncSetAttribute(row_gemm_splitk_kernel<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * kSplitGroupBytes));
+        CER_CUDA(cudaFuncSetAttribute(row_gemm_splitk_kernel<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * kSplitGroupBytes));
       }
     }
     const long long iters = (long long)g.taps * ((g.K + kGK - 1) / kGK);
-    if (split && (long long)grid.x * grid.y <= 148 && iters >= 2 * kSplitG) {
-      // at most one tile per SM and a long K: four K-groups per CTA (16 warps per SM instead of 4).  With more
-      // tiles than SMs the 512-thread CTAs (one per SM by registers) would run in waves and lose (measured)
-      if (b_kn) row_gemm_splitk_kernel<true><<<grid, 128 * kSplitG, kSplitSmemBytes, st>>>(g);
-      else row_gemm_splitk_kernel<false><<<grid, 128 * kSplitG, kSplitSmemBytes, st>>>(g);
+    const long long ctas = (long long)grid.x * grid.y;
+    if (split && ctas <= 148 && iters >= 8) {
+      // at most one tile per SM and a long K: four K-groups per CTA (16 warps per SM instead of 4)
+      if (b_kn) row_gemm_splitk_kernel<true, 4><<<grid, 512, 4 * kSplitGroupBytes, st>>>(g);
+      else row_gemm_splitk_kernel<false, 4><<<grid, 512, 4 * kSplitGroupBytes, st>>>(g);
+    } else if (split && ctas <= 2 * 148 && iters >= 4) {
+      // up to two tiles per SM: two K-groups (256 threads, two CTAs per SM by registers)
+      if (b_kn) row_gemm_splitk_kernel<true, 2><<<grid, 256, 2 * kSplitGroupBytes, st>>>(g);
+      else row_gemm_splitk_kernel<false, 2><<<grid, 256, 2 * kSplitGroupBytes, st>>>(g);
     } else if (b_kn) row_gemm_kernel<true, 64><<<grid, 128, 0, st>>>(g);
     else row_gemm_kernel<false, 64><<<grid, 128, 0, st>>>(g);
   }
