@@ -251,6 +251,80 @@ __global__ void stitch_kernel(const float* __restrict__ win, const int* __restri
   out[idx] = cnt > 0 ? s / cnt : 0.f;
 }
 
+// Video-level decision rules of metrics.py:88-145 (format_trg_pred_video) for one video, one CTA:
+// out[0] = FRAMES_VOTE (majority of per-frame argmax; ties -> the class seen first, as
+// Counter.most_common), out[1] = FRAMES_AVG_LOGITS, out[2] = FRAMES_AVG_PROBS (row softmax, :43-48).
+constexpr int kVoteMaxCls = 16;
+__global__ void __launch_bounds__(256) video_vote_kernel(const float* __restrict__ logits, long long T, int n_cls_all,
+                                                         int n_cls, int* __restrict__ out) {
+  __shared__ float s_sum[8][kVoteMaxCls + 1];
+  __shared__ float s_prob[8][kVoteMaxCls + 1];
+  __shared__ int s_cnt[8][kVoteMaxCls + 1];
+  __shared__ long long s_first[8][kVoteMaxCls + 1];
+  float sum[kVoteMaxCls], prob[kVoteMaxCls];
+  int cnt[kVoteMaxCls];
+  long long first[kVoteMaxCls];
+#pragma unroll
+  for (int c = 0; c < kVoteMaxCls; ++c) { sum[c] = 0.f; prob[c] = 0.f; cnt[c] = 0; first[c] = T; }
+  for (long long t = threadIdx.x; t < T; t += blockDim.x) {
+    const float* p = logits + t * n_cls_all;
+    float mx = p[0];
+    int arg = 0;
+    for (int c = 1; c < n_cls; ++c) if (p[c] > mx) { mx = p[c]; arg = c; }      // first maximum, like np.argmax
+    float den = 0.f;
+    for (int c = 0; c < n_cls; ++c) den += expf(p[c] - mx);
+    const float inv = 1.f / den;
+#pragma unroll
+    for (int c = 0; c < kVoteMaxCls; ++c) {
+      if (c < n_cls) {
+        sum[c] += p[c];
+        prob[c] += expf(p[c] - mx) * inv;
+        if (c == arg) { ++cnt[c]; if (t < first[c]) first[c] = t; }
+      }
+    }
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int c = 0; c < kVoteMaxCls; ++c) {
+    if (c < n_cls) {
+      float a = sum[c], b = prob[c];
+      int n = cnt[c];
+      long long f = first[c];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        b += __shfl_xor_sync(0xffffffffu, b, o);
+        n += __shfl_xor_sync(0xffffffffu, n, o);
+        const long long f2 = __shfl_xor_sync(0xffffffffu, f, o);
+        f = f2 < f ? f2 : f;
+      }
+      if (lane == 0) { s_sum[warp][c] = a; s_prob[warp][c] = b; s_cnt[warp][c] = n; s_first[warp][c] = f; }
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < n_cls) {
+    const int c = threadIdx.x;
+    float a = 0.f, b = 0.f;
+    int n = 0;
+    long long f = T;
+    for (int i = 0; i < 8; ++i) {
+      a += s_sum[i][c]; b += s_prob[i][c]; n += s_cnt[i][c];
+      f = s_first[i][c] < f ? s_first[i][c] : f;
+    }
+    s_sum[0][c] = a; s_prob[0][c] = b; s_cnt[0][c] = n; s_first[0][c] = f;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int vote = 0, al = 0, ap = 0;
+    for (int c = 1; c < n_cls; ++c) {
+      if (s_cnt[0][c] > s_cnt[0][vote] || (s_cnt[0][c] == s_cnt[0][vote] && s_first[0][c] < s_first[0][vote])) vote = c;
+      if (s_sum[0][c] > s_sum[0][al]) al = c;
+      if (s_prob[0][c] > s_prob[0][ap]) ap = c;
+    }
+    out[0] = vote; out[1] = al; out[2] = ap;
+  }
+}
+
 }  // namespace cer
 
 extern "C" int cer_fusion_head_forward(const cer_fusion_weights* w, const float* const* feats, int64_t rows,
@@ -312,6 +386,17 @@ extern "C" int cer_stitch_windows(const float* win_logits, const int32_t* win_st
   const long long total = length * n_out;
   stitch_kernel<<<(unsigned)((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       win_logits, win_start, n_windows, win_len, n_out, length, out);
+  CER_CUDA(cudaGetLastError());
+  return CER_OK;
+}
+
+extern "C" int cer_video_vote(const float* logits_dev, int64_t length, int32_t n_cls, int32_t ignore_last_class,
+                              int32_t* out_dev, void* stream) {
+  using namespace cer;
+  const int used = n_cls - (ignore_last_class ? 1 : 0);
+  if (!logits_dev || !out_dev || length <= 0 || used < 1 || used > kVoteMaxCls)
+    return set_error(CER_ERR_INVALID, "cer_video_vote: bad argument (1..16 classes, length >= 1)");
+  video_vote_kernel<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(logits_dev, length, n_cls, used, out_dev);
   CER_CUDA(cudaGetLastError());
   return CER_OK;
 }

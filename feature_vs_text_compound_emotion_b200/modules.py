@@ -545,6 +545,8 @@ class LFAN(_PackedModule):
     def forward_features(self, feats: Dict[str, torch.Tensor]) -> torch.Tensor:
         """feats[m]: [B,T,D_m] fp32 (visual = IR-50 embeddings) -> logits [B,T,output_dim].
         As in the reference, ``feats[m]`` is re-bound to the modality's encoded [B,T,C] features."""
+        from . import _capi
+        _capi.require_gpu()                                        # CerError without a B200: no fallback of any kind
         if not self.head_cuda_graph or os.environ.get("CER_HEAD_GRAPH", "1") == "0" or torch.cuda.is_current_stream_capturing():
             return self._forward_features_eager(feats)
         self._head_engines()

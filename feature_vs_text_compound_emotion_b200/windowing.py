@@ -62,22 +62,25 @@ def wave_to_examples(model, wave: torch.Tensor, n_frames: int, fps: float = 30.0
     return ex[:n_frames].contiguous()
 
 
+VOTE_KEYS = ("FRAMES_VOTE", "FRAMES_AVG_LOGITS", "FRAMES_AVG_PROBS")      # constants.py:136-142
+
+
 def video_level_prediction(frame_logits: torch.Tensor, ignore_last_class: bool = False) -> Dict[str, int]:
-    """The three video-level decision rules of metrics.py:88-145 (format_trg_pred_video) on
-    per-frame logits [T, n_cls]: FRAMES_VOTE (majority of per-frame argmax; ties go to the class
-    that appears first, as Counter.most_common does), FRAMES_AVG_LOGITS, FRAMES_AVG_PROBS.
-    ``ignore_last_class`` drops the 'Other' class first (C-EXPR-DB, metrics.py:118-119)."""
-    lg = frame_logits[:, :-1] if ignore_last_class else frame_logits
-    n_cls = lg.shape[-1]
-    pred = lg.argmax(-1)
-    votes = torch.bincount(pred, minlength=n_cls)
-    first = torch.full((n_cls,), pred.numel(), dtype=torch.long, device=pred.device)
-    first.scatter_reduce_(0, pred, torch.arange(pred.numel(), device=pred.device), reduce="amin")
-    best = votes.max()
-    cand = torch.where(votes == best, first, torch.full_like(first, pred.numel() + 1))
-    return {"FRAMES_VOTE": int(cand.argmin()),
-            "FRAMES_AVG_LOGITS": int(lg.mean(0).argmax()),
-            "FRAMES_AVG_PROBS": int(torch.softmax(lg, -1).mean(0).argmax())}
+    """The three video-level decision rules of metrics.py:88-145 (format_trg_pred_video) on the
+    stitched per-frame logits [T, n_cls] of one video, on the device (cer_video_vote): FRAMES_VOTE
+    (majority of per-frame argmax; ties go to the class that appears first, as Counter.most_common
+    does), FRAMES_AVG_LOGITS, FRAMES_AVG_PROBS.  ``ignore_last_class`` drops the 'Other' class first
+    (C-EXPR-DB, metrics.py:118-119)."""
+    from . import _capi
+    _capi.require_gpu()
+    lg = frame_logits.float().contiguous()
+    if lg.device.type != "cuda":
+        raise _capi.CerError("video_level_prediction needs the logits on the CUDA device (no CPU fallback)")
+    out = torch.empty(3, dtype=torch.int32, device=lg.device)
+    with torch.cuda.device(lg.device):
+        _capi.check(_capi.lib().cer_video_vote(lg.data_ptr(), lg.shape[0], lg.shape[1], int(ignore_last_class), out.data_ptr(),
+                                               _capi.current_stream_ptr()), "cer_video_vote")
+    return dict(zip(VOTE_KEYS, (int(v) for v in out.tolist())))
 
 
 @torch.no_grad()

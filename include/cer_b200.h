@@ -337,6 +337,12 @@ int cer_add_layernorm(const float* x_dev, const float* res_dev, int64_t rows, in
 int cer_stitch_windows(const float* win_logits_dev, const int32_t* win_start_dev, int32_t n_windows,
                        int32_t win_len, int32_t n_out, int64_t length, float* out_dev, void* stream);
 
+/* Video-level decision rules.   Replaces format_trg_pred_video (metrics.py:88-145) for one video:
+ * logits_dev fp32 [length][n_cls] (the stitched per-frame logits); out_dev int32[3] = FRAMES_VOTE,
+ * FRAMES_AVG_LOGITS, FRAMES_AVG_PROBS.  ignore_last_class drops the 'Other' class first (:118-119). */
+int cer_video_vote(const float* logits_dev, int64_t length, int32_t n_cls, int32_t ignore_last_class, int32_t* out_dev,
+                   void* stream);
+
 #ifdef __cplusplus
 }
 #endif

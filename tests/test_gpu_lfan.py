@@ -209,7 +209,7 @@ def test_infer_video_from_stored_uint8_crops_and_logmel():
     want = want / cnt
     assert (out - want).abs().max().item() <= 2e-2
     assert (out.argmax(-1) == want.argmax(-1)).float().mean().item() >= 0.99
-    assert windowing.video_level_prediction(out)["FRAMES_AVG_LOGITS"] == O.video_level_prediction(want.numpy())["FRAMES_AVG_LOGITS"]
+    assert windowing.video_level_prediction(out.to(dev))["FRAMES_AVG_LOGITS"] == O.video_level_prediction(want.numpy())["FRAMES_AVG_LOGITS"]
 
 
 def test_host_prefetcher_matches_direct_calls():
@@ -441,3 +441,19 @@ def test_infer_video_from_waveform():
     pad = lambda t: torch.cat([t, t[-1:].expand(300 - L, -1)]).unsqueeze(0)
     want = O.head_forward(sd, {"video": pad(emb), "logmel": pad(aud), "bert": pad(bert)}, mods)[0, :L]
     assert (out - want).abs().max().item() <= 2e-2
+
+
+def test_video_level_decision_rules_match_reference_semantics():
+    """cer_video_vote vs the restated format_trg_pred_video (metrics.py:118-142), incl. the tie rule."""
+    dev = _dev()
+    from feature_vs_text_compound_emotion_b200 import windowing
+    gen = torch.Generator().manual_seed(9)
+    for T in (1, 2, 7, 300, 1001, 5000):
+        lg = torch.randn(T, 8, generator=gen)
+        for ign in (False, True):
+            assert windowing.video_level_prediction(lg.to(dev), ign) == O.video_level_prediction(lg.numpy(), ign), (T, ign)
+    # tie: classes 2 and 5 both win 2 frames, class 5 appears first -> Counter.most_common picks 5
+    lg = torch.full((4, 7), -1.0)
+    for t, c in enumerate((5, 2, 2, 5)):
+        lg[t, c] = 1.0
+    assert windowing.video_level_prediction(lg.to(dev))["FRAMES_VOTE"] == 5 == O.video_level_prediction(lg.numpy())["FRAMES_VOTE"]
