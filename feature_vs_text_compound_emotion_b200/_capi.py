@@ -145,6 +145,7 @@ SIGNATURES = {
     "cer_modal_attention_forward": (C.c_int, [C.POINTER(C.c_void_p), C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
                                               C.c_void_p]),
     "cer_video_vote": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
+    "cer_tanh_inplace": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p]),
     "cer_stitch_windows": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int64,
                                      C.c_void_p, C.c_void_p]),
 }

@@ -469,3 +469,12 @@ def add_layernorm(x: torch.Tensor, res: Optional[torch.Tensor], gamma: torch.Ten
                                       x.shape[0], x.shape[1], gamma.data_ptr(), beta.data_ptr(), eps, out.data_ptr(),
                                       _capi.current_stream_ptr()), "cer_add_layernorm")
     return out
+
+
+def tanh_(y: torch.Tensor) -> torch.Tensor:
+    """In-place tanh on a contiguous fp32 CUDA tensor (cer_tanh_inplace)."""
+    if not y.is_contiguous() or y.dtype != torch.float32:
+        raise ValueError("tanh_: contiguous fp32 tensor expected")
+    with torch.cuda.device(y.device):
+        check(lib().cer_tanh_inplace(y.data_ptr(), y.numel(), _capi.current_stream_ptr()), "cer_tanh_inplace")
+    return y

@@ -191,7 +191,7 @@ class _FeatureHead(_PackedModule):
         _, w1, b1 = self._engines()
         h = E.linear(c2d, w1, b1, "leaky_relu")
         out = E.linear(h, self.fc2.weight, self.fc2.bias).view(B, T, -1)
-        return torch.tanh(out) if self.task == "REGRESSION" else out
+        return E.tanh_(out.contiguous()) if self.task == "REGRESSION" else out
 
 
 class CAN(_FeatureHead):

@@ -617,5 +617,6 @@ class LFAN(_PackedModule):
         out = self.forward_features(X)
         out = out.reshape(batch_size, self.example_length, -1)
         if self.task == "REGRESSION":
-            out = torch.tanh(out)
+            from .engine import tanh_
+            out = tanh_(out.contiguous())
         return out
