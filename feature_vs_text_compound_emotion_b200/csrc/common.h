@@ -14,3 +14,16 @@ int set_error(int code, const std::string& msg);   // records msg for cer_last_e
     if (_e != cudaSuccess)                                                                          \
       return ::cer::set_error(CER_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));    \
   } while (0)
+
+namespace cer {
+// Kernel attributes (max dynamic shared memory) belong to a device context: one-time setup must
+// run once per DEVICE, not once per process.  `mask` is a static bitmask owned by the call site.
+inline bool first_use_on_device(unsigned long long* mask) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (*mask & bit) return false;
+  *mask |= bit;
+  return true;
+}
+}  // namespace cer

@@ -150,11 +150,9 @@ extern "C" int cer_sdpa_forward(const float* q_dev, int32_t ldq, const float* k_
   const size_t smem = (size_t)8 * (dim + ((len_k + 3) & ~3)) * sizeof(float);
   if (smem > 200 * 1024) return set_error(CER_ERR_INVALID, "cer_sdpa_forward: sequence too long for the shared-memory score rows");
   if (smem > 48 * 1024) {
-    static size_t configured = 0;
-    if (smem > configured) {
+    static unsigned long long configured = 0;
+    if (first_use_on_device(&configured))
       CER_CUDA(cudaFuncSetAttribute(sdpa_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      configured = 200 * 1024;
-    }
   }
   dim3 grid((len_q + 7) / 8, batch);
   sdpa_kernel<<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(q_dev, ldq, k_dev, ldk, v_dev, ldv, len_q, len_k, dim,

@@ -381,10 +381,9 @@ template <int BN>
 static int launch_halo_inst(const ConvKernelParams& p, int num_sms, cudaStream_t st) {
   using L = HaloSmem<BN>;
   static_assert(L::kTotal <= 232448, "halo conv kernel shared memory exceeds 227 KB");
-  static bool configured = false;
-  if (!configured) {
+  static unsigned long long configured = 0;
+  if (first_use_on_device(&configured)) {
     CER_CUDA(cudaFuncSetAttribute(conv_halo_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
-    configured = true;
   }
   const int tiles = p.halo_frames * p.halo_bands * p.halo_cts;
   return launch_conv_kernel(conv_halo_kernel<BN>, std::min(tiles, num_sms), kHaloThreads, L::kTotal, st, 1, p);
@@ -402,11 +401,10 @@ static int launch_conv_inst(const ConvKernelParams& p, int grid, cudaStream_t st
   using L = ConvSmem<BN, STAGES, BRES>;
   static_assert(L::kTotal <= 232448, "conv kernel shared memory exceeds 227 KB");
   static_assert(!ALIGNED || (BRES ? STAGES % 3 == 0 : STAGES % 2 == 0), "aligned variant: producers must divide the ring");
-  static bool configured = false;
-  if (!configured) {
+  static unsigned long long configured = 0;
+  if (first_use_on_device(&configured)) {
     CER_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<BN, STAGES, BRES, ALIGNED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   L::kTotal));
-    configured = true;
   }
   if ((p.bias_classes + 1) * p.Cout > L::kTableFloats) return set_error(CER_ERR_INVALID, "conv: Cout too large for the epilogue table");
   return launch_conv_kernel(conv_igemm_kernel<BN, STAGES, BRES, ALIGNED>, grid, kConvThreads, L::kTotal, st, 1, p);
@@ -416,10 +414,9 @@ template <int BN, int STAGES>
 static int launch_conv2_inst(const ConvKernelParams& p, int num_sms, cudaStream_t st) {
   using L = Conv2Smem<BN, STAGES>;
   static_assert(L::kTotal <= 232448, "pair conv kernel shared memory exceeds 227 KB");
-  static bool configured = false;
-  if (!configured) {
+  static unsigned long long configured = 0;
+  if (first_use_on_device(&configured)) {
     CER_CUDA(cudaFuncSetAttribute(conv_igemm2_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
-    configured = true;
   }
   if ((p.bias_classes + 1) * p.Cout > L::kTableFloats) return set_error(CER_ERR_INVALID, "conv: Cout too large for the epilogue table");
   const int ptiles = ((p.num_m_tiles + 1) / 2) * p.num_n_tiles;
@@ -431,10 +428,9 @@ template <int BN, int STAGES, int KSTEPS>
 static int launch_conv2_bres_inst(const ConvKernelParams& p, int num_sms, cudaStream_t st) {
   using L = Conv2BresSmem<BN, STAGES, KSTEPS>;
   static_assert(L::kTotal <= 232448, "resident-weights pair conv kernel shared memory exceeds 227 KB");
-  static bool configured = false;
-  if (!configured) {
+  static unsigned long long configured = 0;
+  if (first_use_on_device(&configured)) {
     CER_CUDA(cudaFuncSetAttribute(conv_igemm2_bres_kernel<BN, STAGES, KSTEPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
-    configured = true;
   }
   if ((p.bias_classes + 1) * p.Cout > L::kTableFloats) return set_error(CER_ERR_INVALID, "conv: Cout too large for the epilogue table");
   const int pairs = std::min((p.num_m_tiles + 1) / 2, num_sms / 2);

@@ -217,10 +217,9 @@ __global__ void __launch_bounds__(kTcnThreads) tcn_block_kernel(cer_tcn_block bl
 template <int COUT, int DIL>
 static int launch_tcn(const cer_tcn_block& blk, const float* x, float* y, int B, int T, cudaStream_t st) {
   using C = TcnCfg<COUT, DIL, 5>;
-  static bool configured = false;
-  if (!configured) {
+  static unsigned long long configured = 0;
+  if (first_use_on_device(&configured)) {
     CER_CUDA(cudaFuncSetAttribute(tcn_block_kernel<COUT, DIL, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
-    configured = true;
   }
   dim3 grid((T + kTT - 1) / kTT, B);
   tcn_block_kernel<COUT, DIL, 5><<<grid, kTcnThreads, C::SMEM, st>>>(blk, x, y, T);

@@ -242,10 +242,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) tcn_igemm_kernel(const __grid_c
 template <int BN, int STAGES>
 static int launch_tcn_tc(const TcnKernelParams& p, int grid, cudaStream_t st) {
   using L = TcnSmem<BN, STAGES>;
-  static bool configured = false;
-  if (!configured) {
+  static unsigned long long configured = 0;
+  if (first_use_on_device(&configured)) {
     CER_CUDA(cudaFuncSetAttribute(tcn_igemm_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
-    configured = true;
   }
   tcn_igemm_kernel<BN, STAGES><<<grid, kTcThreads, L::kTotal, st>>>(p);
   CER_CUDA(cudaGetLastError());

@@ -951,10 +951,11 @@ int cer::launch_row_gemm(const RowGemm& g, bool b_kn, cudaStream_t st) {
     if (split < 0) {
       const char* e = getenv("CER_GEMM_SPLITK");
       split = (e && e[0] == '0') ? 0 : 1;
-      if (split) {
-        CER_CUDA(cudaFuncSetAttribute(row_gemm_splitk_kernel<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * kSplitGroupBytes));
-        CER_CUDA(cudaFuncSetAttribute(row_gemm_splitk_kernel<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * kSplitGroupBytes));
-      }
+    }
+    static unsigned long long configured = 0;
+    if (split && first_use_on_device(&configured)) {
+      CER_CUDA(cudaFuncSetAttribute(row_gemm_splitk_kernel<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * kSplitGroupBytes));
+      CER_CUDA(cudaFuncSetAttribute(row_gemm_splitk_kernel<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * kSplitGroupBytes));
     }
     const long long iters = (long long)g.taps * ((g.K + kGK - 1) / kGK);
     const long long ctas = (long long)grid.x * grid.y;
