@@ -99,6 +99,9 @@ SIGNATURES = {
     "cer_ir50_create": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(Ir50Weights), C.c_int64, C.c_void_p, C.c_size_t]),
     "cer_ir50_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "cer_ir50_debug_activation": (C.c_int64, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]),
+    "cer_ir50_op_variant": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_char_p, C.c_int32]),
+    "cer_ir50_run_ops": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p]),
+    "cer_conv_last_variant": (C.c_char_p, []),
     "cer_ir50_launches": (C.c_int64, [C.c_void_p, C.c_int64]),
     "cer_ir50_destroy": (None, [C.c_void_p]),
     "cer_conv_forward": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
@@ -184,6 +187,8 @@ def require_gpu() -> None:
     check(lib().cer_check_device(), "cer_check_device")
 
 
-def current_stream_ptr() -> int:
+def current_stream_ptr(device=None) -> int:
+    """Raw handle of torch's current stream on ``device`` (default: the current device).  Engines pass
+    their own device: a handle taken from another device's current stream is invalid there."""
     import torch
-    return torch.cuda.current_stream().cuda_stream
+    return torch.cuda.current_stream(device).cuda_stream

@@ -90,13 +90,13 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
 template <int BN>
 __device__ __forceinline__ void conv_epilogue_core(const ConvKernelParams& p, const float* s_bias, const float* s_alpha,
                                                    uint32_t tmem_acc, int n0, int warp, uint32_t tfull, uint32_t parity,
-                                                   bool valid, int cls, size_t out_off, bool pool_store = false,
-                                                   size_t pool_off = 0);
+                                                   bool valid, int cls, size_t out_off, uint32_t tempty,
+                                                   bool pool_store = false, size_t pool_off = 0);
 
 template <int BN>
 __device__ __forceinline__ void conv_epilogue_tile(const ConvKernelParams& p, const float* s_bias, const float* s_alpha,
                                                    uint32_t tmem_acc, int m_tile, int n_tile, int warp, int lane,
-                                                   uint32_t tfull, uint32_t parity) {
+                                                   uint32_t tfull, uint32_t parity, uint32_t tempty) {
   constexpr int kHalf = BN / 2;                // columns per thread per tile
   const int quarter = warp & 3;                // TMEM lane quarter this warp may read
   const int half = warp >> 2;                  // column half
@@ -121,13 +121,14 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvKernelParams& p, co
     pool_off = ((static_cast<size_t>(m / hw) * (p.Hout >> 1) + (oh >> 1)) * (p.Wout >> 1) + (ow >> 1)) * p.Cout + n0;
   }
   conv_epilogue_core<BN>(p, s_bias, s_alpha, tmem_acc, n0, warp, tfull, parity, valid, cls,
-                         static_cast<size_t>(m) * p.Cout + n0, pool_store, pool_off);
+                         static_cast<size_t>(m) * p.Cout + n0, tempty, pool_store, pool_off);
 }
 
 template <int BN>
 __device__ __forceinline__ void conv_epilogue_core(const ConvKernelParams& p, const float* s_bias, const float* s_alpha,
                                                    uint32_t tmem_acc, int n0, int warp, uint32_t tfull, uint32_t parity,
-                                                   bool valid, int cls, size_t out_off, bool pool_store, size_t pool_off) {
+                                                   bool valid, int cls, size_t out_off, uint32_t tempty, bool pool_store,
+                                                   size_t pool_off) {
   constexpr int kHalf = BN / 2;
   const int quarter = warp & 3;
   const int half = warp >> 2;
@@ -161,6 +162,14 @@ __device__ __forceinline__ void conv_epilogue_core(const ConvKernelParams& p, co
       for (int j = 0; j < 4; ++j) rnext[j] = __ldg(rp + j);
     }
     tmem_ld_wait();
+    if (c0 + 32 >= kHalf) {
+      // The accumulator is free as soon as its last tcgen05.ld has landed in registers (ld / wait::ld are
+      // warp-collective, so lane 0 speaks for the warp).  Arriving HERE -- before the global stores, with
+      // relaxed semantics -- keeps the MMA warp from waiting on this tile's stores and avoids the
+      // MEMBAR.ALL.GPU + ERRBAR a release.cluster arrive after the stores costs (profiles/r01_full_pair128.txt).
+      tc_fence_before();
+      if ((threadIdx.x & 31) == 0) mbar_arrive_relaxed_cluster(tempty);
+    }
     float f[32];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -262,7 +271,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull_bar[a], 1);
-      mbar_init(&tempty_bar[a], kEpiWarps * 32);
+      mbar_init(&tempty_bar[a], kEpiWarps);          // one arrival per epilogue warp
     }
     mbar_init(bres_bar, 1);
     fence_barrier_init();
@@ -529,9 +538,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
       const uint32_t acc_phase = (it >> 1) & 1;
       const int m_tile = tile / p.num_n_tiles;
       const int n_tile = tile - m_tile * p.num_n_tiles;
-      conv_epilogue_tile<BN>(p, s_bias, s_alpha, tmem_base + acc * BN, m_tile, n_tile, warp, lane, tfull0 + acc * 8, acc_phase);
-      tc_fence_before();
-      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tempty0 + acc * 8) : "memory");   // 256 arrivals free the accumulator
+      conv_epilogue_tile<BN>(p, s_bias, s_alpha, tmem_base + acc * BN, m_tile, n_tile, warp, lane, tfull0 + acc * 8, acc_phase,
+                             tempty0 + acc * 8);          // arrives on tempty once the accumulator is in registers
     }
   }
 

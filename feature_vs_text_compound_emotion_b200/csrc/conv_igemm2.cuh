@@ -13,7 +13,8 @@
 //   * empty[s] and tfull[a] exist in both CTAs; the leader's MMA warp signals them with
 //     `tcgen05.commit.cta_group::2...multicast::cluster` (mask 0b11).
 //   * tempty[a] lives in the leader and counts one arrival per epilogue warp of both CTAs
-//     (remote `mbarrier.arrive.shared::cluster` from the peer).
+//     (remote `mbarrier.arrive.relaxed.cluster` from the peer, issued as soon as the accumulator
+//     is in registers -- before the epilogue's global stores, see conv_epilogue_core).
 //   * TMEM is allocated with `tcgen05.alloc.cta_group::2` by the same warp in both CTAs; each CTA
 //     keeps its own 128 rows x BN columns of the accumulator and runs the ordinary epilogue on them.
 // Requires ksteps % STAGES == 0 (stage-aligned unrolled loops, as in the ALIGNED 1-CTA variant).
@@ -61,9 +62,6 @@ __device__ __forceinline__ void umma2_commit_mc(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                ::"r"(bar), "h"((uint16_t)3)
                : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 
 template <int BN, int STAGES>
@@ -230,10 +228,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm2_kernel(const __gr
       const int pm = pt / p.num_n_tiles;
       const int n_tile = pt - pm * p.num_n_tiles;
       conv_epilogue_tile<BN>(p, s_bias, s_alpha, tmem_base + acc * BN, 2 * pm + (int)rank, n_tile, warp, lane,
-                             tfull0 + acc * 8, acc_phase);
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(tempty_leader + acc * 8);
+                             tfull0 + acc * 8, acc_phase, tempty_leader + acc * 8);
     }
   }
 
@@ -391,10 +386,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm2_bres_kernel(const
       const uint32_t acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       conv_epilogue_tile<BN>(p, s_bias, s_alpha, tmem_base + acc * BN, 2 * pt + (int)rank, 0, warp, lane, tfull0 + acc * 8,
-                             acc_phase);
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(tempty_leader + acc * 8);
+                             acc_phase, tempty_leader + acc * 8);
     }
   }
 

@@ -32,5 +32,8 @@ bool conv_can_pool(int H, int W, int Cin, int Cout);
 // n_cap: frames the activation allocation holds (tensor-map N extent)
 int build_conv_op(ConvOp* op, const ConvGeom& g, int n_cap);
 int launch_conv(const ConvOp& op, int frames, int num_sms, cudaStream_t st);
+// name of the kernel instantiation launch_conv picks for `op` at `frames` frames / launched last on this thread
+const char* conv_variant_name(const ConvOp& op, int frames, int num_sms);
+const char* conv_last_variant();
 
 }  // namespace cer

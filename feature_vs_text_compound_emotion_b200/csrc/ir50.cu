@@ -450,44 +450,80 @@ static bool pair_mode_enabled() {
   return v == 1;
 }
 
-int launch_conv(const ConvOp& op, int frames, int num_sms, cudaStream_t st) {
-  ConvKernelParams p = op.kp;
-  p.M = frames * op.hw_out;
-  p.num_m_tiles = (p.M + kBlockM - 1) / kBlockM;
-  const int tiles = p.num_m_tiles * p.num_n_tiles;
-  if (tiles == 0) return CER_OK;
-  if (op.halo_ok && ((halo_mode() != 0 && tiles >= 2 * num_sms) || (p.pool_xor && p.cin_chunks == 1))) {
-    p.tmap_a = op.tmap_halo;
-    p.halo_frames = frames;
-    p.halo_bands = (p.Hout + kHaloTileH - 1) / kHaloTileH;
-    p.halo_cts = p.Wout / kHaloTileW;
-    return op.bn == 64 ? launch_halo_inst<64>(p, num_sms, st) : launch_halo_inst<128>(p, num_sms, st);
-  }
+// Which kernel instantiation a layer runs at a given number of frames.  Selection is separate from
+// launching so that the plan can REPORT its choice (cer_ir50_op_variant / cer_conv_last_variant):
+// bench.py labels its roofline line with the variant that actually ran.
+enum ConvVariant {
+  kVarNone = 0, kVarHalo64, kVarHalo128, kVarPairBres128, kVarPair256, kVarPair128,
+  kVar256Aligned, kVar256, kVar128Bres, kVar128Aligned, kVar128, kVar64Bres9, kVar64Aligned, kVar64
+};
+static const char* const kVariantNames[] = {
+  "none", "conv_halo_kernel<64>", "conv_halo_kernel<128>", "conv_igemm2_bres_kernel<128,4,18>",
+  "conv_igemm2_kernel<256,6>", "conv_igemm2_kernel<128,6>", "conv_igemm_kernel<256,4,0,1>", "conv_igemm_kernel<256,4,0,0>",
+  "conv_igemm_kernel<128,4,1,0>", "conv_igemm_kernel<128,6,0,1>", "conv_igemm_kernel<128,6,0,0>",
+  "conv_igemm_kernel<64,9,1,1>", "conv_igemm_kernel<64,8,0,1>", "conv_igemm_kernel<64,8,0,0>"};
+
+static ConvVariant select_conv_variant(const ConvOp& op, int frames, int num_sms) {
+  const ConvKernelParams& p = op.kp;
+  const int num_m_tiles = (frames * op.hw_out + kBlockM - 1) / kBlockM;
+  const int tiles = num_m_tiles * p.num_n_tiles;
+  if (tiles == 0) return kVarNone;
+  if (op.halo_ok && ((halo_mode() != 0 && tiles >= 2 * num_sms) || (p.pool_xor && p.cin_chunks == 1)))
+    return op.bn == 64 ? kVarHalo64 : kVarHalo128;
   const int grid = std::min(tiles, num_sms);
   const int ksteps = p.ksteps_main + p.ksteps2;
   // CTA-pair (cta_group::2) variant: plain 3x3 / 1x1 layers whose k-steps fill the 6-stage ring a whole
   // number of times and that have at least two waves of pair tiles
   if (pair_mode_enabled() && p.ksteps2 == 0 && ksteps % 6 == 0 && tiles >= 4 * num_sms && op.bn >= 128) {
-    p.tmap_b = op.tmap_b_half;
-    if (op.bn == 128 && p.num_n_tiles == 1 && ksteps == 18 && pair_bres_enabled())      // stage 2: weights stay in smem
-      return launch_conv2_bres_inst<128, 4, 18>(p, num_sms, st);
-    return op.bn == 256 ? launch_conv2_inst<256, 6>(p, num_sms, st) : launch_conv2_inst<128, 6>(p, num_sms, st);
+    if (op.bn == 128 && p.num_n_tiles == 1 && ksteps == 18 && pair_bres_enabled()) return kVarPairBres128;   // stage 2: weights stay in smem
+    return op.bn == 256 ? kVarPair256 : kVarPair128;
   }
   // weights-resident variants when the whole layer's B fits (Cin = 64 layers: 9 k-steps, one n-tile)
   const bool bres = p.num_n_tiles == 1 && ksteps <= kBresSteps && tiles >= 4 * grid;
   switch (op.bn) {
-    case 256:
-      return ksteps % 4 == 0 ? launch_conv_inst<256, 4, false, true>(p, grid, st)
-                             : launch_conv_inst<256, 4, false, false>(p, grid, st);
-    case 128:
-      if (bres) return launch_conv_inst<128, 4, true, false>(p, grid, st);
-      return ksteps % 6 == 0 ? launch_conv_inst<128, 6, false, true>(p, grid, st)
-                             : launch_conv_inst<128, 6, false, false>(p, grid, st);
-    default:
-      if (bres && ksteps == 9) return launch_conv_inst<64, 9, true, true>(p, grid, st);
-      return ksteps % 8 == 0 ? launch_conv_inst<64, 8, false, true>(p, grid, st)
-                             : launch_conv_inst<64, 8, false, false>(p, grid, st);
+    case 256: return ksteps % 4 == 0 ? kVar256Aligned : kVar256;
+    case 128: return bres ? kVar128Bres : (ksteps % 6 == 0 ? kVar128Aligned : kVar128);
+    default:  return (bres && ksteps == 9) ? kVar64Bres9 : (ksteps % 8 == 0 ? kVar64Aligned : kVar64);
   }
+}
+
+const char* conv_variant_name(const ConvOp& op, int frames, int num_sms) {
+  return kVariantNames[select_conv_variant(op, frames, num_sms)];
+}
+
+static thread_local const char* g_last_variant = "none";
+const char* conv_last_variant() { return g_last_variant; }
+
+int launch_conv(const ConvOp& op, int frames, int num_sms, cudaStream_t st) {
+  ConvKernelParams p = op.kp;
+  p.M = frames * op.hw_out;
+  p.num_m_tiles = (p.M + kBlockM - 1) / kBlockM;
+  const int tiles = p.num_m_tiles * p.num_n_tiles;
+  const ConvVariant var = select_conv_variant(op, frames, num_sms);
+  g_last_variant = kVariantNames[var];
+  const int grid = std::min(tiles, num_sms);
+  switch (var) {
+    case kVarNone: return CER_OK;
+    case kVarHalo64:
+    case kVarHalo128:
+      p.tmap_a = op.tmap_halo;
+      p.halo_frames = frames;
+      p.halo_bands = (p.Hout + kHaloTileH - 1) / kHaloTileH;
+      p.halo_cts = p.Wout / kHaloTileW;
+      return var == kVarHalo64 ? launch_halo_inst<64>(p, num_sms, st) : launch_halo_inst<128>(p, num_sms, st);
+    case kVarPairBres128: p.tmap_b = op.tmap_b_half; return launch_conv2_bres_inst<128, 4, 18>(p, num_sms, st);
+    case kVarPair256:     p.tmap_b = op.tmap_b_half; return launch_conv2_inst<256, 6>(p, num_sms, st);
+    case kVarPair128:     p.tmap_b = op.tmap_b_half; return launch_conv2_inst<128, 6>(p, num_sms, st);
+    case kVar256Aligned:  return launch_conv_inst<256, 4, false, true>(p, grid, st);
+    case kVar256:         return launch_conv_inst<256, 4, false, false>(p, grid, st);
+    case kVar128Bres:     return launch_conv_inst<128, 4, true, false>(p, grid, st);
+    case kVar128Aligned:  return launch_conv_inst<128, 6, false, true>(p, grid, st);
+    case kVar128:         return launch_conv_inst<128, 6, false, false>(p, grid, st);
+    case kVar64Bres9:     return launch_conv_inst<64, 9, true, true>(p, grid, st);
+    case kVar64Aligned:   return launch_conv_inst<64, 8, false, true>(p, grid, st);
+    case kVar64:          return launch_conv_inst<64, 8, false, false>(p, grid, st);
+  }
+  return set_error(CER_ERR_INVALID, "launch_conv: unknown variant");
 }
 
 }  // namespace cer
@@ -660,6 +696,40 @@ extern "C" int64_t cer_ir50_debug_activation(cer_ir50* p, const float* x, int64_
   const int64_t elems = frames * a.H * a.W * a.C;
   CER_CUDA(cudaMemcpyAsync(dst_dev, a.ptr, (size_t)elems * 2, cudaMemcpyDeviceToDevice, st));
   return elems;
+}
+
+extern "C" int cer_ir50_op_variant(const cer_ir50* p, int32_t op_index, int64_t n_frames, char* buf, int32_t buflen) {
+  if (!p || !buf || buflen <= 0 || op_index < 0 || op_index >= (int)p->ops.size() || n_frames <= 0)
+    return set_error(CER_ERR_INVALID, "cer_ir50_op_variant: bad argument");
+  const int frames = (int)std::min<int64_t>(p->cap, n_frames);
+  const int n = snprintf(buf, (size_t)buflen, "%s", conv_variant_name(p->ops[op_index], frames, p->num_sms));
+  return n < buflen ? n : buflen - 1;
+}
+
+extern "C" const char* cer_conv_last_variant(void) { return conv_last_variant(); }
+
+// Profiling aid: ops [first_op, last_op] of one pass in plan order -- 0 = stem, 1 .. 2U = the unit convs
+// (conv1, conv2 of unit 0, ...), 2U + 1 = FC.  The activation buffers must hold a previous forward of the
+// same frames (every op then reads the same data it reads in a real pass).
+extern "C" int cer_ir50_run_ops(cer_ir50* p, const float* x, int64_t frames, int32_t first_op, int32_t last_op, void* stream) {
+  const int n_conv = p ? (int)p->ops.size() : 0;
+  if (!p || frames <= 0 || frames > p->cap || first_op < 0 || last_op < first_op || last_op > n_conv || (first_op == 0 && !x))
+    return set_error(CER_ERR_INVALID, "cer_ir50_run_ops: bad argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  for (int op = first_op; op <= last_op; ++op) {
+    if (op == 0) {
+      const int H = p->w.in_h, W = p->w.in_w;
+      const long long pix = (long long)frames * H * ((W + 1) / 2);
+      const int blocks = (int)std::min<long long>((pix + 127) / 128, (long long)p->num_sms * 16);
+      stem_kernel<<<blocks, 128, 0, st>>>(x, p->w.stem_w, p->w.stem_bias, p->w.stem_alpha,
+                                          reinterpret_cast<__nv_bfloat16*>(p->buf[0]), (int)frames, H, W);
+      CER_CUDA(cudaGetLastError());
+    } else {
+      int rc = launch_conv(p->ops[op - 1], (int)frames, p->num_sms, st);
+      if (rc) return rc;
+    }
+  }
+  return CER_OK;
 }
 
 extern "C" int64_t cer_ir50_launches(const cer_ir50* p, int64_t n_frames) {

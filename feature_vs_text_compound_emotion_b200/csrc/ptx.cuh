@@ -100,6 +100,11 @@ __device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity) {
     }
   }
 }
+// Relaxed arrive on a barrier in this CTA or (pair kernels) in the cluster leader: `addr` is a
+// shared::cluster address (a shared::cta address names the executing CTA's own barrier).
+__device__ __forceinline__ void mbar_arrive_relaxed_cluster(uint32_t addr) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(addr) : "memory");
+}
 __device__ __forceinline__ void mbar_expect_tx_a(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }

@@ -863,23 +863,39 @@ __global__ void __launch_bounds__(256) ln_drop_bwd_kernel(const float* __restric
 __global__ void __launch_bounds__(256) ce_loss_kernel(const float* __restrict__ logits, const long long* __restrict__ labels,
                                                       int R, int n_cls, float* __restrict__ loss, float* __restrict__ dlogits) {
   __shared__ float red[8];
+  // nn.CrossEntropyLoss(reduction="mean") averages over the rows whose label is not ignore_index (-100).
+  // Every block counts the valid labels itself (R is a few thousand rows on this path), so the kernel
+  // needs no scratch memory and no second launch.  Labels outside [0, n_cls) are treated as ignored:
+  // they contribute neither loss nor gradient and are never used as an index.
+  float cnt = 0.f;
+  for (int i = threadIdx.x; i < R; i += blockDim.x) {
+    const long long yi = labels[i];
+    cnt += (yi >= 0 && yi < n_cls) ? 1.f : 0.f;
+  }
+  cnt = block_sum(cnt, red);
+  __syncthreads();
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   float l = 0.f;
   if (r < R) {
     const float* p = logits + (long long)r * n_cls;
-    float mx = p[0];
-    for (int c = 1; c < n_cls; ++c) mx = fmaxf(mx, p[c]);
-    float den = 0.f;
-    for (int c = 0; c < n_cls; ++c) den += expf(p[c] - mx);
-    const float lse = logf(den) + mx;
-    const int y = (int)labels[r];
-    const float invR = 1.f / R;
-    l = (lse - p[y]) * invR;
-    if (dlogits)
-      for (int c = 0; c < n_cls; ++c) dlogits[(long long)r * n_cls + c] = (expf(p[c] - lse) - (c == y ? 1.f : 0.f)) * invR;
+    const long long y = labels[r];
+    const bool ok = y >= 0 && y < n_cls;
+    const float inv = 1.f / cnt;
+    if (ok) {
+      float mx = p[0];
+      for (int c = 1; c < n_cls; ++c) mx = fmaxf(mx, p[c]);
+      float den = 0.f;
+      for (int c = 0; c < n_cls; ++c) den += expf(p[c] - mx);
+      const float lse = logf(den) + mx;
+      l = (lse - p[y]) * inv;
+      if (dlogits)
+        for (int c = 0; c < n_cls; ++c) dlogits[(long long)r * n_cls + c] = (expf(p[c] - lse) - (c == (int)y ? 1.f : 0.f)) * inv;
+    } else if (dlogits) {
+      for (int c = 0; c < n_cls; ++c) dlogits[(long long)r * n_cls + c] = 0.f;
+    }
   }
   l = block_sum(l, red);
-  if (threadIdx.x == 0) atomicAdd(loss, l);
+  if (threadIdx.x == 0) atomicAdd(loss, cnt > 0.f ? l : (blockIdx.x == 0 ? __int_as_float(0x7fc00000) : 0.f));   // no valid row: nan, as torch
 }
 
 // Fused optimizer update on a flat fp32 buffer (torch.optim.{SGD,Adam,AdamW} arithmetic;
@@ -1324,7 +1340,7 @@ extern "C" int cer_head_train_backward(cer_head_train* p, const float* const* fe
 
 extern "C" int cer_ce_loss(const float* logits, const int64_t* labels, int64_t rows, int32_t n_cls, float* loss_out,
                            float* dlogits_out, void* stream) {
-  if (!logits || !labels || !loss_out || rows <= 0 || n_cls <= 0 || rows > (1 << 30))
+  if (!logits || !labels || !loss_out || rows <= 0 || n_cls <= 0 || rows > (1 << 20))
     return set_error(CER_ERR_INVALID, "cer_ce_loss: bad argument");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   CER_CUDA(cudaMemsetAsync(loss_out, 0, 4, st));

@@ -45,10 +45,19 @@ class Ir50Engine:
         self.emb_dim = packed["emb_dim"]
         self.in_hw = packed["in_hw"]
         self.unit_shapes = []
+        self.conv_ops = []            # per conv op in plan order: geometry and algorithmic FLOPs per frame (bench accounting)
         hw = self.in_hw
         for u in units:
+            hin = hw
             hw = (hw - 1) // u["stride"] + 1
             self.unit_shapes.append((hw, hw, u["depth"]))
+            self.conv_ops.append({"cin": u["cin"], "cout": u["depth"], "h_in": hin, "h_out": hin, "stride": 1, "proj_cin": 0,
+                                  "flop": 2.0 * hin * hin * u["depth"] * 9 * u["cin"]})
+            kproj = u["cin"] if u["has_proj"] else 0
+            self.conv_ops.append({"cin": u["depth"], "cout": u["depth"], "h_in": hin, "h_out": hw, "stride": u["stride"],
+                                  "proj_cin": kproj, "flop": 2.0 * hw * hw * u["depth"] * (9 * u["depth"] + kproj)})
+        self.conv_ops.append({"cin": packed["fc_in"], "cout": packed["emb_dim"], "h_in": 1, "h_out": 1, "stride": 1, "proj_cin": 0,
+                              "flop": 2.0 * packed["fc_in"] * packed["emb_dim"]})
         with torch.cuda.device(self.device):
             nbytes = lib().cer_ir50_workspace_bytes(C.byref(self._w), self.frames_per_pass)
             self._ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
@@ -68,7 +77,7 @@ class Ir50Engine:
         if out is None:
             out = torch.empty(n, self.emb_dim, dtype=torch.float32, device=self.device)
         with torch.cuda.device(self.device):
-            check(lib().cer_ir50_forward(self._h, x.data_ptr(), n, out.data_ptr(), _capi.current_stream_ptr()),
+            check(lib().cer_ir50_forward(self._h, x.data_ptr(), n, out.data_ptr(), _capi.current_stream_ptr(self.device)),
                   "cer_ir50_forward")
         return out
 
@@ -80,12 +89,29 @@ class Ir50Engine:
         dst = torch.empty(n, H, W, Cc, dtype=torch.bfloat16, device=self.device)
         with torch.cuda.device(self.device):
             r = lib().cer_ir50_debug_activation(self._h, x.data_ptr(), n, unit_index, dst.data_ptr(),
-                                                _capi.current_stream_ptr())
+                                                _capi.current_stream_ptr(self.device))
         check(int(r), "cer_ir50_debug_activation")
         return dst
 
     def launches(self, n_frames: int) -> int:
         return int(lib().cer_ir50_launches(self._h, n_frames))
+
+    @property
+    def n_conv_ops(self) -> int:
+        return 2 * len(self.unit_shapes) + 1
+
+    def op_variant(self, op_index: int, n_frames: int) -> str:
+        """Kernel instantiation the plan launches for conv op ``op_index`` (conv1, conv2 of each unit, then the FC)."""
+        buf = C.create_string_buffer(96)
+        check(lib().cer_ir50_op_variant(self._h, op_index, n_frames, buf, 96), "cer_ir50_op_variant")
+        return buf.value.decode()
+
+    def run_ops(self, x: Optional[torch.Tensor], frames: int, first_op: int, last_op: int) -> None:
+        """Profiling aid: launch ops [first_op, last_op] of one pass (0 = stem, 1.. = unit convs, last = FC) over the
+        activations a previous forward of the same frames left in the plan's buffers."""
+        with torch.cuda.device(self.device):
+            check(lib().cer_ir50_run_ops(self._h, None if x is None else x.data_ptr(), frames, first_op, last_op,
+                                         _capi.current_stream_ptr(self.device)), "cer_ir50_run_ops")
 
     def __del__(self):
         h = getattr(self, "_h", None)
@@ -139,7 +165,7 @@ class VggishEngine:
         if out is None:
             out = torch.empty(n, self.emb_dim, dtype=torch.float32, device=self.device)
         with torch.cuda.device(self.device):
-            check(lib().cer_vggish_forward(self._h, x.data_ptr(), n, out.data_ptr(), _capi.current_stream_ptr()),
+            check(lib().cer_vggish_forward(self._h, x.data_ptr(), n, out.data_ptr(), _capi.current_stream_ptr(self.device)),
                   "cer_vggish_forward")
         return out
 
@@ -189,6 +215,7 @@ class TcnEngine:
                                         put(b["w2"]), put(b["b2"]), put(b["wd"]), put(b["bd"]), put(b["post_scale"]),
                                         put(b["post_shift"])))
         self._ws: Optional[torch.Tensor] = None
+        self._retired: List[torch.Tensor] = []
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         if x.dim() != 3 or x.shape[2] != self.c_in:
@@ -199,12 +226,16 @@ class TcnEngine:
             x = torch.nn.functional.pad(x, (0, self.blocks[0].c_in - self.c_in))
         x = x.contiguous()
         B, T, _ = x.shape
-        stream = _capi.current_stream_ptr()
+        stream = _capi.current_stream_ptr(self.device)
         cur = x
         with torch.cuda.device(self.device):
             if self.precision == "tf32":
                 need = max(B * T * blk.c_out * 4 for blk in self.blocks)
                 if self._ws is None or self._ws.numel() < need:
+                    # CUDA graphs captured for smaller shapes (LFAN.forward_features) have the old block's
+                    # address baked into their kernel nodes: retired workspaces stay alive with the engine
+                    if self._ws is not None:
+                        self._retired.append(self._ws)
                     self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
             for blk in self.blocks:
                 y = torch.empty(B, T, blk.c_out, dtype=torch.float32, device=self.device)
@@ -280,7 +311,7 @@ class FusionEngine:
         fused = torch.empty(rows, self.E, dtype=torch.float32, device=self.device) if want_fused else None
         with torch.cuda.device(self.device):
             check(lib().cer_fusion_head_forward(C.byref(self._w), ptrs, rows, logits.data_ptr(), _ptr(fused),
-                                                _capi.current_stream_ptr()), "cer_fusion_head_forward")
+                                                _capi.current_stream_ptr(self.device)), "cer_fusion_head_forward")
         return (logits, fused) if want_fused else logits
 
 
@@ -310,7 +341,7 @@ class PreprocEngine:
         if out is None:
             out = torch.empty(n, 3, self.crop, self.crop, dtype=torch.float32, device=self.device)
         with torch.cuda.device(self.device):
-            check(lib().cer_preproc_forward(self._h, frames.data_ptr(), n, out.data_ptr(), _capi.current_stream_ptr()),
+            check(lib().cer_preproc_forward(self._h, frames.data_ptr(), n, out.data_ptr(), _capi.current_stream_ptr(self.device)),
                   "cer_preproc_forward")
         return out
 
@@ -346,7 +377,7 @@ class LogMelEngine:
         out = torch.empty(n, c["n_mel"], dtype=torch.float32, device=self.device)
         with torch.cuda.device(self.device):
             check(lib().cer_logmel_forward(wave.data_ptr(), wave.numel(), self._tables.data_ptr(), c["win"], c["hop"], c["fft"],
-                                           c["n_mel"], c["log_offset"], out.data_ptr(), _capi.current_stream_ptr()),
+                                           c["n_mel"], c["log_offset"], out.data_ptr(), _capi.current_stream_ptr(self.device)),
                   "cer_logmel_forward")
         return out
 
@@ -361,7 +392,7 @@ class LogMelEngine:
         out = torch.empty(n, win, self.cfg["n_mel"], dtype=torch.float32, device=self.device)
         with torch.cuda.device(self.device):
             check(lib().cer_frame_examples(lm.data_ptr(), starts.data_ptr(), n, win, self.cfg["n_mel"], out.data_ptr(),
-                                           _capi.current_stream_ptr()), "cer_frame_examples")
+                                           _capi.current_stream_ptr(self.device)), "cer_frame_examples")
         return out
 
 
@@ -373,7 +404,7 @@ def _fusion_forward_composed(self, feats, rows, want_fused):
     vals = torch.empty(rows, self.E, dtype=torch.float32, device=self.device)
     with torch.cuda.device(self.device):
         check(lib().cer_modal_attention_forward(ptrs, rows, len(qkv), self.num_heads, self.head_dim, vals.data_ptr(),
-                                                _capi.current_stream_ptr()), "cer_modal_attention_forward")
+                                                _capi.current_stream_ptr(self.device)), "cer_modal_attention_forward")
     fused = add_layernorm(linear(vals, c["wo"], c["bo"]), None, c["g"], c["b"])
     cat = torch.empty(rows, self.dims[0] + self.E, dtype=torch.float32, device=self.device)
     cat[:, :self.dims[0]].copy_(feats[0])

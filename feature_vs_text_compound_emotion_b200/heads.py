@@ -160,7 +160,7 @@ class _FeatureHead(_PackedModule):
             self.spatial["audio"] = vggish
 
     def _engines(self):
-        eng = self.__dict__["_engine"]
+        eng = self._fresh_engine()
         if eng is None:
             dev = self.fc2.weight.device
             tcn = {}
@@ -171,7 +171,7 @@ class _FeatureHead(_PackedModule):
             s1, t1 = packing._bn_affine({f"bn1.{k}": v.detach().cpu() for k, v in self.bn1.state_dict().items()}, "bn1")
             w = (self.fc1.weight.detach().cpu().double() * s1.view(-1, 1)).float().contiguous().to(dev)
             b = (self.fc1.bias.detach().cpu().double() * s1 + t1).float().contiguous().to(dev)
-            eng = self.__dict__["_engine"] = (tcn, w, b)
+            eng = self._set_engine((tcn, w, b))
         return eng
 
     def _encode(self, X) -> Dict[str, torch.Tensor]:

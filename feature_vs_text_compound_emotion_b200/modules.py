@@ -29,21 +29,52 @@ TASKS = ("CLASSIFICATION", "REGRESSION")          # constants.py:17-20
 
 class _PackedModule(nn.Module):
     """Caches a device engine built from the current parameters; dropped whenever the
-    parameters may have changed (load_state_dict, .to()/.cuda()/.half(), explicit repack())."""
+    parameters may have changed: load_state_dict, .to()/.cuda()/.half(), explicit repack(), a
+    training-mode forward (``_mark_dirty``), or any in-place update of a parameter or buffer since
+    the engine was packed (``optimizer.step()`` of a torch optimizer bumps the tensors' version
+    counters; ``_fresh_engine`` compares their sum with the stamp taken at packing time)."""
 
     def __init__(self):
         super().__init__()
         self.__dict__["_engine"] = None
+        self.__dict__["_stamp"] = None
         self.register_load_state_dict_post_hook(lambda module, incompatible: module.repack())
 
     def repack(self):
         self.__dict__["_engine"] = None
+        self.__dict__["_stamp"] = None
+        self.__dict__.pop("_ptensors", None)
         for m in self.children():
             if isinstance(m, _PackedModule):
                 m.repack()
 
+    def _stamp_tensors(self):
+        """Tensors whose in-place modification invalidates this module's packed engine."""
+        return list(self.parameters()) + list(self.buffers())
+
+    def _version_stamp(self) -> int:
+        ts = self.__dict__.get("_ptensors")
+        if ts is None:
+            ts = self.__dict__["_ptensors"] = self._stamp_tensors()
+        return sum(t._version for t in ts)
+
+    def _fresh_engine(self):
+        """The cached engine, or None if there is none or the weights changed since it was packed."""
+        eng = self.__dict__["_engine"]
+        if eng is not None and self.__dict__["_stamp"] != self._version_stamp():
+            self.repack()                                      # weights were updated in place: re-pack
+            eng = None
+        return eng
+
+    def _set_engine(self, eng):
+        self.__dict__["_engine"] = eng
+        self.__dict__["_stamp"] = self._version_stamp()
+        return eng
+
     def _apply(self, fn, *a, **kw):
         self.__dict__["_engine"] = None
+        self.__dict__["_stamp"] = None
+        self.__dict__.pop("_ptensors", None)
         self.__dict__.pop("_trainer", None)      # a training plan holds raw pointers into the old parameter storage
         self.__dict__.pop("_preproc", None)
         self.__dict__.pop("_logmel", None)
@@ -56,8 +87,8 @@ class _PackedModule(nn.Module):
     def _check_inference(self):
         if self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
             raise NotImplementedError(
-                "the B200 kernels are forward-only: call .eval() or run under torch.no_grad() "
-                "(the fusion-head training step of BASELINE config 4 is not built yet)")
+                "this sub-module's B200 kernels are forward-only: call .eval() or run under torch.no_grad() "
+                "(training runs through LFAN.forward in train mode / training.HeadTrainer)")
 
 
 class Flatten(nn.Module):                      # models/arcface_model.py:12-14 (container only)
@@ -136,9 +167,8 @@ class Backbone(_PackedModule):
         return Ir50Engine(pk, self._device(), self.frames_per_pass)
 
     def engine(self) -> Ir50Engine:
-        if self.__dict__["_engine"] is None:
-            self.__dict__["_engine"] = self._build_engine()
-        return self.__dict__["_engine"]
+        eng = self._fresh_engine()
+        return eng if eng is not None else self._set_engine(self._build_engine())
 
     def forward(self, x):
         if self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
@@ -208,10 +238,11 @@ class VGG(_PackedModule):
                                         nn.ReLU(True), nn.Linear(4096, 128))
 
     def engine(self) -> VggishEngine:
-        if self.__dict__["_engine"] is None:
+        eng = self._fresh_engine()
+        if eng is None:
             sd = {k: v.detach().cpu() for k, v in self.state_dict().items()}
-            self.__dict__["_engine"] = VggishEngine(packing.pack_vggish(sd), self._device(), self.patches_per_pass)
-        return self.__dict__["_engine"]
+            eng = self._set_engine(VggishEngine(packing.pack_vggish(sd), self._device(), self.patches_per_pass))
+        return eng
 
     def forward(self, x):
         self._check_inference()
@@ -300,9 +331,10 @@ class TemporalBlock(_PackedModule):
 
     def forward(self, x):
         self._check_inference()
-        if self.__dict__["_engine"] is None:
-            self.__dict__["_engine"] = TcnEngine([self.packed()], self._device())
-        return self.__dict__["_engine"].forward(x.float().transpose(1, 2)).transpose(1, 2)
+        eng = self._fresh_engine()
+        if eng is None:
+            eng = self._set_engine(TcnEngine([self.packed()], self._device()))
+        return eng.forward(x.float().transpose(1, 2)).transpose(1, 2)
 
 
 class TemporalConvNet(_PackedModule):
@@ -328,9 +360,10 @@ class TemporalConvNet(_PackedModule):
 
     def forward_time_major(self, x):
         """x [B,T,C] -> [B,T,C'] without the reference's transposes."""
-        if self.__dict__["_engine"] is None:
-            self.__dict__["_engine"] = TcnEngine(self.packed_blocks(), self._device())
-        return self.__dict__["_engine"].forward(x)
+        eng = self._fresh_engine()
+        if eng is None:
+            eng = self._set_engine(TcnEngine(self.packed_blocks(), self._device()))
+        return eng.forward(x)
 
     def forward(self, x):
         self._check_inference()
@@ -394,11 +427,12 @@ class MultimodalTransformerEncoder(_PackedModule):
         self._check_inference()
         if mask is not None:
             raise NotImplementedError("mask is never passed on the LFAN path (model.py:517)")
-        if self.__dict__["_engine"] is None:
-            self.__dict__["_engine"] = FusionEngine(self.packed(), self._device())
+        eng = self._fresh_engine()
+        if eng is None:
+            eng = self._set_engine(FusionEngine(self.packed(), self._device()))
         B, T, _ = x[self.modalities[0]].shape
         feats = [x[m].float().reshape(B * T, -1) for m in self.modalities]
-        _, fused = self.__dict__["_engine"].forward(feats, want_fused=True)
+        _, fused = eng.forward(feats, want_fused=True)
         return fused.view(B, T, -1)
 
     def get_attention_maps(self, x, mask=None):
@@ -502,8 +536,20 @@ class LFAN(_PackedModule):
         self.repack()
 
     # -- engines ------------------------------------------------------------------------------
+    def _stamp_tensors(self):
+        # the head's engines depend on everything but the (frozen) backbones, which track themselves
+        return ([p for k, p in self.named_parameters() if not k.startswith("spatial.")]
+                + [b for k, b in self.named_buffers() if not k.startswith("spatial.")])
+
+    def _mark_dirty(self):
+        """A training-mode forward ran: BatchNorm1d statistics moved (and an optimizer step usually
+        follows).  The next inference forward re-packs the head."""
+        self.__dict__["_dirty"] = True
+
     def _head_engines(self):
-        eng = self.__dict__["_engine"]
+        if self.__dict__.pop("_dirty", False):
+            self.repack()
+        eng = self._fresh_engine()
         if eng is None:
             dev = self.regressor.weight.device
             tcn = {}
@@ -511,7 +557,7 @@ class LFAN(_PackedModule):
                 s, t = packing._bn_affine({f"bn.{k}": v.detach().cpu() for k, v in self.bn[m].state_dict().items()}, "bn")
                 tcn[m] = TcnEngine(self.temporal[m].packed_blocks(s.float(), t.float()), dev)
             fus = FusionEngine(self.fusion.packed(self.regressor), dev)
-            eng = self.__dict__["_engine"] = (tcn, fus)
+            eng = self._set_engine((tcn, fus))
         return eng
 
     def encode_frames(self, video: torch.Tensor) -> torch.Tensor:
@@ -597,6 +643,7 @@ class LFAN(_PackedModule):
             if 'logmel' in X:
                 X['logmel'] = self.encode_logmel(X['logmel']).unsqueeze(1)
         feats = {m: X[m].squeeze(1) for m in self.modality}
+        self._mark_dirty()
         out = training.forward_with_grad(self, feats)
         for m in X:
             X[m] = feats.get(m, X[m])

@@ -90,7 +90,10 @@ class HeadTrainer:
             self._views[k] = view
             self._gviews[k] = self.grads[o:o + n].view(p.shape)
         self._keep = []
-        self._build_plan()
+        self._plans: Dict[tuple, tuple] = {}        # (B, T) -> (handle, workspace): all plans share the flat buffers
+        self._gen = 0                               # bumped by every forward: the saved activations belong to the latest one
+        self._build_spec()
+        self._plan(self.batch, self.length)
         model.repack()
 
     # -- plan ---------------------------------------------------------------------------------
@@ -100,7 +103,7 @@ class HeadTrainer:
     def _gp(self, name):
         return self._gviews[name].data_ptr()
 
-    def _build_plan(self):
+    def _build_spec(self):
         m = self.model
         s = HeadTrainSpec()
         s.n_modals = len(self.mods)
@@ -142,42 +145,52 @@ class HeadTrainer:
         s.wr, s.br, s.dwr, s.dbr = self._pp("regressor.weight"), self._pp("regressor.bias"), self._gp("regressor.weight"), self._gp("regressor.bias")
         s.grad_flat, s.grad_count = self.grads.data_ptr(), self.flat_count
         self._spec = s
-        with torch.cuda.device(self.device):
-            nbytes = lib().cer_head_train_workspace_bytes(C.byref(s), self.batch, self.length)
-            if nbytes == 0:
-                raise _capi.CerError("cer_head_train_workspace_bytes rejected the spec: " + (lib().cer_last_error() or b"").decode())
-            self._ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
-            h = C.c_void_p()
-            check(lib().cer_head_train_create(C.byref(h), C.byref(s), self.batch, self.length, self._ws.data_ptr(), nbytes),
-                  "cer_head_train_create")
-        self._h = h
+
+    def _plan(self, batch: int, length: int):
+        """The CUDA plan (workspace for saved activations + launch descriptors) for ``batch`` windows of
+        ``length`` frames.  Plans are cached per shape -- the ragged last batch of an epoch gets its own --
+        and all of them point at the same flat parameter / gradient buffers."""
+        key = (int(batch), int(length))
+        p = self._plans.get(key)
+        if p is None:
+            with torch.cuda.device(self.device):
+                nbytes = lib().cer_head_train_workspace_bytes(C.byref(self._spec), key[0], key[1])
+                if nbytes == 0:
+                    raise _capi.CerError("cer_head_train_workspace_bytes rejected the spec: " + (lib().cer_last_error() or b"").decode())
+                ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+                h = C.c_void_p()
+                check(lib().cer_head_train_create(C.byref(h), C.byref(self._spec), key[0], key[1], ws.data_ptr(), nbytes),
+                      "cer_head_train_create")
+            p = self._plans[key] = (h, ws)
+        return p
 
     def __del__(self):
-        h = getattr(self, "_h", None)
-        if h:
+        for h, _ in getattr(self, "_plans", {}).values():
             try:
                 lib().cer_head_train_destroy(h)
             except Exception:
                 pass
-            self._h = None
+        self._plans = {}
 
     # -- pieces ---------------------------------------------------------------------------------
     def _feat_ptrs(self, feats: Dict[str, torch.Tensor]):
-        rows = self.batch * self.length
+        f0 = feats[self.mods[0]]
+        batch, length = int(f0.shape[0]), int(f0.shape[-2])
+        rows = batch * length
         keep, ptrs = [], (C.c_void_p * len(self.mods))()
         for i, mod in enumerate(self.mods):
             f = feats[mod]
             if f.dim() == 4:
                 f = f.squeeze(1)
             d = self.model.embedding_dim[mod]
-            if tuple(f.shape) != (self.batch, self.length, d):
-                raise ValueError(f"{mod}: expected [{self.batch},{self.length},{d}], got {tuple(f.shape)}")
+            if tuple(f.shape) != (batch, length, d):
+                raise ValueError(f"{mod}: expected [{batch},{length},{d}], got {tuple(f.shape)}")
             if f.device != self.device:
                 raise ValueError("features must be on the trainer's CUDA device")
             f = f.float().contiguous().view(rows, d)
             keep.append(f)
             ptrs[i] = f.data_ptr()
-        return keep, ptrs
+        return keep, ptrs, batch, length
 
     def next_seed(self) -> int:
         s = (self.base_seed + self.calls * 0x632BE5AB) & 0xFFFFFFFF
@@ -186,12 +199,14 @@ class HeadTrainer:
 
     def forward(self, feats: Dict[str, torch.Tensor], seed: Optional[int] = None) -> torch.Tensor:
         """Training-mode forward: logits [B, T, n_out]; keeps what backward needs."""
-        keep, ptrs = self._feat_ptrs(feats)
-        self._last = (keep, ptrs)
+        keep, ptrs, batch, length = self._feat_ptrs(feats)
+        h, _ = self._plan(batch, length)
+        self._gen += 1
+        self._last = (keep, ptrs, h, self._gen)
         seed = self.next_seed() if seed is None else int(seed) & 0xFFFFFFFF
-        logits = torch.empty(self.batch, self.length, self.model.output_dim, dtype=torch.float32, device=self.device)
+        logits = torch.empty(batch, length, self.model.output_dim, dtype=torch.float32, device=self.device)
         with torch.cuda.device(self.device):
-            check(lib().cer_head_train_forward(self._h, ptrs, seed, logits.data_ptr(), _capi.current_stream_ptr()),
+            check(lib().cer_head_train_forward(h, ptrs, seed, logits.data_ptr(), _capi.current_stream_ptr()),
                   "cer_head_train_forward")
         for mod in self.mods:
             self.model.bn[mod].num_batches_tracked += 1
@@ -210,10 +225,10 @@ class HeadTrainer:
 
     def backward(self, dlogits: torch.Tensor) -> None:
         """Fills the flat gradient buffer (overwrites) from d loss / d logits of the last forward."""
-        keep, ptrs = self._last
+        keep, ptrs, h, _ = self._last
         dl = dlogits.float().contiguous()
         with torch.cuda.device(self.device):
-            check(lib().cer_head_train_backward(self._h, ptrs, dl.data_ptr(), _capi.current_stream_ptr()),
+            check(lib().cer_head_train_backward(h, ptrs, dl.data_ptr(), _capi.current_stream_ptr()),
                   "cer_head_train_backward")
 
     def grad(self, name: str) -> torch.Tensor:
@@ -261,11 +276,18 @@ class _HeadFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, trainer: HeadTrainer, feats: dict, *params):
         ctx.trainer = trainer
-        return trainer.forward(feats)
+        out = trainer.forward(feats)
+        ctx.gen = trainer._gen
+        return out
 
     @staticmethod
     def backward(ctx, dlogits):
         tr = ctx.trainer
+        if ctx.gen != tr._gen:
+            # the plan keeps ONE set of saved activations: a later training forward has overwritten the ones
+            # this graph needs -- fail instead of returning gradients of the wrong batch
+            raise RuntimeError("LFAN training forward was called again before backward() of an earlier output: "
+                               "run backward (or drop the earlier output) before the next training forward")
         tr.backward(dlogits)
         return (None, None) + tuple(tr.grad(k).clone() for k in tr.names)
 
@@ -275,8 +297,8 @@ def forward_with_grad(model, feats: Dict[str, torch.Tensor]) -> torch.Tensor:
     any_f = feats[model.modality[0]]
     B, T = any_f.shape[0], any_f.shape[-2]
     tr = model.__dict__.get("_trainer")
-    if tr is None or tr.batch != B or tr.length != T:
-        tr = HeadTrainer(model, B, T)
+    if tr is None:
+        tr = HeadTrainer(model, B, T)                 # other (B, T) shapes add a plan to the same trainer
         model.__dict__["_trainer"] = tr
     params = [p for _, p in head_parameters(model)]
     return _HeadFunction.apply(tr, feats, *params)

@@ -84,6 +84,14 @@ int cer_ir50_forward(cer_ir50* plan, const float* x_nchw_dev, int64_t n_frames, 
  * (frames*H*W*C bf16).  Returns the element count or a negative cer_status. */
 int64_t cer_ir50_debug_activation(cer_ir50* plan, const float* x_nchw_dev, int64_t frames, int32_t unit_index,
                                   void* dst_dev, void* stream);
+/* Name of the kernel instantiation the plan launches for conv op `op_index` (0 .. 2*n_units - 1: conv1,
+ * conv2 of each unit in order; 2*n_units: the FC) when a pass holds min(n_frames, frames_per_pass) frames,
+ * e.g. "conv_igemm2_kernel<256,6>".  Writes a NUL-terminated string, returns its length or a negative status. */
+int cer_ir50_op_variant(const cer_ir50* plan, int32_t op_index, int64_t n_frames, char* buf, int32_t buflen);
+/* Profiling aid: launch ops [first_op, last_op] of one pass in plan order (0 = stem, 1 .. 2*n_units = unit
+ * convs, 2*n_units + 1 = FC) on `frames` <= frames_per_pass frames.  The plan's activation buffers must hold
+ * an earlier forward of the same frames.  x_nchw_dev is read by op 0 only. */
+int cer_ir50_run_ops(cer_ir50* plan, const float* x_nchw_dev, int64_t frames, int32_t first_op, int32_t last_op, void* stream);
 /* Number of kernel launches one forward of n_frames enqueues (for bench accounting). */
 int64_t cer_ir50_launches(const cer_ir50* plan, int64_t n_frames);
 void cer_ir50_destroy(cer_ir50* plan);
@@ -98,6 +106,8 @@ int cer_conv_forward(const void* src_nhwc_dev, int32_t n_frames, int32_t n_alloc
                      const void* weight_dev, int32_t cout, int32_t ksize, int32_t stride, int32_t pad,
                      const float* bias_dev, int32_t bias_classes, const float* alpha_dev, const void* res_dev,
                      void* dst_dev, int32_t out_fp32, void* stream);
+/* Name of the kernel instantiation the last cer_conv_forward call on this thread launched. */
+const char* cer_conv_last_variant(void);
 
 /* ------------------------------------------------------------------------------------------
  * VGGish audio backbone (the inline `logmel` modality).   Replaces AudioBackbone.forward /
@@ -281,8 +291,11 @@ int cer_head_train_forward(cer_head_train* plan, const float* const* feats_dev, 
 int cer_head_train_backward(cer_head_train* plan, const float* const* feats_dev, const float* dlogits_dev, void* stream);
 void cer_head_train_destroy(cer_head_train* plan);
 
-/* Mean cross-entropy over `rows` rows and (optionally) its gradient w.r.t. the logits
- * (nn.CrossEntropyLoss(reduction="mean"), experiment.py:133).  labels: int64 [rows]. */
+/* Mean cross-entropy over `rows` rows (<= 2^20) and (optionally) its gradient w.r.t. the logits
+ * (nn.CrossEntropyLoss(reduction="mean"), experiment.py:133).  labels: int64 [rows].  Rows whose label is
+ * ignore_index (-100) are excluded from the mean and get a zero gradient, as in torch; any other label
+ * outside [0, n_cls) is treated the same way (torch raises a device assert there) -- it is never used as
+ * an index.  With no valid row the loss is NaN, as in torch. */
 int cer_ce_loss(const float* logits_dev, const int64_t* labels_dev, int64_t rows, int32_t n_cls, float* loss_out_dev,
                 float* dlogits_out_dev /* or NULL */, void* stream);
 

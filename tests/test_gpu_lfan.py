@@ -457,3 +457,54 @@ def test_video_level_decision_rules_match_reference_semantics():
     for t, c in enumerate((5, 2, 2, 5)):
         lg[t, c] = 1.0
     assert windowing.video_level_prediction(lg.to(dev))["FRAMES_VOTE"] == 5 == O.video_level_prediction(lg.numpy())["FRAMES_VOTE"]
+
+
+def test_full_size_oracle_parity_config2():
+    """The BENCHMARKED size and plan: 8 windows x 300 frames from pixels through LFAN.forward with the
+    default frames_per_pass (so the CTA-pair / halo / resident-weight kernel selection bench.py times is
+    the one checked) against the oracle's fp32 CPU forward (models/model.py:487-526 at B=8, T=300).
+    BASELINE.json bars on every one of the 2400 frames."""
+    dev = _dev()
+    from feature_vs_text_compound_emotion_b200.models.arcface_model import Backbone
+    assert Backbone.frames_per_pass == 2400
+    mods = ["video", "vggish", "bert"]
+    m = _lfan(mods, dev, seed=0)
+    sd = synthetic.lfan_state_dict(0, mods)
+    feats = synthetic.feature_windows(8, 300, seed=101, modalities=["vggish", "bert"])
+    vid = synthetic.frames(2400, seed=102).view(8, 300, 3, 40, 40)
+    emb = m.spatial["visual"](vid.view(2400, 3, 40, 40).to(dev)).cpu()
+    ref_emb = O.ir50_forward(sd, vid.view(2400, 3, 40, 40), "spatial.visual.backbone.")
+    cos = F.cosine_similarity(emb, ref_emb, dim=1)
+    assert cos.min().item() >= 0.999, cos.min().item()
+    X = {"video": vid, "vggish": feats["vggish"], "bert": feats["bert"]}
+    out = m({k: v.to(dev) for k, v in X.items()}).cpu()
+    ref = O.head_forward(sd, {"video": ref_emb.view(8, 300, 512), "vggish": feats["vggish"].squeeze(1),
+                              "bert": feats["bert"].squeeze(1)}, mods)
+    assert out.shape == ref.shape == (8, 300, 7)
+    err = (out - ref).abs().max().item()
+    agree = (out.argmax(-1) == ref.argmax(-1)).float().mean().item()
+    assert err <= 2e-2, err
+    assert agree >= 0.995, agree
+
+
+def test_head_graph_replay_after_workspace_regrow():
+    """A CUDA graph captured for a small (B, T) must stay valid after a larger input made the TCN
+    engines grow their workspace (the graph's kernel nodes hold the old block's address)."""
+    dev = _dev()
+    mods = ["cnn_res50", "vggish", "bert"]
+    m = _lfan(mods, dev, seed=13)
+    small = {k: v.squeeze(1).to(dev) for k, v in synthetic.feature_windows(1, 300, seed=131, modalities=mods).items()}
+    big = {k: v.squeeze(1).to(dev) for k, v in synthetic.feature_windows(6, 300, seed=132, modalities=mods).items()}
+    y_small = m.forward_features(dict(small)).clone()          # captures the (1, 300) graph
+    m.forward_features(dict(small))
+    keep = [m.forward_features(dict(big)).clone() for _ in range(2)]      # regrows the workspaces
+    junk = [torch.full((1 << 20,), float("nan"), device=dev) for _ in range(8)]   # would land in a freed block
+    y_again = m.forward_features(dict(small))                  # replays the old graph
+    assert torch.equal(y_again, y_small)
+    m.head_cuda_graph = False
+    try:
+        assert torch.equal(m.forward_features(dict(small)), y_small)
+        assert torch.equal(m.forward_features(dict(big)), keep[0])
+    finally:
+        m.head_cuda_graph = True
+    assert all(torch.isnan(j).all() for j in junk)
