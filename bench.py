@@ -244,7 +244,16 @@ def library_bar(dev, frames):
     if model is None:
         return {"unavailable": "oracle/_ref not staged"}
     import copy
-    vb = copy.deepcopy(model.spatial["visual"]).to(dev).eval().to(memory_format=torch.channels_last)
+    ref_vb = copy.deepcopy(model.spatial["visual"]).to(dev).eval().to(memory_format=torch.channels_last)
+    l2_norm = sys.modules["models.arcface_model"].l2_norm
+
+    def vb(t):
+        # Backbone.forward (models/arcface_model.py:147-151) module by module: the reference's Flatten is a
+        # .view, which needs an NCHW-contiguous tensor, so the 5x5x512 map is made contiguous before output_layer
+        bb = ref_vb.backbone
+        h = bb.body(bb.input_layer(t))
+        return l2_norm(bb.output_layer(h.contiguous()))
+
     x = synthetic.frames(frames, seed=9).to(dev).contiguous(memory_format=torch.channels_last)
     old = (torch.backends.cudnn.benchmark, torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
     res = {"frames": frames, "what": "reference VisualBackbone.forward (oracle/_ref), eager, channels_last, cudnn.benchmark"}
@@ -262,7 +271,7 @@ def library_bar(dev, frames):
         res["error"] = f"{type(e).__name__}: {e}"[:200]
     finally:
         torch.backends.cudnn.benchmark, torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
-        del vb, x
+        del ref_vb, x
         torch.cuda.empty_cache()
     best = min([v for k, v in res.items() if k.endswith("_ms")], default=None)
     if best:

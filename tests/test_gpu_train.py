@@ -1,7 +1,7 @@
 """GPU parity of the fusion-head training step (BASELINE config 4) -- forward in training mode,
 cross-entropy, backward, optimizer -- against the reference-generated golden (Dropout p = 0) and
 against the oracle with this repo's dropout masks.  Tolerances: fp32 kernels vs fp32 CPU autograd,
-gradients within 2e-4 of each tensor's norm, loss within 2e-5."""
+gradients within 2e-5 of each tensor's norm (8x what was measured, see _grad_close), loss within 2e-5."""
 import os
 import warnings
 
@@ -39,19 +39,20 @@ def _lfan(mods, dev, seed=0, length=300, p_drop=None):
     return m
 
 
-def _grad_close(mine, ref, norm=None, rel=2e-4):
-    """Gradient parity robust to LeakyReLU kinks.  Almost every element must agree within
-    rel * ||ref||; a handful may not: with ~4e6 LeakyReLU sites per step, about one pre-activation
-    lies within fp32 round-off of zero, and the summation order (kernel vs MKL) then decides whether
-    its slope is 1 or 0.01 -- that moves one output channel's gradients (and, more weakly, everything
-    upstream of it), in the reference as much as here.  Those are bounded by count (<= 2 % of the
-    tensor, at least 4 elements) and by 2 % in L2."""
+def _grad_close(mine, ref, norm=None, rel=2e-5):
+    """Gradient parity of the exact-fp32 training kernels against fp32 CPU autograd.
+    Measured on B200 (gpurun_out/r02_grad_stats.json, 888 tensor comparisons of this file): NO element
+    further than 2.5e-6 * ||ref|| from the reference, relative L2 error <= 3.8e-6.  The bounds are set
+    8x above that: every element within 2e-5 * ||ref||, except that a LeakyReLU kink may move a few
+    (a pre-activation within fp32 round-off of zero gets slope 1 or 0.01 depending on the summation
+    order, here as in MKL -- none was observed, so the allowance is 2 elements or 0.02 % of the tensor),
+    and 1e-3 in relative L2."""
     mine, ref = mine.double().flatten(), ref.double().flatten()
     norm = float(ref.norm()) if norm is None else norm
     err = (mine - ref).abs()
     n_bad = int((err > rel * norm + 1e-7).sum())
-    assert n_bad <= max(4, mine.numel() // 50), (n_bad, mine.numel(), err.max().item())
-    assert float(err.norm()) <= 2e-2 * norm + 1e-6, (float(err.norm()), norm)
+    assert n_bad <= max(2, mine.numel() // 5000), (n_bad, mine.numel(), err.max().item())
+    assert float(err.norm()) <= 1e-3 * norm + 1e-6, (float(err.norm()), norm)
     _STATS.append({"numel": mine.numel(), "n_bad": n_bad, "rel_l2": float(err.norm()) / max(norm, 1e-30),
                    "max_rel": float(err.max()) / max(norm, 1e-30)})
     return n_bad
@@ -72,14 +73,14 @@ def _dump_grad_stats():
             json.dump(_STATS, f)
 
 
-def _check_grads(tr, grads, rel=2e-4):
+def _check_grads(tr, grads, rel=2e-5):
     kinks = 0
     for k, g in grads.items():
         try:
             kinks += _grad_close(tr.grad(k).cpu(), g, rel=rel) > 0
         except AssertionError as e:
             raise AssertionError(f"{k}: {e}") from None
-    assert kinks <= 12, f"{kinks} tensors with out-of-tolerance elements: more than LeakyReLU kinks explain"
+    assert kinks <= 3, f"{kinks} tensors with out-of-tolerance elements: more than LeakyReLU kinks explain"
     return kinks
 
 
