@@ -37,7 +37,10 @@ struct HaloSmem {
   static constexpr int kNumBars = 2 * kStages + 5;
   static constexpr int kTableOffset = (kBarOffset + kNumBars * 8 + 16 + 15) & ~15;
   static constexpr int kTableFloats = 10 * BN;
-  static constexpr int kTotal = kTableOffset + kTableFloats * 4 + 1024;
+  // BN = 64: 2 KB per epilogue warp for the staged (coalescing) epilogue; BN = 128 has no room beside its 144 KB of weights
+  static constexpr bool kStaged = BN == 64;
+  static constexpr int kEpiStageOffset = kTableOffset + kTableFloats * 4;
+  static constexpr int kTotal = kEpiStageOffset + (kStaged ? kEpiWarps * 2048 : 0) + 1024;
 };
 
 __device__ __forceinline__ void tma_load_tile_4d(const CUtensorMap* m, uint32_t bar, uint32_t dst, int c, int w, int h, int n) {
@@ -187,8 +190,13 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
       }
       const bool pool_store = p.pool_xor && valid && !(oh & 1) && !(ow & 1);
       const size_t pool_off = ((static_cast<size_t>(n) * (p.Hout >> 1) + (oh >> 1)) * (p.Wout >> 1) + (ow >> 1)) * p.Cout + n0;
-      conv_epilogue_core<BN>(p, s_bias, s_alpha, tmem_base + acc * BN, n0, warp, tfull0 + acc * 8, acc_phase, valid, cls,
-                             m * p.Cout + n0, tempty0 + acc * 8, pool_store, pool_off);
+      if (L::kStaged && !p.pool_xor)
+        conv_epilogue_core_staged<BN>(p, s_bias, s_alpha, tmem_base + acc * BN, n0, warp, tfull0 + acc * 8, acc_phase, valid, cls,
+                                      m * p.Cout + n0, tempty0 + acc * 8,
+                                      reinterpret_cast<uint4*>(smem + L::kEpiStageOffset + warp * 2048));
+      else
+        conv_epilogue_core<BN>(p, s_bias, s_alpha, tmem_base + acc * BN, n0, warp, tfull0 + acc * 8, acc_phase, valid, cls,
+                               m * p.Cout + n0, tempty0 + acc * 8, pool_store, pool_off);
     }
   }
 

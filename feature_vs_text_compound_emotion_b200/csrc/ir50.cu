@@ -15,6 +15,7 @@
 #include "conv_plan.h"
 #include "conv_igemm2.cuh"
 #include "conv_halo.cuh"
+#include "stem_tc.cuh"
 #include <cstdlib>
 
 namespace cer {
@@ -526,6 +527,36 @@ int launch_conv(const ConvOp& op, int frames, int num_sms, cudaStream_t st) {
   return set_error(CER_ERR_INVALID, "launch_conv: unknown variant");
 }
 
+// CER_STEM_TC=0 keeps the CUDA-core stem (A/B timing, exact-fp32 first layer).
+static bool stem_tc_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("CER_STEM_TC"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v == 1;
+}
+
+int launch_stem(const float* x, const float* w, const float* bias, const float* alpha, __nv_bfloat16* out,
+                const CUtensorMap& tmap_out, int frames, int H, int W, int num_sms, cudaStream_t st) {
+  if (frames <= 0) return CER_OK;
+  if (stem_tc_enabled()) {
+    static unsigned long long configured = 0;
+    if (first_use_on_device(&configured))
+      CER_CUDA(cudaFuncSetAttribute(stem_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, StemSmem::kTotal));
+    ConvKernelParams p;
+    memset(&p, 0, sizeof p);
+    p.M = frames * H * W;
+    p.Hout = H; p.Wout = W; p.Cout = 64;
+    p.num_m_tiles = (p.M + kBlockM - 1) / kBlockM; p.num_n_tiles = 1;
+    p.bias_classes = 1; p.bias = bias; p.alpha = alpha; p.out = out;
+    stem_tc_kernel<<<std::min(p.num_m_tiles, num_sms), kStemThreads, StemSmem::kTotal, st>>>(p, tmap_out, x, w);
+  } else {
+    const long long pix = (long long)frames * H * ((W + 1) / 2);      // one thread per pixel pair
+    const int blocks = (int)std::min<long long>((pix + 127) / 128, (long long)num_sms * 16);
+    stem_kernel<<<blocks, 128, 0, st>>>(x, w, bias, alpha, out, frames, H, W);
+  }
+  CER_CUDA(cudaGetLastError());
+  return CER_OK;
+}
+
 }  // namespace cer
 
 using namespace cer;
@@ -543,6 +574,7 @@ struct cer_ir50 {
   struct ActInfo { const void* ptr; int H, W, C; };
   std::vector<ActInfo> unit_out;    // where each unit's output lives
   ActInfo stem_out;
+  CUtensorMap stem_out_map;         // stem output [pixels][64] bf16 for the TMA store of stem_tc_kernel
 };
 
 static const int kPadFrames = 8;   // a 128-pixel tile may run at most 127 pixels (<= 6 frames of 5x5) past the end
@@ -597,6 +629,8 @@ extern "C" int cer_ir50_create(cer_ir50** out, const cer_ir50_weights* w, int64_
   int H = w->in_h, W = w->in_w;
   int cur = 0, tb = 1, nxt = 2;
   p->stem_out = {p->buf[cur], H, W, 64};
+  rc = make_tiled2d_map_generic(&p->stem_out_map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, p->buf[cur], p->n_cap * H * W, 64, kBlockM, 64);
+  if (rc) { delete p; return rc; }
   int C = 64;
   for (int i = 0; i < w->n_units; ++i) {
     const cer_ir_unit& u = p->units[i];
@@ -648,12 +682,11 @@ extern "C" int cer_ir50_create(cer_ir50** out, const cer_ir50_weights* w, int64_
 }
 
 static int run_pass(cer_ir50* p, const float* x, int frames, int last_unit, float* emb_out, cudaStream_t st) {
-  const int H = p->w.in_h, W = p->w.in_w;
-  const long long pix = (long long)frames * H * ((W + 1) / 2);      // one thread per pixel pair
-  const int blocks = (int)std::min<long long>((pix + 127) / 128, (long long)p->num_sms * 16);
-  stem_kernel<<<blocks, 128, 0, st>>>(x, p->w.stem_w, p->w.stem_bias, p->w.stem_alpha,
-                                      reinterpret_cast<__nv_bfloat16*>(p->buf[0]), frames, H, W);
-  CER_CUDA(cudaGetLastError());
+  {
+    int rc = launch_stem(x, p->w.stem_w, p->w.stem_bias, p->w.stem_alpha, reinterpret_cast<__nv_bfloat16*>(p->buf[0]), p->stem_out_map,
+                         frames, p->w.in_h, p->w.in_w, p->num_sms, st);
+    if (rc) return rc;
+  }
   const int n_units = (int)p->units.size();
   for (int i = 0; i < n_units && i <= last_unit; ++i) {
     int rc = launch_conv(p->ops[2 * i], frames, p->num_sms, st);
@@ -718,12 +751,9 @@ extern "C" int cer_ir50_run_ops(cer_ir50* p, const float* x, int64_t frames, int
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   for (int op = first_op; op <= last_op; ++op) {
     if (op == 0) {
-      const int H = p->w.in_h, W = p->w.in_w;
-      const long long pix = (long long)frames * H * ((W + 1) / 2);
-      const int blocks = (int)std::min<long long>((pix + 127) / 128, (long long)p->num_sms * 16);
-      stem_kernel<<<blocks, 128, 0, st>>>(x, p->w.stem_w, p->w.stem_bias, p->w.stem_alpha,
-                                          reinterpret_cast<__nv_bfloat16*>(p->buf[0]), (int)frames, H, W);
-      CER_CUDA(cudaGetLastError());
+      int rc = launch_stem(x, p->w.stem_w, p->w.stem_bias, p->w.stem_alpha, reinterpret_cast<__nv_bfloat16*>(p->buf[0]),
+                           p->stem_out_map, (int)frames, p->w.in_h, p->w.in_w, p->num_sms, st);
+      if (rc) return rc;
     } else {
       int rc = launch_conv(p->ops[op - 1], (int)frames, p->num_sms, st);
       if (rc) return rc;

@@ -19,6 +19,8 @@ struct Params {
   int stages;     // distinct A/B smem slots walked round-robin
   int sbo;        // A descriptor group stride in bytes (1024 dense, 1280 halo slab)
   int a_step;     // bytes between the A starts of consecutive k-steps inside a slot (halo taps: 128)
+  int layout;     // descriptor swizzle mode: 2 = 128 B rows, 4 = 64 B rows, 6 = 32 B rows (K-major)
+  int nacc;       // accumulators the MMAs rotate over (1 = every MMA depends on the previous one's accumulator)
   long long* cycles;
 };
 
@@ -36,10 +38,10 @@ __global__ void __launch_bounds__(128, 1) probe(const Params p) {
   fence_proxy_async();
   if (warp == 0) {
     if (CG == 2) {
-      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(256) : "memory");
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(512) : "memory");
       asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
     } else {
-      tmem_alloc(&tmem_slot, 256);
+      tmem_alloc(&tmem_slot, 512);
       tmem_relinquish();
     }
   }
@@ -55,18 +57,34 @@ __global__ void __launch_bounds__(128, 1) probe(const Params p) {
   long long t0 = 0, t1 = 0;
   if (warp == 0 && rank == 0) {
     const uint32_t idesc = umma_idesc(128 * CG, p.n, 1);
-    const uint32_t hi_a = (static_cast<uint32_t>(p.sbo) >> 4) | (1u << 14) | (2u << 29);
+    // row bytes of the swizzle mode; a K = 16 slice is 32 B: slices_per_row of them share a row, the next
+    // group of slices starts a new [rows x row_bytes] tile
+    const int row_bytes = p.layout == 2 ? 128 : (p.layout == 4 ? 64 : 32);
+    const int spr = row_bytes / 32;
+    const uint32_t sbo = p.sbo != 1024 ? (uint32_t)p.sbo : 8u * row_bytes;
+    const uint32_t hi_a = (sbo >> 4) | (1u << 14) | ((uint32_t)p.layout << 29);
+    const uint32_t hi_b = ((8u * row_bytes) >> 4) | (1u << 14) | ((uint32_t)p.layout << 29);
+    const uint32_t a_tile = (128 * row_bytes) >> 4, b_tile = ((p.n / CG) * row_bytes) >> 4;
+    // all descriptors of one round (4 stages x 4 k-slices) are built BEFORE the timed loop: the loop body is
+    // nothing but 16 tcgen05.mma with register operands (an issue loop with address arithmetic in it measured
+    // 84-111 cycles per MMA whatever N was: the issuing thread, not the tensor pipe)
+    uint64_t ad[16], bd[16];
+    uint32_t td[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const int s = (i >> 2) % p.stages, k = i & 3;
+      const uint32_t a_lo = umma_desc_lo(base + s * kSlot + (i >> 2) * p.a_step);
+      const uint32_t b_lo = umma_desc_lo(b_base + (s & 1) * b_bytes);
+      ad[i] = (static_cast<uint64_t>(hi_a) << 32) | (a_lo + (k / spr) * a_tile + (k % spr) * 2);
+      bd[i] = (static_cast<uint64_t>(hi_b) << 32) | (b_lo + (k / spr) * b_tile + (k % spr) * 2);
+      td[i] = tmem + (i % p.nacc) * p.n;
+    }
     t0 = clock64();
-    for (int it = 0; it < p.iters; ++it) {
-      const int s = it % p.stages;
-      const uint32_t a_lo = umma_desc_lo(base + s * kSlot + (it % 9) * p.a_step);
-      const uint32_t b_lo = umma_desc_lo(b_base + (s & 1) * b_bytes);      // two B slots
+    for (int it = 0; it < p.iters; it += 4) {
       if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const uint64_t ad = (static_cast<uint64_t>(hi_a) << 32) | (a_lo + 2 * k);
-          const uint64_t bd = umma_desc_from_lo(b_lo + 2 * k);
-          if (CG == 2) umma2_f16(tmem, ad, bd, idesc, 1u); else umma_f16(tmem, ad, bd, idesc, 1u);
+        for (int i = 0; i < 16; ++i) {
+          if (CG == 2) umma2_f16(td[i], ad[i], bd[i], idesc, 1u); else umma_f16(td[i], ad[i], bd[i], idesc, 1u);
         }
       }
       __syncwarp();
@@ -86,17 +104,17 @@ __global__ void __launch_bounds__(128, 1) probe(const Params p) {
   if (CG == 2) cluster_sync_all();
   if (warp == 0) {
     tc_fence_after();
-    if (CG == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256) : "memory");
-    else tmem_dealloc(tmem, 256);
+    if (CG == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
+    else tmem_dealloc(tmem, 512);
   }
 }
 
 template <int CG>
-static double run(int n, int stages, int sbo, int a_step, int iters, int sms) {
+static double run(int n, int stages, int sbo, int a_step, int nacc, int layout, int iters, int sms) {
   long long* d;
   cudaMalloc(&d, sizeof(long long) * sms);
   cudaMemset(d, 0, sizeof(long long) * sms);
-  Params p{n, iters, stages, sbo, a_step, d};
+  Params p{n, iters, stages, sbo, a_step, layout, nacc, d};
   const size_t smem = 205 * 1024;
   cudaFuncSetAttribute(probe<CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   cudaLaunchConfig_t cfg = {};
@@ -126,16 +144,19 @@ int main() {
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
   const int iters = 4096;
   printf("cycles per tcgen05.mma (K = 16, bf16, SS mode), max over CTAs, %d k-steps of 4 MMAs\n", iters);
-  printf("%-4s %-5s %-7s %-6s %-7s %10s %12s %12s\n", "cg", "N", "stages", "sbo", "a_step", "cyc/MMA", "floor", "B/clk/SM");
+  printf("%-4s %-5s %-7s %-6s %-5s %-7s %10s %12s %12s\n", "cg", "N", "stages", "sbo", "nacc", "swizzle", "cyc/MMA", "floor", "B/clk/SM");
   for (int cg = 1; cg <= 2; ++cg)
     for (int n : {64, 128, 256})
-      for (int mode = 0; mode < 3; ++mode) {
+      for (int mode = 0; mode < 6; ++mode) {
         const int stages = mode == 0 ? 1 : 4;
         const int sbo = mode == 2 ? 1280 : 1024, a_step = mode == 2 ? 128 : 0;
-        const double c = cg == 1 ? run<1>(n, stages, sbo, a_step, iters, sms) : run<2>(n, stages, sbo, a_step, iters, sms);
-        const double floor_c = 128.0 * n / 256.0;            // per SM: M = 128 rows x N x K=16 at 8192 MAC-pairs... see DESIGN
+        const int nacc = mode == 3 ? 2 : 1;
+        const int layout = mode == 4 ? 4 : (mode == 5 ? 6 : 2);
+        if (nacc * n > 512) continue;
+        const double c = cg == 1 ? run<1>(n, stages, sbo, a_step, nacc, layout, iters, sms) : run<2>(n, stages, sbo, a_step, nacc, layout, iters, sms);
+        const double floor_c = 128.0 * n / 256.0;            // tensor-pipe floor per MMA: max(M,128) * N / (256 * cg) cycles for M = 128 * cg
         const double bytes = 128 * 32 + (n / cg) * 32;       // smem bytes one SM reads per MMA
-        printf("%-4d %-5d %-7d %-6d %-7d %10.1f %12.1f %12.1f\n", cg, n, stages, sbo, a_step, c, floor_c, bytes / c);
+        printf("%-4d %-5d %-7d %-6d %-5d %-7d %10.1f %12.1f %12.1f\n", cg, n, stages, sbo, nacc, layout == 2 ? 128 : (layout == 4 ? 64 : 32), c, floor_c, bytes / c);
       }
   return 0;
 }
