@@ -490,6 +490,33 @@ def measure_head_only(dev, reps=50):
             "hbm_frac": by / (ms * 1e-3) / 1e9 / hbm, "bound": "launch latency (9 kernels in one CUDA graph)"}
 
 
+def measure_alt_heads(dev, reps=10):
+    """the alternative heads CAN / JMT / MT (models/model.py:529-684, :895-1167) alone, on
+    pre-encoded features for 8 windows x 300 frames: TCN stacks + fusion (JMT / MT: single-head attention over
+    T = 300 and over all 2400 positions, TF32 tensor-core flash attention) + the fc tail."""
+    from feature_vs_text_compound_emotion_b200 import synthetic
+    from feature_vs_text_compound_emotion_b200.models.model import CAN, JMT
+    out = {}
+    for name in ("CAN", "JMT", "MT"):
+        mods = ["video", "vggish", "bert"] if name == "CAN" else ["video", "vggish"]
+        if name == "CAN":
+            m = CAN(task="CLASSIFICATION", modalities=mods, tcn_settings=synthetic.TCN_SETTINGS, backbone_settings=BS, output_dim=7,
+                    root_dir="", device=dev, visual_state_dict=synthetic.visual_backbone_state_dict(0))
+            m.load_state_dict(synthetic.can_state_dict(0, mods), strict=True)
+        else:
+            m = JMT(task="CLASSIFICATION", modalities=mods, tcn_settings=synthetic.TCN_SETTINGS, backbone_settings=BS, output_dim=7,
+                    root_dir="", device=dev, model_name=name, visual_state_dict=synthetic.visual_backbone_state_dict(0))
+            m.load_state_dict(synthetic.jmt_state_dict(0, mods, model_name=name), strict=True)
+        m = m.to(dev).eval()
+        dims = {"video": 512, "vggish": 128, "bert": 768}
+        feats = {k: torch.randn(WINDOWS, LENGTH, dims[k], device=dev) for k in mods}
+        ms = _events_ms(lambda i: m.forward_features(dict(feats)), reps, warm=2)
+        out[name] = {"ms_per_forward": ms, "frames_per_s": WINDOWS * LENGTH / ms * 1e3}
+        del m
+    out["workload"] = "alternative heads on pre-encoded features, 8 windows x 300 frames (head only: TCN + fusion + fc tail)"
+    return out
+
+
 def hbm_rooflines(dev, model, devb, frames):
     """Memory-/latency-bound kernels of the path, each timed alone over rotating inputs: algorithmic bytes
      / time against the measured HBM copy bandwidth."""
@@ -692,6 +719,7 @@ def run_infer(args, dev, world, rank, local, dist):
         line["gather_verified"] = gather_verified
     if not args.no_sub_records:
         sub["head_only"] = measure_head_only(dev)
+        sub["alt_heads"] = measure_alt_heads(dev)
         line.update(sub)
     if world == 1 and not args.no_library_bar:
         line["library_bar"] = library_bar(dev, frames)

@@ -481,14 +481,18 @@ def softmax_gate(gate: torch.Tensor, feat: torch.Tensor) -> torch.Tensor:
     return out
 
 
-def sdpa(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, batch: int, len_q: int, len_k: int) -> torch.Tensor:
+def sdpa(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, batch: int, len_q: int, len_k: int,
+         precision: str = "tf32") -> torch.Tensor:
     """Single-head attention.  q [batch*len_q, E], k / v [batch*len_k, E] (column slices of a packed
-    projection are fine) -> [batch*len_q, E]."""
+    projection are fine) -> [batch*len_q, E].  precision="tf32": tensor-core flash attention
+    (cer_sdpa_tc_forward, E in {64, 128}); "fp32": the exact CUDA-core kernel (cer_sdpa_forward)."""
     e = q.shape[1]
     out = torch.empty(batch * len_q, e, dtype=torch.float32, device=q.device)
+    tc = precision == "tf32" and e in (64, 128) and all(t.stride(0) % 4 == 0 and t.data_ptr() % 16 == 0 for t in (q, k, v))
+    fn, name = (lib().cer_sdpa_tc_forward, "cer_sdpa_tc_forward") if tc else (lib().cer_sdpa_forward, "cer_sdpa_forward")
     with torch.cuda.device(q.device):
-        check(lib().cer_sdpa_forward(q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), v.data_ptr(), v.stride(0), batch,
-                                     len_q, len_k, e, out.data_ptr(), e, _capi.current_stream_ptr()), "cer_sdpa_forward")
+        check(fn(q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), v.data_ptr(), v.stride(0), batch, len_q, len_k, e,
+                 out.data_ptr(), e, _capi.current_stream_ptr()), name)
     return out
 
 

@@ -184,8 +184,18 @@ class _FeatureHead(_PackedModule):
             B, hh, T, ww = X['logmel'].shape
             patches = X['logmel'].permute(0, 2, 3, 1).contiguous().view(-1, ww, hh)
             X['logmel'] = self.spatial["audio"](patches).view(B, T, -1).unsqueeze(1)
+        return self._encode_features({m: X[m].squeeze(1) for m in X})
+
+    def _encode_features(self, feats) -> Dict[str, torch.Tensor]:
+        """feats[m] [B, T, D_m] (visual = 512-d IR-50 embeddings) -> z[m] [B, T, C_m]."""
         tcn, _, _ = self._engines()
-        return {m: tcn[m].forward(X[m].squeeze(1).float().contiguous()) for m in X}
+        return {m: tcn[m].forward(feats[m].float().contiguous()) for m in feats}
+
+    def forward_features(self, feats) -> torch.Tensor:
+        """The head alone on pre-encoded features (like LFAN.forward_features): feats[m] [B, T, D_m]."""
+        from . import _capi
+        _capi.require_gpu()
+        return self._fuse(self._encode_features(feats))
 
     def _tail(self, c2d: torch.Tensor, B: int, T: int) -> torch.Tensor:
         _, w1, b1 = self._engines()
@@ -212,7 +222,9 @@ class CAN(_FeatureHead):
         self._load_backbones(modalities, visual_state_dict, audio_state_dict)
 
     def forward(self, X):
-        z = self._encode(X)
+        return self._fuse(self._encode(X))
+
+    def _fuse(self, z):
         order = list(z)                                   # AttentionFusion walks x.values() (model.py:560-561)
         B, T, _ = z[order[0]].shape
         n = len(order)
@@ -245,7 +257,9 @@ class JMT(_FeatureHead):
         self._load_backbones(modalities, visual_state_dict, audio_state_dict)
 
     def forward(self, X):
-        z = self._encode(X)
+        return self._fuse(self._encode(X))
+
+    def _fuse(self, z):
         f = self.fuse
         B, T, _ = z['video'].shape
         R = B * T

@@ -338,6 +338,11 @@ int cer_linear_forward(const float* x_dev, int64_t rows, int32_t in_dim, int32_t
 int cer_softmax_gate(const float* gate_dev, const float* feat_dev, int64_t rows, int32_t dim, float* out_dev, void* stream);
 int cer_sdpa_forward(const float* q_dev, int32_t ldq, const float* k_dev, int32_t ldk, const float* v_dev, int32_t ldv,
                      int32_t batch, int32_t len_q, int32_t len_k, int32_t dim, float* out_dev, int32_t ldo, void* stream);
+/* The same attention on the tensor cores (flash-attention forward, TF32 mma with fp32 accumulate and an fp32
+ * online softmax): dim 64 or 128; q / k / v 16-byte aligned with row pitches that are multiples of 4 floats.
+ * Any len_q / len_k (ragged tiles are masked).  Result within ~1e-3 of cer_sdpa_forward. */
+int cer_sdpa_tc_forward(const float* q_dev, int32_t ldq, const float* k_dev, int32_t ldk, const float* v_dev, int32_t ldv,
+                        int32_t batch, int32_t len_q, int32_t len_k, int32_t dim, float* out_dev, int32_t ldo, void* stream);
 /* y = tanh(y) in place: the output squashing of task == REGRESSION (models/model.py:523, :682, :1165). */
 int cer_tanh_inplace(float* y_dev, int64_t n, void* stream);
 int cer_add_layernorm(const float* x_dev, const float* res_dev, int64_t rows, int32_t dim, const float* gamma_dev,

@@ -15,6 +15,7 @@ reference modules, imported as they are, are the source of truth):
   * eval_transform.pt -- the reference's eval transform classes (PIL resize 48, crop 40, normalise) on seeded uint8 frames
   * logmel.pt       -- mel_features.log_mel_spectrogram + my_frame (the reference code) on a seeded 3 s waveform
   * heads.pt        -- CAN / JMT / MT forward from pixels (B=2 x T=24) and their state_dict key listings
+  * heads_t300.pt   -- the same heads at the reference's window length (B=2 x T=300)
   * attention_maps.pt -- MultimodalTransformerEncoder.get_attention_maps on seeded encoder outputs
   * windowing.json  -- Trainer.windowing outputs for a set of lengths
 Weights are NOT stored: they are regenerated from the seed by
@@ -40,6 +41,52 @@ warnings.filterwarnings("ignore")
 from feature_vs_text_compound_emotion_b200 import synthetic  # noqa: E402
 
 OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def _heads(TH, ref_configs, tmp, with_keys=True):
+    """CAN / JMT / MT from pixels, B = 2 windows of TH frames, through the reference modules."""
+    from models.model import CAN, JMT
+    ts = ref_configs.config["tcn_settings"]
+    assert {k: ts[k] for k in synthetic.TCN_SETTINGS} == synthetic.TCN_SETTINGS
+    heads = {}
+    cmods = ["video", "vggish", "bert"]
+    can = CAN(task="CLASSIFICATION", modalities=cmods, tcn_settings=ts, backbone_settings=ref_configs.config["backbone_settings"],
+              output_dim=7, root_dir=tmp, device="cpu")
+    csd = synthetic.can_state_dict(0, cmods)
+    assert list(can.state_dict()) == list(csd)
+    can.load_state_dict(csd, strict=True)
+    can.eval()
+    fh = synthetic.feature_windows(2, TH, seed=705, modalities=["vggish", "bert"])
+    Xc = {"video": synthetic.frames(2 * TH, seed=706).view(2, TH, 3, 40, 40), "vggish": fh["vggish"], "bert": fh["bert"]}
+    heads["CAN"] = {"modalities": cmods, "feat_seed": 705, "frame_seed": 706, "T": TH, "out": can({k: v.clone() for k, v in Xc.items()})}
+    if with_keys:
+        heads["CAN"]["keys"] = {k: list(v.shape) for k, v in can.state_dict().items()}
+    for name in ("JMT", "MT"):
+        jmods = ["video", "vggish"]
+        jm = JMT(task="CLASSIFICATION", modalities=jmods, tcn_settings=ts, backbone_settings=ref_configs.config["backbone_settings"],
+                 output_dim=7, root_dir=tmp, device="cpu", model_name=name)
+        jsd = synthetic.jmt_state_dict(0, jmods, model_name=name)
+        assert list(jm.state_dict()) == list(jsd)
+        jm.load_state_dict(jsd, strict=True)
+        jm.eval()
+        Xj = {"video": synthetic.frames(2 * TH, seed=707).view(2, TH, 3, 40, 40),
+              "vggish": synthetic.feature_windows(2, TH, seed=708, modalities=["vggish"])["vggish"]}
+        heads[name] = {"modalities": jmods, "feat_seed": 708, "frame_seed": 707, "T": TH, "out": jm({k: v.clone() for k, v in Xj.items()})}
+        if with_keys:
+            heads[name]["keys"] = {k: list(v.shape) for k, v in jm.state_dict().items()}
+    return heads
+
+
+def only_heads_t300():
+    """python oracle/gen_golden.py heads300 -- just tests/golden/heads_t300.pt (the other fixtures are untouched)."""
+    torch.manual_seed(0)
+    torch.set_grad_enabled(False)
+    import configs as ref_configs
+    tmp = tempfile.mkdtemp()
+    torch.save(synthetic.visual_backbone_state_dict(seed=0), os.path.join(tmp, "res50_ir_0.887.pth"))
+    heads = _heads(300, ref_configs, tmp, with_keys=False)
+    torch.save(heads, os.path.join(OUT, "heads_t300.pt"))
+    print("heads_t300", {k: tuple(v["out"].shape) for k, v in heads.items()})
 
 
 def main():
@@ -204,35 +251,12 @@ def main():
     print("logmel", lm.shape, ex.shape)
 
     # ---- alternative heads CAN / JMT / MT (models/model.py:529-684, :895-1167) ------------------
-    from models.model import CAN, JMT
-    ts = ref_configs.config["tcn_settings"]
-    assert {k: ts[k] for k in synthetic.TCN_SETTINGS} == synthetic.TCN_SETTINGS
-    TH, heads = 24, {}
-    cmods = ["video", "vggish", "bert"]
-    can = CAN(task="CLASSIFICATION", modalities=cmods, tcn_settings=ts, backbone_settings=ref_configs.config["backbone_settings"],
-              output_dim=7, root_dir=tmp, device="cpu")
-    csd = synthetic.can_state_dict(0, cmods)
-    assert list(can.state_dict()) == list(csd)
-    can.load_state_dict(csd, strict=True)
-    can.eval()
-    fh = synthetic.feature_windows(2, TH, seed=705, modalities=["vggish", "bert"])
-    Xc = {"video": synthetic.frames(2 * TH, seed=706).view(2, TH, 3, 40, 40), "vggish": fh["vggish"], "bert": fh["bert"]}
-    heads["CAN"] = {"modalities": cmods, "feat_seed": 705, "frame_seed": 706, "T": TH, "out": can({k: v.clone() for k, v in Xc.items()}),
-                    "keys": {k: list(v.shape) for k, v in can.state_dict().items()}}
-    for name in ("JMT", "MT"):
-        jmods = ["video", "vggish"]
-        jm = JMT(task="CLASSIFICATION", modalities=jmods, tcn_settings=ts, backbone_settings=ref_configs.config["backbone_settings"],
-                 output_dim=7, root_dir=tmp, device="cpu", model_name=name)
-        jsd = synthetic.jmt_state_dict(0, jmods, model_name=name)
-        assert list(jm.state_dict()) == list(jsd)
-        jm.load_state_dict(jsd, strict=True)
-        jm.eval()
-        Xj = {"video": synthetic.frames(2 * TH, seed=707).view(2, TH, 3, 40, 40),
-              "vggish": synthetic.feature_windows(2, TH, seed=708, modalities=["vggish"])["vggish"]}
-        heads[name] = {"modalities": jmods, "feat_seed": 708, "frame_seed": 707, "T": TH, "out": jm({k: v.clone() for k, v in Xj.items()}),
-                       "keys": {k: list(v.shape) for k, v in jm.state_dict().items()}}
+    heads = _heads(24, ref_configs, tmp)
     torch.save(heads, os.path.join(OUT, "heads.pt"))
     print("heads", {k: (tuple(v["out"].shape), len(v["keys"])) for k, v in heads.items()})
+    heads = _heads(300, ref_configs, tmp, with_keys=False)         # the reference's window length
+    torch.save(heads, os.path.join(OUT, "heads_t300.pt"))
+    print("heads_t300", {k: tuple(v["out"].shape) for k, v in heads.items()})
 
     # ---- attention maps of the cross-modal encoder (transformer.py:211-215) ---------------------
     from models.transformer import MultimodalTransformerEncoder
@@ -257,4 +281,7 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "heads300":
+        only_heads_t300()
+    else:
+        main()

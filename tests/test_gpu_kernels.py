@@ -267,3 +267,39 @@ def test_c_abi_error_paths_report_status_and_message():
         eng.forward(torch.zeros(2, 3, 32, 32, device=dev))
     with pytest.raises(ValueError):
         eng.forward(torch.zeros(2, 3, 40, 40))                               # CPU tensor
+
+
+def test_head_building_blocks_vs_torch():
+    """cer_linear_forward / cer_softmax_gate / cer_add_layernorm (exact fp32) and both attention kernels --
+    cer_sdpa_forward (fp32 CUDA cores) and cer_sdpa_tc_forward (TF32 tensor-core flash attention) --
+    against plain PyTorch fp32 on the CPU: ragged lengths, several batches, operands that are column slices
+    of a packed projection (row pitch 3E), E = 128 and 64."""
+    dev = _dev()
+    from feature_vs_text_compound_emotion_b200 import engine as E
+    g = torch.Generator().manual_seed(31)
+    x = torch.randn(333, 200, generator=g)
+    w, b = torch.randn(96, 200, generator=g) * 0.1, torch.randn(96, generator=g)
+    for act, f in ((None, lambda t: t), ("leaky_relu", F.leaky_relu), ("relu", F.relu)):
+        got = E.linear(x.to(dev), w.to(dev), b.to(dev), act).cpu()
+        assert (got - f(x @ w.t() + b)).abs().max().item() < 1e-4, act
+    wide = torch.zeros(333, 256, device=dev)
+    E.linear(x.to(dev), w.to(dev), b.to(dev), out=wide[:, 128:224])                    # concat without a copy
+    assert (wide[:, 128:224].cpu() - (x @ w.t() + b)).abs().max().item() < 1e-4 and float(wide[:, :128].abs().max()) == 0.0
+    gate, feat = torch.randn(77, 384, generator=g), torch.randn(77, 384, generator=g)
+    assert (E.softmax_gate(gate.to(dev), feat.to(dev)).cpu() - torch.softmax(gate, -1) * feat).abs().max().item() < 1e-6
+    res = torch.randn(333, 96, generator=g)
+    gam, bet = torch.rand(96, generator=g) + 0.5, torch.randn(96, generator=g)
+    want = F.layer_norm(x @ w.t() + res, (96,), gam, bet, 1e-5)
+    got = E.add_layernorm((x @ w.t()).to(dev), res.to(dev), gam.to(dev), bet.to(dev)).cpu()
+    assert (got - want).abs().max().item() < 1e-4
+    for (e, batch, lq, lk) in ((128, 2, 300, 300), (128, 1, 600, 600), (128, 3, 37, 91), (64, 2, 65, 130), (128, 1, 1, 1)):
+        qkv = torch.randn(batch * max(lq, lk), 3 * e, generator=g)
+        q, k, v = qkv[:batch * lq, :e], qkv[:batch * lk, e:2 * e], qkv[:batch * lk, 2 * e:]
+        want = F.scaled_dot_product_attention(q.reshape(batch, lq, e), k.reshape(batch, lk, e), v.reshape(batch, lk, e)).reshape(-1, e)
+        qd = qkv.to(dev)
+        qs, ks, vs = qd[:batch * lq, :e], qd[:batch * lk, e:2 * e], qd[:batch * lk, 2 * e:]
+        exact = E.sdpa(qs, ks, vs, batch, lq, lk, precision="fp32").cpu()
+        assert (exact - want).abs().max().item() < 2e-5, (e, batch, lq, lk)
+        tc = E.sdpa(qs, ks, vs, batch, lq, lk, precision="tf32").cpu()
+        assert (tc - want).abs().max().item() < 5e-3, (e, batch, lq, lk, (tc - want).abs().max().item())
+        assert not torch.equal(tc, exact) or lk == 1                                    # the tensor-core kernel did run

@@ -265,12 +265,17 @@ def test_empty_ragged_and_short_inputs():
         assert (out - want).abs().max().item() <= 2e-2, L
 
 
-@pytest.mark.parametrize("name", ["CAN", "JMT", "MT"])
-def test_alternative_heads_vs_golden(golden_dir, name):
-    """CAN / JMT / MT drop-ins from pixels vs the reference's outputs (same tolerances as LFAN)."""
+@pytest.mark.parametrize("name,fixture,bar", [("CAN", "heads.pt", 0.95), ("JMT", "heads.pt", 0.95), ("MT", "heads.pt", 0.95),
+                                              ("CAN", "heads_t300.pt", 0.995), ("JMT", "heads_t300.pt", 0.995),
+                                              ("MT", "heads_t300.pt", 0.995)])
+def test_alternative_heads_vs_golden(golden_dir, name, fixture, bar):
+    """CAN / JMT / MT drop-ins from pixels vs the reference's outputs: B = 2 windows of T = 24 frames (48
+    frames: at most two argmax flips) and of the reference's window length T = 300, where JMT / MT run
+    nn.MultiheadAttention(128, 1) over 300 positions and the final encoder over all 600 (models/model.py:731,
+    :917-931, :1003-1012) -- BASELINE.json's bars: logit max-abs <= 2e-2, argmax agreement >= 99.5 %."""
     dev = _dev()
     from feature_vs_text_compound_emotion_b200.models.model import CAN, JMT
-    g = torch.load(os.path.join(golden_dir, "heads.pt"))[name]
+    g = torch.load(os.path.join(golden_dir, fixture))[name]
     mods, T = g["modalities"], g["T"]
     vsd = synthetic.visual_backbone_state_dict(0)
     if name == "CAN":
@@ -290,7 +295,7 @@ def test_alternative_heads_vs_golden(golden_dir, name):
     err = (out - g["out"]).abs().max().item()
     agree = (out.argmax(-1) == g["out"].argmax(-1)).float().mean().item()
     assert err <= 2e-2 * max(1.0, g["out"].abs().max().item()), err
-    assert agree >= 0.95, agree          # 48 frames: at most two flips
+    assert agree >= bar, agree
 
 
 def test_vggish_fused_pool_equals_separate_pool_kernel(monkeypatch):
