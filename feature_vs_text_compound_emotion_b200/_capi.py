@@ -74,7 +74,7 @@ class TrainModal(C.Structure):
 
 class HeadTrainSpec(C.Structure):
     _fields_ = [("n_modals", C.c_int32), ("kernel_size", C.c_int32), ("modal_dim", C.c_int32), ("num_heads", C.c_int32),
-                ("n_out", C.c_int32), ("reserved", C.c_int32),
+                ("n_out", C.c_int32), ("precision", C.c_int32),
                 ("p_tcn", C.c_double), ("p_fusion", C.c_double), ("bn_momentum", C.c_double),
                 ("modal", TrainModal * CER_MAX_MODALS),
                 ("wo", _F), ("bo", _F), ("ln_g", _F), ("ln_b", _F), ("wr", _F), ("br", _F),

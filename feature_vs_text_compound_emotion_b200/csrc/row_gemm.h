@@ -29,6 +29,7 @@ struct RowGemm {
   int epi;
   float* aux; int ld_aux;                   // BLOCK_OUT: h2d out; DGRAD_ACT: saved activation in
   Drop drop;
+  int tf32;                                 // 1: TF32 tensor-core kernel (mma.sync, fp32 accumulate); 0: exact fp32 FFMA2
 };
 
 

@@ -225,6 +225,194 @@ __global__ void __launch_bounds__(2 * BM) row_gemm_kernel(const RowGemm g) {
 }
 
 // ------------------------------------------------------------------------------------------
+// TF32 tensor-core variants (precision = "tf32", the default of the training plan).  Same tiles, same
+// loaders (register prefetch of the next tile), same epilogues; the inner product runs on warp-level
+// mma.sync.m16n8k8 TF32 MMAs with fp32 accumulate: each warp owns 32 x 32 outputs = 2 x 4 MMA tiles.
+// Operands are rounded to TF32 (cvt.rna) when they are written to shared memory; tiles are stored
+// [k][m] / [k][n] with row pitches of BM + 8 / 72 floats, which makes every fragment load
+// (address = (k0 + t) * pitch + m0 + g) bank-conflict free.  The step is ~30 MFLOP per frame at 600-4800
+// rows: latency- and launch-bound, so the descriptor-free warp-level MMA is used here rather than tcgen05;
+// it removes the fp32 FMA floor (20 TFLOP/s) without a second set of epilogues.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t to_tf32_bits(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ void mma_16x8x8_tf32(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+constexpr int kTcLdn = kGN + 8;      // 72
+
+// one 16-deep k tile: Ms [16][LDM] (m contiguous), Ns [16][72]; this warp's 32 x 32 block at (m0, n0)
+template <int LDM>
+__device__ __forceinline__ void mma_tile_step(const uint32_t* Ms, const uint32_t* Ns, int m0, int n0, int g, int t,
+                                              float (&acc)[2][4][4]) {
+#pragma unroll
+  for (int k8 = 0; k8 < kGK; k8 += 8) {
+    uint32_t a[2][4], b[4][2];
+#pragma unroll
+    for (int mi = 0; mi < 2; ++mi) {
+      const uint32_t* p = Ms + (k8 + t) * LDM + m0 + mi * 16 + g;
+      a[mi][0] = p[0]; a[mi][1] = p[8]; a[mi][2] = p[4 * LDM]; a[mi][3] = p[4 * LDM + 8];
+    }
+#pragma unroll
+    for (int ni = 0; ni < 4; ++ni) {
+      const uint32_t* p = Ns + (k8 + t) * kTcLdn + n0 + ni * 8 + g;
+      b[ni][0] = p[0]; b[ni][1] = p[4 * kTcLdn];
+    }
+#pragma unroll
+    for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni) mma_16x8x8_tf32(acc[mi][ni], a[mi], b[ni]);
+  }
+}
+
+template <bool B_KN, int BM>
+__global__ void __launch_bounds__(2 * BM) row_gemm_tf32_kernel(const RowGemm g) {
+  constexpr int NT = 2 * BM;
+  constexpr int LDM = BM + 8;
+  __shared__ __align__(16) uint32_t As[kGK * LDM];        // [k][row]
+  __shared__ __align__(16) uint32_t Bs[kGK * kTcLdn];     // [k][col]
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int gq = lane >> 2, tq = lane & 3;
+  const int wm = (warp >> 1) * 32, wn = (warp & 1) * 32;
+  const int row0 = blockIdx.y * BM, col0 = blockIdx.x * kGN;
+  float acc[2][4][4];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { acc[i][j][0] = acc[i][j][1] = acc[i][j][2] = acc[i][j][3] = 0.f; }
+
+  constexpr int AH = BM / 2;
+  const int a_r = tid >> 2, a_k = (tid & 3) * 4;
+  const bool a_vec = (g.lda & 3) == 0 && (g.K & 3) == 0 && (reinterpret_cast<uintptr_t>(g.A) & 15) == 0;
+  int a_t[2];
+#pragma unroll
+  for (int h = 0; h < 2; ++h) { const int r = row0 + a_r + AH * h; a_t[h] = r < g.R ? r % g.T : -(1 << 30); }
+  constexpr int BP = 256 / NT;
+  const int b_ld = B_KN ? g.N : g.K;
+  const bool b_vec = (b_ld & 3) == 0 && (reinterpret_cast<uintptr_t>(g.B) & 15) == 0 && (g.b_tap_stride & 3) == 0;
+  const int ksteps = (g.K + kGK - 1) / kGK;
+  const int total = g.taps * ksteps;
+  float4 ra[2], rbv[BP];
+  auto fetch = [&](int it) {
+    const int j = it / ksteps, k0 = (it - j * ksteps) * kGK;
+    const int shift = g.shift0 + j * g.shift_step;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int r = row0 + a_r + AH * h;
+      const bool ok = (a_t[h] + shift) >= 0 && (a_t[h] + shift) < g.T;
+      const float* ap = g.A + (long long)(r + shift) * g.lda + k0 + a_k;
+      if (ok && a_vec && k0 + a_k + 3 < g.K) ra[h] = __ldg(reinterpret_cast<const float4*>(ap));
+      else {
+        ra[h].x = (ok && k0 + a_k + 0 < g.K) ? __ldg(ap + 0) : 0.f;
+        ra[h].y = (ok && k0 + a_k + 1 < g.K) ? __ldg(ap + 1) : 0.f;
+        ra[h].z = (ok && k0 + a_k + 2 < g.K) ? __ldg(ap + 2) : 0.f;
+        ra[h].w = (ok && k0 + a_k + 3 < g.K) ? __ldg(ap + 3) : 0.f;
+      }
+    }
+    const float* bp = g.B + j * g.b_tap_stride;
+#pragma unroll
+    for (int u = 0; u < BP; ++u) {
+      const int slot = tid + u * NT;
+      const int b_a = B_KN ? (slot >> 4) : (slot >> 2);
+      const int b_b = B_KN ? (slot & 15) * 4 : (slot & 3) * 4;
+      float4& rb = rbv[u];
+      if (B_KN) {
+        const int k = k0 + b_a, n = col0 + b_b;
+        const float* q = bp + (long long)k * g.N + n;
+        if (k < g.K && b_vec && n + 3 < g.N) rb = __ldg(reinterpret_cast<const float4*>(q));
+        else {
+          rb.x = (k < g.K && n + 0 < g.N) ? __ldg(q + 0) : 0.f;
+          rb.y = (k < g.K && n + 1 < g.N) ? __ldg(q + 1) : 0.f;
+          rb.z = (k < g.K && n + 2 < g.N) ? __ldg(q + 2) : 0.f;
+          rb.w = (k < g.K && n + 3 < g.N) ? __ldg(q + 3) : 0.f;
+        }
+      } else {
+        const int n = col0 + b_a, k = k0 + b_b;
+        const float* q = bp + (long long)n * g.K + k;
+        if (n < g.N && b_vec && k + 3 < g.K) rb = __ldg(reinterpret_cast<const float4*>(q));
+        else {
+          rb.x = (n < g.N && k + 0 < g.K) ? __ldg(q + 0) : 0.f;
+          rb.y = (n < g.N && k + 1 < g.K) ? __ldg(q + 1) : 0.f;
+          rb.z = (n < g.N && k + 2 < g.K) ? __ldg(q + 2) : 0.f;
+          rb.w = (n < g.N && k + 3 < g.K) ? __ldg(q + 3) : 0.f;
+        }
+      }
+    }
+  };
+  auto stash = [&]() {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      uint32_t* p = As + a_k * LDM + a_r + AH * h;
+      p[0] = to_tf32_bits(ra[h].x); p[LDM] = to_tf32_bits(ra[h].y); p[2 * LDM] = to_tf32_bits(ra[h].z); p[3 * LDM] = to_tf32_bits(ra[h].w);
+    }
+#pragma unroll
+    for (int u = 0; u < BP; ++u) {
+      const int slot = tid + u * NT;
+      const int b_a = B_KN ? (slot >> 4) : (slot >> 2);
+      const int b_b = B_KN ? (slot & 15) * 4 : (slot & 3) * 4;
+      const float4 rb = rbv[u];
+      if (B_KN) {
+        *reinterpret_cast<uint4*>(Bs + b_a * kTcLdn + b_b) = make_uint4(to_tf32_bits(rb.x), to_tf32_bits(rb.y), to_tf32_bits(rb.z), to_tf32_bits(rb.w));
+      } else {
+        uint32_t* p = Bs + b_b * kTcLdn + b_a;
+        p[0] = to_tf32_bits(rb.x); p[kTcLdn] = to_tf32_bits(rb.y); p[2 * kTcLdn] = to_tf32_bits(rb.z); p[3 * kTcLdn] = to_tf32_bits(rb.w);
+      }
+    }
+  };
+  fetch(0);
+  for (int it = 0; it < total; ++it) {
+    stash();
+    __syncthreads();
+    if (it + 1 < total) fetch(it + 1);
+    mma_tile_step<LDM>(As, Bs, wm, wn, gq, tq, acc);
+    __syncthreads();
+  }
+#pragma unroll
+  for (int mi = 0; mi < 2; ++mi) {
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const int r = row0 + wm + mi * 16 + gq + 8 * half;
+      if (r >= g.R) continue;
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni) {
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const int n = col0 + wn + ni * 8 + 2 * tq + c;
+          if (n >= g.N) continue;
+          float v = acc[mi][ni][2 * half + c];
+          if (g.bias) v += __ldg(g.bias + n);
+          const uint32_t idx = (uint32_t)r * (uint32_t)g.N + (uint32_t)n;
+          float* cp = g.C + (long long)r * g.ldc + n;
+          if (g.epi == EPI_LINEAR) {
+            if (g.addend) v += g.addend[(long long)r * g.ld_add + n];
+            if (g.accumulate) v += *cp;
+            *cp = v;
+          } else if (g.epi == EPI_RELU) {
+            *cp = fmaxf(v, 0.f);
+          } else if (g.epi == EPI_LRELU_DROP) {
+            *cp = lrelu(v) * drop_factor(g.drop, idx);
+          } else if (g.epi == EPI_BLOCK_OUT) {
+            const float h2d = lrelu(v) * drop_factor(g.drop, idx);
+            g.aux[(long long)r * g.ld_aux + n] = h2d;
+            *cp = lrelu(h2d + g.addend[(long long)r * g.ld_add + n]);
+          } else {   // EPI_DGRAD_ACT
+            if (g.addend) v += g.addend[(long long)r * g.ld_add + n];
+            const float saved = g.aux[(long long)r * g.ld_aux + n];
+            *cp = v * drop_factor(g.drop, idx) * lrelu_grad(saved);
+          }
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // Intra-CTA split-K variant of the row GEMM for SMALL grids.  The head's GEMMs have only 75-300
 // 64x64 output tiles: with one 4-warp CTA per tile an SM holds 4-8 warps and every LDS->FFMA2
 // dependency is exposed (ncu: short_scoreboard stalls, sm active 65 %).  Here a CTA is four groups
@@ -421,6 +609,7 @@ struct WGrad {
   int taps, shift0, shift_step;
   int k_tiles;
   int rows_per_split;
+  int tf32;                                 // 1: TF32 tensor-core kernel
 };
 
 __global__ void __launch_bounds__(256) wgrad_kernel(const WGrad g) {
@@ -499,6 +688,88 @@ __global__ void __launch_bounds__(256) wgrad_kernel(const WGrad g) {
       }
     }
   }
+}
+
+// TF32 tensor-core weight gradient: same tiling (128 n x 64 k per tap, a slice of the rows, fp32 atomics);
+// the reduction dimension (rows) is the MMA's k.  Gs [16 rows][136] is the "m" operand, As [16 rows][72] the "n".
+__global__ void __launch_bounds__(256) wgrad_tf32_kernel(const WGrad g) {
+  constexpr int LDM = kGM + 8;
+  __shared__ __align__(16) uint32_t Gs[kGK * LDM];
+  __shared__ __align__(16) uint32_t As[kGK * kTcLdn];
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int gq = lane >> 2, tq = lane & 3;
+  const int wm = (warp >> 1) * 32, wn = (warp & 1) * 32;
+  const int j = blockIdx.x / g.k_tiles;
+  const int k0 = (blockIdx.x - j * g.k_tiles) * kGN;
+  const int n0 = blockIdx.y * kGM;
+  const int shift = g.shift0 + j * g.shift_step;
+  const int r_begin = blockIdx.z * g.rows_per_split;
+  const int r_end = min(g.R, r_begin + g.rows_per_split);
+  float acc[2][4][4];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { acc[i][q][0] = acc[i][q][1] = acc[i][q][2] = acc[i][q][3] = 0.f; }
+  const int g_r = tid >> 4, g_c = (tid & 15) * 4;
+  const int a_r = tid >> 4, a_c = (tid & 15) * 4;
+  const bool g_vec = (g.ldg & 3) == 0 && (reinterpret_cast<uintptr_t>(g.G) & 15) == 0;
+  const bool a_vec = (g.lda & 3) == 0 && (reinterpret_cast<uintptr_t>(g.A) & 15) == 0;
+  float4 rg[2], ra;
+  auto fetch = [&](int r0) {
+    const int r = r0 + g_r;
+    const bool r_ok = r < r_end;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int n = n0 + g_c + 64 * h;
+      const float* q = g.G + (long long)r * g.ldg + n;
+      if (r_ok && g_vec && n + 3 < g.N) rg[h] = __ldg(reinterpret_cast<const float4*>(q));
+      else {
+        rg[h].x = (r_ok && n + 0 < g.N) ? __ldg(q + 0) : 0.f;
+        rg[h].y = (r_ok && n + 1 < g.N) ? __ldg(q + 1) : 0.f;
+        rg[h].z = (r_ok && n + 2 < g.N) ? __ldg(q + 2) : 0.f;
+        rg[h].w = (r_ok && n + 3 < g.N) ? __ldg(q + 3) : 0.f;
+      }
+    }
+    const int t = r_ok ? r % g.T : -(1 << 30);
+    const bool ok = (t + shift) >= 0 && (t + shift) < g.T;
+    const int k = k0 + a_c;
+    const float* q = g.A + (long long)(r + shift) * g.lda + k;
+    if (ok && a_vec && k + 3 < g.K) ra = __ldg(reinterpret_cast<const float4*>(q));
+    else {
+      ra.x = (ok && k + 0 < g.K) ? __ldg(q + 0) : 0.f;
+      ra.y = (ok && k + 1 < g.K) ? __ldg(q + 1) : 0.f;
+      ra.z = (ok && k + 2 < g.K) ? __ldg(q + 2) : 0.f;
+      ra.w = (ok && k + 3 < g.K) ? __ldg(q + 3) : 0.f;
+    }
+  };
+  if (r_begin < r_end) fetch(r_begin);
+  for (int r0 = r_begin; r0 < r_end; r0 += kGK) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+      *reinterpret_cast<uint4*>(Gs + g_r * LDM + g_c + 64 * h) =
+          make_uint4(to_tf32_bits(rg[h].x), to_tf32_bits(rg[h].y), to_tf32_bits(rg[h].z), to_tf32_bits(rg[h].w));
+    *reinterpret_cast<uint4*>(As + a_r * kTcLdn + a_c) = make_uint4(to_tf32_bits(ra.x), to_tf32_bits(ra.y), to_tf32_bits(ra.z), to_tf32_bits(ra.w));
+    __syncthreads();
+    if (r0 + kGK < r_end) fetch(r0 + kGK);
+    mma_tile_step<LDM>(Gs, As, wm, wn, gq, tq, acc);
+    __syncthreads();
+  }
+  float* wp = g.dW + j * g.w_tap_stride;
+#pragma unroll
+  for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const int n = n0 + wm + mi * 16 + gq + 8 * half;
+      if (n >= g.N) continue;
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const int k = k0 + wn + ni * 8 + 2 * tq + c;
+          if (k < g.K) atomicAdd(wp + (long long)n * g.K + k, acc[mi][ni][2 * half + c]);
+        }
+    }
 }
 
 // Column sums  out[n] += sum_r X[r, n] (bias gradients).  grid = (ceil(N/32), row splits), block 32x8.
@@ -957,6 +1228,20 @@ inline size_t align_up(size_t x) { return (x + 255) & ~size_t(255); }
 int cer::launch_row_gemm(const RowGemm& g, bool b_kn, cudaStream_t st) {
   const int nt = (g.N + kGN - 1) / kGN;
   const bool big = (long long)((g.R + 127) / 128) * nt >= 2 * 148;      // enough 128-row tiles for two waves
+  if (g.tf32) {
+    // tensor-core path: 128-row tiles when they fill the SMs twice, else 64-row tiles (twice the CTAs)
+    if (big) {
+      dim3 grid(nt, (g.R + 127) / 128);
+      if (b_kn) row_gemm_tf32_kernel<true, 128><<<grid, 256, 0, st>>>(g);
+      else row_gemm_tf32_kernel<false, 128><<<grid, 256, 0, st>>>(g);
+    } else {
+      dim3 grid(nt, (g.R + 63) / 64);
+      if (b_kn) row_gemm_tf32_kernel<true, 64><<<grid, 128, 0, st>>>(g);
+      else row_gemm_tf32_kernel<false, 64><<<grid, 128, 0, st>>>(g);
+    }
+    CER_CUDA(cudaGetLastError());
+    return CER_OK;
+  }
   if (big) {
     dim3 grid(nt, (g.R + 127) / 128);
     if (b_kn) row_gemm_kernel<true, 128><<<grid, 256, 0, st>>>(g);
@@ -998,7 +1283,8 @@ int launch_wgrad(WGrad g, int num_sms, cudaStream_t st) {
   g.rows_per_split = (((g.R + splits - 1) / splits) + 15) / 16 * 16;
   splits = (g.R + g.rows_per_split - 1) / g.rows_per_split;
   dim3 grid(g.k_tiles * g.taps, (g.N + kGM - 1) / kGM, splits);
-  wgrad_kernel<<<grid, 256, 0, st>>>(g);
+  if (g.tf32) wgrad_tf32_kernel<<<grid, 256, 0, st>>>(g);
+  else wgrad_kernel<<<grid, 256, 0, st>>>(g);
   CER_CUDA(cudaGetLastError());
   return CER_OK;
 }
@@ -1027,6 +1313,7 @@ Drop make_drop(double p, uint32_t seed, uint32_t stream) {
 struct cer_head_train {
   cer_head_train_spec s;
   int B, T, R, E, md3, num_sms;
+  int tf32;                         // spec.precision: 1 = TF32 tensor-core GEMMs, 0 = exact fp32
   std::vector<ModalBuf> mod;
   float *vals, *o, *ln_mean, *ln_rstd, *cat, *gcat, *go, *gvals;
   cudaStream_t side[CER_MAX_MODALS];      // modality m > 0 runs on side[m]; modality 0 on the caller's stream
@@ -1114,6 +1401,7 @@ extern "C" int cer_head_train_create(cer_head_train** out, const cer_head_train_
   p->s = *s;
   p->B = (int)batch; p->T = (int)length; p->R = (int)(batch * length);
   p->E = s->modal_dim * s->n_modals; p->md3 = 3 * s->modal_dim;
+  p->tf32 = s->precision == 1 ? 1 : 0;
   int dev = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&p->num_sms, cudaDevAttrMultiProcessorCount, dev);
@@ -1166,7 +1454,7 @@ extern "C" int cer_head_train_forward(cer_head_train* p, const float* const* fea
       wn_fwd_kernel<<<b.c_out, 256, 0, st>>>(b.conv1.g, b.conv1.v, bb.c1.w_eff, bb.c1.inv_norm, b.c_out, b.c_in, k);
       wn_fwd_kernel<<<b.c_out, 256, 0, st>>>(b.conv2.g, b.conv2.v, bb.c2.w_eff, bb.c2.inv_norm, b.c_out, b.c_out, k);
       CER_CUDA(cudaGetLastError());
-      RowGemm g{};
+      RowGemm g{}; g.tf32 = p->tf32;
       g.R = R; g.T = T; g.taps = k; g.shift0 = -(k - 1) * b.dilation; g.shift_step = b.dilation;
       // conv1: h1d = drop(LReLU(conv1(x) + b1))
       g.A = x; g.lda = b.c_in; g.K = b.c_in; g.B = bb.c1.w_eff; g.b_tap_stride = (long long)b.c_out * b.c_in;
@@ -1176,7 +1464,7 @@ extern "C" int cer_head_train_forward(cer_head_train* p, const float* const* fea
       // residual branch
       const float* res = x; int ld_res = b.c_in;
       if (b.wd) {
-        RowGemm d{};
+        RowGemm d{}; d.tf32 = p->tf32;
         d.R = R; d.T = T; d.taps = 1; d.A = x; d.lda = b.c_in; d.K = b.c_in; d.B = b.wd; d.C = bb.res; d.ldc = b.c_out;
         d.N = b.c_out; d.bias = b.bd; d.epi = EPI_LINEAR;
         RC(launch_row_gemm(d, false, st));
@@ -1194,7 +1482,7 @@ extern "C" int cer_head_train_forward(cer_head_train* p, const float* const* fea
     bn_train_fwd_kernel<<<(C + 31) / 32, dim3(32, 8), 0, st>>>(x, C, R, C, M.bn_w, M.bn_b, mb.z, mb.ld_z, mb.bn_mean,
                                                                 mb.bn_invstd, M.bn_mean, M.bn_var, (float)s.bn_momentum);
     CER_CUDA(cudaGetLastError());
-    RowGemm q{};
+    RowGemm q{}; q.tf32 = p->tf32;
     q.R = R; q.T = T; q.taps = 1; q.A = mb.z; q.lda = mb.ld_z; q.K = C; q.B = M.wqkv; q.C = mb.qkv; q.ldc = p->md3;
     q.N = p->md3; q.bias = M.bqkv; q.epi = EPI_LINEAR;
     RC(launch_row_gemm(q, false, st));
@@ -1208,14 +1496,14 @@ extern "C" int cer_head_train_forward(cer_head_train* p, const float* const* fea
   attn_fwd_kernel<<<(R * a.H + 127) / 128, 128, 0, st>>>(a);
   CER_CUDA(cudaGetLastError());
   const int E = p->E, c0 = p->ld_cat - E;
-  RowGemm o{};
+  RowGemm o{}; o.tf32 = p->tf32;
   o.R = R; o.T = T; o.taps = 1; o.A = p->vals; o.lda = E; o.K = E; o.B = s.wo; o.C = p->o; o.ldc = E; o.N = E; o.bias = s.bo;
   o.epi = EPI_LINEAR;
   RC(launch_row_gemm(o, false, st));
   ln_drop_fwd_kernel<<<(R + 7) / 8, 256, 0, st>>>(p->o, R, E, s.ln_g, s.ln_b, p->cat + c0, p->ld_cat, p->ln_mean, p->ln_rstd,
                                                   make_drop(s.p_fusion, seed, 4096));
   CER_CUDA(cudaGetLastError());
-  RowGemm r{};
+  RowGemm r{}; r.tf32 = p->tf32;
   r.R = R; r.T = T; r.taps = 1; r.A = p->cat; r.lda = p->ld_cat; r.K = p->ld_cat; r.B = s.wr; r.C = logits; r.ldc = s.n_out;
   r.N = s.n_out; r.bias = s.br; r.epi = EPI_LINEAR;
   RC(launch_row_gemm(r, false, st));
@@ -1232,10 +1520,10 @@ extern "C" int cer_head_train_backward(cer_head_train* p, const float* const* fe
   CER_CUDA(cudaMemsetAsync(p->scratch_zero, 0, p->scratch_zero_bytes, st));
 
   // classifier: logits = cat Wr^T + br
-  { WGrad w{}; w.G = dlogits; w.ldg = s.n_out; w.A = p->cat; w.lda = p->ld_cat; w.dW = s.dwr; w.R = R; w.T = T; w.N = s.n_out;
+  { WGrad w{}; w.tf32 = p->tf32; w.G = dlogits; w.ldg = s.n_out; w.A = p->cat; w.lda = p->ld_cat; w.dW = s.dwr; w.R = R; w.T = T; w.N = s.n_out;
     w.K = p->ld_cat; w.taps = 1; RC(launch_wgrad(w, sms, st)); }
   RC(launch_colsum(dlogits, s.n_out, R, s.n_out, s.dbr, st));
-  { RowGemm g{}; g.R = R; g.T = T; g.taps = 1; g.A = dlogits; g.lda = s.n_out; g.K = s.n_out; g.B = s.wr; g.C = p->gcat;
+  { RowGemm g{}; g.tf32 = p->tf32; g.R = R; g.T = T; g.taps = 1; g.A = dlogits; g.lda = s.n_out; g.K = s.n_out; g.B = s.wr; g.C = p->gcat;
     g.ldc = p->ld_cat; g.N = p->ld_cat; g.epi = EPI_LINEAR; RC(launch_row_gemm(g, true, st)); }
   // LayerNorm + dropout
   { const int rpb = std::max(8, (R + 4 * sms - 1) / (4 * sms));
@@ -1243,10 +1531,10 @@ extern "C" int cer_head_train_backward(cer_head_train* p, const float* const* fe
                                                              p->go, s.dln_g, s.dln_b, make_drop(s.p_fusion, seed, 4096), rpb);
     CER_CUDA(cudaGetLastError()); }
   // o_proj
-  { WGrad w{}; w.G = p->go; w.ldg = E; w.A = p->vals; w.lda = E; w.dW = s.dwo; w.R = R; w.T = T; w.N = E; w.K = E; w.taps = 1;
+  { WGrad w{}; w.tf32 = p->tf32; w.G = p->go; w.ldg = E; w.A = p->vals; w.lda = E; w.dW = s.dwo; w.R = R; w.T = T; w.N = E; w.K = E; w.taps = 1;
     RC(launch_wgrad(w, sms, st)); }
   RC(launch_colsum(p->go, E, R, E, s.dbo, st));
-  { RowGemm g{}; g.R = R; g.T = T; g.taps = 1; g.A = p->go; g.lda = E; g.K = E; g.B = s.wo; g.C = p->gvals; g.ldc = E; g.N = E;
+  { RowGemm g{}; g.tf32 = p->tf32; g.R = R; g.T = T; g.taps = 1; g.A = p->go; g.lda = E; g.K = E; g.B = s.wo; g.C = p->gvals; g.ldc = E; g.N = E;
     g.epi = EPI_LINEAR; RC(launch_row_gemm(g, true, st)); }
   // attention
   { AttnArgs a{};
@@ -1264,11 +1552,11 @@ extern "C" int cer_head_train_backward(cer_head_train* p, const float* const* fe
     st = m == 0 ? main_st : p->side[m];
     if (m > 0) CER_CUDA(cudaStreamWaitEvent(st, p->ev_fork, 0));
     // qkv projection
-    { WGrad w{}; w.G = mb.gqkv; w.ldg = p->md3; w.A = mb.z; w.lda = mb.ld_z; w.dW = M.dwqkv; w.R = R; w.T = T; w.N = p->md3;
+    { WGrad w{}; w.tf32 = p->tf32; w.G = mb.gqkv; w.ldg = p->md3; w.A = mb.z; w.lda = mb.ld_z; w.dW = M.dwqkv; w.R = R; w.T = T; w.N = p->md3;
       w.K = C; w.taps = 1; RC(launch_wgrad(w, sms, st)); }
     RC(launch_colsum(mb.gqkv, p->md3, R, p->md3, M.dbqkv, st));
     float* gz = mb.ga;        // [R][C]
-    { RowGemm g{}; g.R = R; g.T = T; g.taps = 1; g.A = mb.gqkv; g.lda = p->md3; g.K = p->md3; g.B = M.wqkv; g.C = gz; g.ldc = C;
+    { RowGemm g{}; g.tf32 = p->tf32; g.R = R; g.T = T; g.taps = 1; g.A = mb.gqkv; g.lda = p->md3; g.K = p->md3; g.B = M.wqkv; g.C = gz; g.ldc = C;
       g.N = C; g.epi = EPI_LINEAR;
       if (m == 0) { g.addend = p->gcat; g.ld_add = p->ld_cat; }        // the leader also feeds the classifier directly
       RC(launch_row_gemm(g, true, st)); }
@@ -1290,21 +1578,21 @@ extern "C" int cer_head_train_backward(cer_head_train* p, const float* const* fe
       CER_CUDA(cudaGetLastError());
       // conv2: bias, weight, input gradients
       RC(launch_colsum(ga2, b.c_out, R, b.c_out, b.conv2.dbias, st));
-      { WGrad w{}; w.G = ga2; w.ldg = b.c_out; w.A = bb.h1d; w.lda = b.c_out; w.dW = bb.c2.dw_eff;
+      { WGrad w{}; w.tf32 = p->tf32; w.G = ga2; w.ldg = b.c_out; w.A = bb.h1d; w.lda = b.c_out; w.dW = bb.c2.dw_eff;
         w.w_tap_stride = (long long)b.c_out * b.c_out; w.R = R; w.T = T; w.N = b.c_out; w.K = b.c_out; w.taps = k;
         w.shift0 = -(k - 1) * b.dilation; w.shift_step = b.dilation; RC(launch_wgrad(w, sms, st)); }
       wn_bwd_kernel<<<b.c_out, 256, 0, st>>>(b.conv2.g, b.conv2.v, bb.c2.dw_eff, bb.c2.inv_norm, b.conv2.dg, b.conv2.dv,
                                              b.c_out, b.c_out, k);
       CER_CUDA(cudaGetLastError());
       float* ga1 = gy;         // gy is dead once gpre/ga2 exist
-      { RowGemm g{}; g.R = R; g.T = T; g.taps = k; g.shift0 = (k - 1) * b.dilation; g.shift_step = -b.dilation;
+      { RowGemm g{}; g.tf32 = p->tf32; g.R = R; g.T = T; g.taps = k; g.shift0 = (k - 1) * b.dilation; g.shift_step = -b.dilation;
         g.A = ga2; g.lda = b.c_out; g.K = b.c_out; g.B = bb.c2.w_eff; g.b_tap_stride = (long long)b.c_out * b.c_out;
         g.C = ga1; g.ldc = b.c_out; g.N = b.c_out; g.epi = EPI_DGRAD_ACT; g.aux = bb.h1d; g.ld_aux = b.c_out;
         g.drop = make_drop(s.p_tcn, seed, m * 16 + i * 2 + 0);
         RC(launch_row_gemm(g, true, st)); }
       // conv1: bias, weight gradients
       RC(launch_colsum(ga1, b.c_out, R, b.c_out, b.conv1.dbias, st));
-      { WGrad w{}; w.G = ga1; w.ldg = b.c_out; w.A = x; w.lda = b.c_in; w.dW = bb.c1.dw_eff;
+      { WGrad w{}; w.tf32 = p->tf32; w.G = ga1; w.ldg = b.c_out; w.A = x; w.lda = b.c_in; w.dW = bb.c1.dw_eff;
         w.w_tap_stride = (long long)b.c_out * b.c_in; w.R = R; w.T = T; w.N = b.c_out; w.K = b.c_in; w.taps = k;
         w.shift0 = -(k - 1) * b.dilation; w.shift_step = b.dilation; RC(launch_wgrad(w, sms, st)); }
       wn_bwd_kernel<<<b.c_out, 256, 0, st>>>(b.conv1.g, b.conv1.v, bb.c1.dw_eff, bb.c1.inv_norm, b.conv1.dg, b.conv1.dv,
@@ -1313,19 +1601,19 @@ extern "C" int cer_head_train_backward(cer_head_train* p, const float* const* fe
       // downsample parameters
       if (b.wd) {
         RC(launch_colsum(gpre, b.c_out, R, b.c_out, b.dbd, st));
-        WGrad w{}; w.G = gpre; w.ldg = b.c_out; w.A = x; w.lda = b.c_in; w.dW = b.dwd; w.R = R; w.T = T; w.N = b.c_out;
+        WGrad w{}; w.tf32 = p->tf32; w.G = gpre; w.ldg = b.c_out; w.A = x; w.lda = b.c_in; w.dW = b.dwd; w.R = R; w.T = T; w.N = b.c_out;
         w.K = b.c_in; w.taps = 1; RC(launch_wgrad(w, sms, st));
       }
       if (i == 0) break;       // the input features need no gradient
       // gx = dgrad(conv1)(ga1) + residual-branch gradient
       float* gx = spare;
-      { RowGemm g{}; g.R = R; g.T = T; g.taps = k; g.shift0 = (k - 1) * b.dilation; g.shift_step = -b.dilation;
+      { RowGemm g{}; g.tf32 = p->tf32; g.R = R; g.T = T; g.taps = k; g.shift0 = (k - 1) * b.dilation; g.shift_step = -b.dilation;
         g.A = ga1; g.lda = b.c_out; g.K = b.c_out; g.B = bb.c1.w_eff; g.b_tap_stride = (long long)b.c_out * b.c_in;
         g.C = gx; g.ldc = b.c_in; g.N = b.c_in; g.epi = EPI_LINEAR;
         if (!b.wd) { g.addend = gpre; g.ld_add = b.c_out; }
         RC(launch_row_gemm(g, true, st)); }
       if (b.wd) {
-        RowGemm g{}; g.R = R; g.T = T; g.taps = 1; g.A = gpre; g.lda = b.c_out; g.K = b.c_out; g.B = b.wd; g.C = gx; g.ldc = b.c_in;
+        RowGemm g{}; g.tf32 = p->tf32; g.R = R; g.T = T; g.taps = 1; g.A = gpre; g.lda = b.c_out; g.K = b.c_out; g.B = b.wd; g.C = gx; g.ldc = b.c_in;
         g.N = b.c_in; g.epi = EPI_LINEAR; g.accumulate = 1;
         RC(launch_row_gemm(g, true, st));
       }

@@ -52,8 +52,15 @@ def all_reduce_flat(flat: torch.Tensor, group=None) -> float:
 
 class HeadTrainer:
     def __init__(self, model, batch: int, length: Optional[int] = None, optimizer: Optional[dict] = None,
-                 seed: int = 0, process_group=None):
+                 seed: int = 0, process_group=None, precision: str = "tf32"):
+        """precision="tf32" (default): the GEMMs of forward, dgrad and wgrad run on TF32 tensor cores with
+        fp32 accumulation -- what the reference's own GPU run does for its convolutions
+        (torch.backends.cudnn.allow_tf32 defaults to True); "fp32": exact fp32 FMAs on CUDA cores
+        (gradients within 2e-5 of CPU autograd, ~2.5x slower)."""
         _capi.require_gpu()
+        if precision not in ("tf32", "fp32"):
+            raise ValueError(precision)
+        self.precision = precision
         self.model = model
         self.batch = int(batch)
         self.length = int(length or model.example_length)
@@ -110,6 +117,7 @@ class HeadTrainer:
         s.kernel_size = m.kernel_size
         s.modal_dim, s.num_heads, s.n_out = m.modal_dim, m.num_heads, m.output_dim
         first = m.temporal[self.mods[0]].network[0]
+        s.precision = 1 if self.precision == "tf32" else 0
         s.p_tcn = float(first.dropout1.p)
         s.p_fusion = float(m.fusion.layers.dropout.p)
         s.bn_momentum = float(m.bn[self.mods[0]].momentum)
@@ -298,7 +306,8 @@ def forward_with_grad(model, feats: Dict[str, torch.Tensor]) -> torch.Tensor:
     B, T = any_f.shape[0], any_f.shape[-2]
     tr = model.__dict__.get("_trainer")
     if tr is None:
-        tr = HeadTrainer(model, B, T)                 # other (B, T) shapes add a plan to the same trainer
+        # other (B, T) shapes add a plan to the same trainer; model.train_precision ("tf32" | "fp32") picks the GEMMs
+        tr = HeadTrainer(model, B, T, precision=getattr(model, "train_precision", "tf32"))
         model.__dict__["_trainer"] = tr
     params = [p for _, p in head_parameters(model)]
     return _HeadFunction.apply(tr, feats, *params)

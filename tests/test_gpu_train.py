@@ -24,7 +24,7 @@ def _dev():
     return torch.device("cuda:0")
 
 
-def _lfan(mods, dev, seed=0, length=300, p_drop=None):
+def _lfan(mods, dev, seed=0, length=300, p_drop=None, precision="fp32"):
     from feature_vs_text_compound_emotion_b200.models.model import LFAN
     m = LFAN(backbone_settings=BS, output_dim=7, task="CLASSIFICATION", modality=mods, kernel_size=5,
              example_length=length, tcn_channel=synthetic.TCN_CHANNELS, modal_dim=32, num_heads=2, root_dir="",
@@ -32,6 +32,7 @@ def _lfan(mods, dev, seed=0, length=300, p_drop=None):
     m.init()
     m.load_state_dict(synthetic.lfan_state_dict(seed, mods), strict=True)
     m = m.to(dev).train()
+    m.train_precision = precision            # what LFAN.forward's training branch hands to HeadTrainer
     if p_drop is not None:
         for mod in m.modules():
             if isinstance(mod, torch.nn.Dropout):
@@ -90,7 +91,7 @@ def test_two_sgd_steps_vs_reference_golden(golden_dir):
     g = torch.load(os.path.join(golden_dir, "train_b2.pt"))
     mods = g["modalities"]
     m = _lfan(mods, dev, g["weights_seed"], p_drop=0.0)
-    tr = HeadTrainer(m, 2, 300, optimizer=g["opt"])
+    tr = HeadTrainer(m, 2, 300, optimizer=g["opt"], precision="fp32")
     X = {k: v.to(dev) for k, v in synthetic.feature_windows(2, 300, seed=g["x_seed"], modalities=mods).items()}
     labels = torch.randint(0, 7, (2, 300, 1), generator=torch.Generator().manual_seed(g["label_seed"])).float().to(dev)
     for step in g["steps"]:
@@ -116,7 +117,7 @@ def test_dropout_forward_backward_vs_oracle():
     from feature_vs_text_compound_emotion_b200.training import HeadTrainer
     dev = _dev()
     m = _lfan(MODS, dev, seed=3)
-    tr = HeadTrainer(m, 2, 300)
+    tr = HeadTrainer(m, 2, 300, precision="fp32")
     sd = synthetic.lfan_state_dict(3, MODS)
     X = synthetic.feature_windows(2, 300, seed=21, modalities=MODS)
     labels = torch.randint(0, 7, (2, 300, 1), generator=torch.Generator().manual_seed(22)).float()
@@ -146,7 +147,7 @@ def test_optimizers_vs_oracle(name, cfg):
     dev = _dev()
     mods = ["vggish", "bert"]          # a two-modality head: E = 64, leader width 32
     m = _lfan(mods, dev, seed=1, length=120, p_drop=0.0)
-    tr = HeadTrainer(m, 3, 120, optimizer=cfg)
+    tr = HeadTrainer(m, 3, 120, optimizer=cfg, precision="fp32")
     sd = synthetic.lfan_state_dict(1, mods)
     X = synthetic.feature_windows(3, 120, seed=31, modalities=mods)
     labels = torch.randint(0, 7, (3, 120, 1), generator=torch.Generator().manual_seed(32)).float()
@@ -239,6 +240,7 @@ def test_training_from_pixels_with_frozen_backbone_and_odd_widths():
     sd = synthetic.lfan_state_dict(4, mods)
     m.load_state_dict(sd, strict=True)
     m = m.to(dev).train()
+    m.train_precision = "fp32"
     for mod in m.modules():
         if isinstance(mod, torch.nn.Dropout):
             mod.p = 0.0
@@ -264,7 +266,7 @@ def test_training_from_pixels_with_frozen_backbone_and_odd_widths():
 
     mods2 = ["mfcc", "egemaps"]
     m2 = _lfan(mods2, dev, seed=6, length=100, p_drop=0.0)
-    tr = HeadTrainer(m2, 2, 100)
+    tr = HeadTrainer(m2, 2, 100, precision="fp32")
     sd2 = synthetic.lfan_state_dict(6, mods2)
     X = synthetic.feature_windows(2, 100, seed=54, modalities=mods2)
     y = torch.randint(0, 7, (2, 100, 1), generator=torch.Generator().manual_seed(55)).float()
@@ -361,3 +363,80 @@ def test_ce_loss_ignore_index_and_out_of_range_labels():
     _capi.check(_capi.lib().cer_ce_loss(logits.to(dev).data_ptr(), none.to(dev).data_ptr(), 777, 7, loss2.data_ptr(), None,
                                         _capi.current_stream_ptr()))
     assert torch.isnan(loss2).item()
+
+
+# ----------------------------------------------------------------------------------------------
+# TF32 tensor-core mode (HeadTrainer's default).  Tolerances: products carry 10 mantissa bits, sums are
+# fp32; measured on B200 (CER_GRAD_STATS): see _tf32_close.
+# ----------------------------------------------------------------------------------------------
+_TF32_STATS = []
+
+
+def _tf32_close(mine, ref, norm=None, what=""):
+    """TF32 GEMMs vs fp32 CPU autograd: relative L2 error of a gradient tensor <= 1e-2 (products are
+    rounded to 10 mantissa bits: ~5e-4 per operand, averaged over the reduction)."""
+    mine, ref = mine.double().flatten(), ref.double().flatten()
+    norm = float(ref.norm()) if norm is None else norm
+    rel = float((mine - ref).norm()) / max(norm, 1e-30)
+    _TF32_STATS.append(rel)
+    assert rel <= 1e-2, (what, rel)
+    return rel
+
+
+def test_tf32_two_sgd_steps_vs_reference_golden(golden_dir):
+    """The default (TF32 tensor-core) training step against the reference's two SGD steps: loss within 2e-3,
+    every gradient within 1e-2 in relative L2, BatchNorm statistics within 1e-3, parameters after the update
+    within lr * 1e-2 * |g| of the reference's."""
+    from feature_vs_text_compound_emotion_b200.training import HeadTrainer
+    dev = _dev()
+    g = torch.load(os.path.join(golden_dir, "train_b2.pt"))
+    mods = g["modalities"]
+    m = _lfan(mods, dev, g["weights_seed"], p_drop=0.0, precision="tf32")
+    tr = HeadTrainer(m, 2, 300, optimizer=g["opt"])
+    assert tr.precision == "tf32"
+    X = {k: v.to(dev) for k, v in synthetic.feature_windows(2, 300, seed=g["x_seed"], modalities=mods).items()}
+    labels = torch.randint(0, 7, (2, 300, 1), generator=torch.Generator().manual_seed(g["label_seed"])).float().to(dev)
+    worst = 0.0
+    for step in g["steps"]:
+        loss = tr.step(X, labels)
+        assert abs(loss.item() - step["loss"]) < 2e-3
+        for k, gn in step["grad_norm"].items():
+            mine = tr.grad(k).cpu()
+            ref = step["grad_small"][k] if k in step["grad_small"] else step["grad_sample"][k]
+            got = mine if k in step["grad_small"] else mine.flatten()[::997]
+            if k in step["grad_small"]:
+                worst = max(worst, _tf32_close(got, ref, norm=gn, what=k))
+            else:                                # a 1/997 sample of a big tensor: compare against the sample's own norm
+                worst = max(worst, _tf32_close(got, ref, what=k))
+            assert abs(float(mine.double().norm()) - gn) <= 1e-2 * gn + 1e-7, k
+        sd = m.state_dict()
+        for k, v in step["bn"].items():
+            assert (sd[k].cpu().float() - v.float()).abs().max().item() < 1e-3, k
+    print("tf32 worst relative L2 gradient error", worst)
+
+
+def test_tf32_dropout_forward_backward_vs_oracle_and_fp32_mode():
+    """TF32 mode with dropout ON against the oracle (same mask hash), and against this repo's exact fp32
+    mode on the same inputs: logits within 5e-3, loss within 2e-3, gradients within 1e-2 (relative L2)."""
+    from feature_vs_text_compound_emotion_b200.training import HeadTrainer
+    dev = _dev()
+    sd = synthetic.lfan_state_dict(3, MODS)
+    X = synthetic.feature_windows(2, 300, seed=21, modalities=MODS)
+    labels = torch.randint(0, 7, (2, 300, 1), generator=torch.Generator().manual_seed(22)).float()
+    seed = 0xC0FFEE
+    outs = {}
+    for prec in ("tf32", "fp32"):
+        m = _lfan(MODS, dev, seed=3, precision=prec)
+        tr = HeadTrainer(m, 2, 300, precision=prec)
+        logits = tr.forward({k: v.to(dev) for k, v in X.items()}, seed=seed)
+        loss, dl = tr.cross_entropy(logits, labels.to(dev))
+        tr.backward(dl)
+        outs[prec] = (logits.cpu(), loss.item(), {k: tr.grad(k).cpu().clone() for k in tr.names})
+    ref_loss, grads, _, _ = O.train_step(sd, X, labels, MODS, {"name": "sgd", "lr": 0.0}, None, seed=seed)
+    lt, losst, gt = outs["tf32"]
+    lf, lossf, gf = outs["fp32"]
+    assert (lt - lf).abs().max().item() < 5e-3 and not torch.equal(lt, lf)
+    assert abs(losst - float(ref_loss)) < 2e-3 and abs(losst - lossf) < 2e-3
+    for k, g in grads.items():
+        _tf32_close(gt[k], g, what=k)
+        _tf32_close(gt[k], gf[k], what=k)
