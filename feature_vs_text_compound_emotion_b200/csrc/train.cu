@@ -1313,7 +1313,10 @@ Drop make_drop(double p, uint32_t seed, uint32_t stream) {
 struct cer_head_train {
   cer_head_train_spec s;
   int B, T, R, E, md3, num_sms;
-  int tf32;                         // spec.precision: 1 = TF32 tensor-core GEMMs, 0 = exact fp32
+  int tf32;                         // spec.precision: 1 = TF32 tensor-core GEMMs for the TCN convolutions (forward, dgrad, wgrad:
+                                    // 99 % of the step's FLOPs), 0 = exact fp32.  The Linear layers of the fusion head
+                                    // (qkv_proj, o_proj, regressor) stay fp32 in both modes, like torch's defaults
+                                    // (cudnn.allow_tf32 = True, cuda.matmul.allow_tf32 = False)
   std::vector<ModalBuf> mod;
   float *vals, *o, *ln_mean, *ln_rstd, *cat, *gcat, *go, *gvals;
   cudaStream_t side[CER_MAX_MODALS];      // modality m > 0 runs on side[m]; modality 0 on the caller's stream
@@ -1482,7 +1485,7 @@ extern "C" int cer_head_train_forward(cer_head_train* p, const float* const* fea
     bn_train_fwd_kernel<<<(C + 31) / 32, dim3(32, 8), 0, st>>>(x, C, R, C, M.bn_w, M.bn_b, mb.z, mb.ld_z, mb.bn_mean,
                                                                 mb.bn_invstd, M.bn_mean, M.bn_var, (float)s.bn_momentum);
     CER_CUDA(cudaGetLastError());
-    RowGemm q{}; q.tf32 = p->tf32;
+    RowGemm q{};
     q.R = R; q.T = T; q.taps = 1; q.A = mb.z; q.lda = mb.ld_z; q.K = C; q.B = M.wqkv; q.C = mb.qkv; q.ldc = p->md3;
     q.N = p->md3; q.bias = M.bqkv; q.epi = EPI_LINEAR;
     RC(launch_row_gemm(q, false, st));
@@ -1496,14 +1499,14 @@ extern "C" int cer_head_train_forward(cer_head_train* p, const float* const* fea
   attn_fwd_kernel<<<(R * a.H + 127) / 128, 128, 0, st>>>(a);
   CER_CUDA(cudaGetLastError());
   const int E = p->E, c0 = p->ld_cat - E;
-  RowGemm o{}; o.tf32 = p->tf32;
+  RowGemm o{};
   o.R = R; o.T = T; o.taps = 1; o.A = p->vals; o.lda = E; o.K = E; o.B = s.wo; o.C = p->o; o.ldc = E; o.N = E; o.bias = s.bo;
   o.epi = EPI_LINEAR;
   RC(launch_row_gemm(o, false, st));
   ln_drop_fwd_kernel<<<(R + 7) / 8, 256, 0, st>>>(p->o, R, E, s.ln_g, s.ln_b, p->cat + c0, p->ld_cat, p->ln_mean, p->ln_rstd,
                                                   make_drop(s.p_fusion, seed, 4096));
   CER_CUDA(cudaGetLastError());
-  RowGemm r{}; r.tf32 = p->tf32;
+  RowGemm r{};
   r.R = R; r.T = T; r.taps = 1; r.A = p->cat; r.lda = p->ld_cat; r.K = p->ld_cat; r.B = s.wr; r.C = logits; r.ldc = s.n_out;
   r.N = s.n_out; r.bias = s.br; r.epi = EPI_LINEAR;
   RC(launch_row_gemm(r, false, st));
@@ -1520,10 +1523,10 @@ extern "C" int cer_head_train_backward(cer_head_train* p, const float* const* fe
   CER_CUDA(cudaMemsetAsync(p->scratch_zero, 0, p->scratch_zero_bytes, st));
 
   // classifier: logits = cat Wr^T + br
-  { WGrad w{}; w.tf32 = p->tf32; w.G = dlogits; w.ldg = s.n_out; w.A = p->cat; w.lda = p->ld_cat; w.dW = s.dwr; w.R = R; w.T = T; w.N = s.n_out;
+  { WGrad w{}; w.G = dlogits; w.ldg = s.n_out; w.A = p->cat; w.lda = p->ld_cat; w.dW = s.dwr; w.R = R; w.T = T; w.N = s.n_out;
     w.K = p->ld_cat; w.taps = 1; RC(launch_wgrad(w, sms, st)); }
   RC(launch_colsum(dlogits, s.n_out, R, s.n_out, s.dbr, st));
-  { RowGemm g{}; g.tf32 = p->tf32; g.R = R; g.T = T; g.taps = 1; g.A = dlogits; g.lda = s.n_out; g.K = s.n_out; g.B = s.wr; g.C = p->gcat;
+  { RowGemm g{}; g.R = R; g.T = T; g.taps = 1; g.A = dlogits; g.lda = s.n_out; g.K = s.n_out; g.B = s.wr; g.C = p->gcat;
     g.ldc = p->ld_cat; g.N = p->ld_cat; g.epi = EPI_LINEAR; RC(launch_row_gemm(g, true, st)); }
   // LayerNorm + dropout
   { const int rpb = std::max(8, (R + 4 * sms - 1) / (4 * sms));
@@ -1531,10 +1534,10 @@ extern "C" int cer_head_train_backward(cer_head_train* p, const float* const* fe
                                                              p->go, s.dln_g, s.dln_b, make_drop(s.p_fusion, seed, 4096), rpb);
     CER_CUDA(cudaGetLastError()); }
   // o_proj
-  { WGrad w{}; w.tf32 = p->tf32; w.G = p->go; w.ldg = E; w.A = p->vals; w.lda = E; w.dW = s.dwo; w.R = R; w.T = T; w.N = E; w.K = E; w.taps = 1;
+  { WGrad w{}; w.G = p->go; w.ldg = E; w.A = p->vals; w.lda = E; w.dW = s.dwo; w.R = R; w.T = T; w.N = E; w.K = E; w.taps = 1;
     RC(launch_wgrad(w, sms, st)); }
   RC(launch_colsum(p->go, E, R, E, s.dbo, st));
-  { RowGemm g{}; g.tf32 = p->tf32; g.R = R; g.T = T; g.taps = 1; g.A = p->go; g.lda = E; g.K = E; g.B = s.wo; g.C = p->gvals; g.ldc = E; g.N = E;
+  { RowGemm g{}; g.R = R; g.T = T; g.taps = 1; g.A = p->go; g.lda = E; g.K = E; g.B = s.wo; g.C = p->gvals; g.ldc = E; g.N = E;
     g.epi = EPI_LINEAR; RC(launch_row_gemm(g, true, st)); }
   // attention
   { AttnArgs a{};
@@ -1552,11 +1555,11 @@ extern "C" int cer_head_train_backward(cer_head_train* p, const float* const* fe
     st = m == 0 ? main_st : p->side[m];
     if (m > 0) CER_CUDA(cudaStreamWaitEvent(st, p->ev_fork, 0));
     // qkv projection
-    { WGrad w{}; w.tf32 = p->tf32; w.G = mb.gqkv; w.ldg = p->md3; w.A = mb.z; w.lda = mb.ld_z; w.dW = M.dwqkv; w.R = R; w.T = T; w.N = p->md3;
+    { WGrad w{}; w.G = mb.gqkv; w.ldg = p->md3; w.A = mb.z; w.lda = mb.ld_z; w.dW = M.dwqkv; w.R = R; w.T = T; w.N = p->md3;
       w.K = C; w.taps = 1; RC(launch_wgrad(w, sms, st)); }
     RC(launch_colsum(mb.gqkv, p->md3, R, p->md3, M.dbqkv, st));
     float* gz = mb.ga;        // [R][C]
-    { RowGemm g{}; g.tf32 = p->tf32; g.R = R; g.T = T; g.taps = 1; g.A = mb.gqkv; g.lda = p->md3; g.K = p->md3; g.B = M.wqkv; g.C = gz; g.ldc = C;
+    { RowGemm g{}; g.R = R; g.T = T; g.taps = 1; g.A = mb.gqkv; g.lda = p->md3; g.K = p->md3; g.B = M.wqkv; g.C = gz; g.ldc = C;
       g.N = C; g.epi = EPI_LINEAR;
       if (m == 0) { g.addend = p->gcat; g.ld_add = p->ld_cat; }        // the leader also feeds the classifier directly
       RC(launch_row_gemm(g, true, st)); }

@@ -271,7 +271,9 @@ typedef struct cer_train_modal {
 
 typedef struct cer_head_train_spec {
   int32_t n_modals, kernel_size, modal_dim, num_heads, n_out;
-  int32_t precision;            /* 0: exact fp32 GEMMs (CUDA cores); 1: TF32 tensor-core GEMMs, fp32 accumulate */
+  int32_t precision;            /* 0: exact fp32 GEMMs (CUDA cores); 1: the TCN convolutions (forward, dgrad, wgrad) on TF32
+                                 * tensor cores with fp32 accumulate -- torch's own GPU default for convolutions; the fusion
+                                 * head's Linear layers stay fp32 */
   double p_tcn, p_fusion, bn_momentum;   /* 0.1, 0.1, 0.1 in the reference (model.py:471,482)        */
   cer_train_modal modal[CER_MAX_MODALS]; /* modality 0 is the leader                                 */
   const float *wo, *bo, *ln_g, *ln_b, *wr, *br;

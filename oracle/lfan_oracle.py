@@ -307,9 +307,42 @@ def dropout_stream(modal_index: int, block: int, site: int) -> int:
 FUSION_STREAM = 4096
 
 
+def tf32_round(x: Tensor) -> Tensor:
+    """Round fp32 to TF32 (10 mantissa bits) to nearest, ties away from zero: PTX cvt.rna.tf32.f32."""
+    bits = x.contiguous().view(torch.int32)
+    return ((bits + 0x1000) & ~0x1FFF).view(torch.float32)
+
+
+class _Tf32Conv1d(torch.autograd.Function):
+    """conv1d whose three GEMMs -- forward, gradient w.r.t. the input, gradient w.r.t. the weight -- see
+    TF32-rounded operands and accumulate in fp32: the arithmetic of the training kernels in
+    precision="tf32" (and of cuDNN with torch.backends.cudnn.allow_tf32, the reference's GPU default)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, padding, dilation):
+        ctx.save_for_backward(x, w)
+        ctx.cfg = (padding, dilation)
+        return F.conv1d(tf32_round(x), tf32_round(w), b, stride=1, padding=padding, dilation=dilation)
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, w = ctx.saved_tensors
+        padding, dilation = ctx.cfg
+        g = tf32_round(gy)
+        gx = torch.nn.grad.conv1d_input(x.shape, tf32_round(w), g, stride=1, padding=padding, dilation=dilation)
+        gw = torch.nn.grad.conv1d_weight(tf32_round(x), w.shape, g, stride=1, padding=padding, dilation=dilation)
+        return gx, gw, gy.sum(dim=(0, 2)), None, None
+
+
+def _conv1d(x, w, b, padding, dilation, tf32):
+    if tf32:
+        return _Tf32Conv1d.apply(x, w, b, padding, dilation)
+    return F.conv1d(x, w, b, stride=1, padding=padding, dilation=dilation)
+
+
 def head_forward_train(P: SD, buffers: SD, feats: Dict[str, Tensor], modalities: Sequence[str],
                        modal_dim: int = 32, num_heads: int = 2, seed=None,
-                       p_tcn: float = TCN_DROPOUT, p_fusion: float = FUSION_DROPOUT) -> Tensor:
+                       p_tcn: float = TCN_DROPOUT, p_fusion: float = FUSION_DROPOUT, tf32: bool = False) -> Tensor:
     """LFAN.forward after the backbones in TRAINING mode (model.py:511-526 under model.train()):
     Dropout active after both LeakyReLUs of every TemporalBlock (temporal_convolutional_model.py:
     28,34) and on the attention output (transformer.py:194); BatchNorm1d uses batch statistics and
@@ -326,12 +359,18 @@ def head_forward_train(P: SD, buffers: SD, feats: Dict[str, Tensor], modalities:
             w1 = weight_norm_effective(P[p + ".conv1.weight_g"], P[p + ".conv1.weight_v"])
             w2 = weight_norm_effective(P[p + ".conv2.weight_g"], P[p + ".conv2.weight_v"])
             xc = x.transpose(1, 2)
-            h = F.leaky_relu(causal_dilated_conv(xc, w1, P[p + ".conv1.bias"], d), LEAKY_SLOPE).transpose(1, 2)
+            pad = (w1.shape[-1] - 1) * d
+
+            def cconv(inp, w, bias):           # causal_dilated_conv, optionally with TF32-rounded GEMM operands
+                y = _conv1d(inp, w, bias, pad, d, tf32)
+                return y[:, :, :-pad] if pad > 0 else y
+
+            h = F.leaky_relu(cconv(xc, w1, P[p + ".conv1.bias"]), LEAKY_SLOPE).transpose(1, 2)
             h = _drop(h, p_tcn, seed, dropout_stream(mi, i, 0))
-            h = F.leaky_relu(causal_dilated_conv(h.transpose(1, 2), w2, P[p + ".conv2.bias"], d), LEAKY_SLOPE).transpose(1, 2)
+            h = F.leaky_relu(cconv(h.transpose(1, 2), w2, P[p + ".conv2.bias"]), LEAKY_SLOPE).transpose(1, 2)
             h = _drop(h, p_tcn, seed, dropout_stream(mi, i, 1))
             if (p + ".downsample.weight") in P:
-                res = F.conv1d(xc, P[p + ".downsample.weight"], P[p + ".downsample.bias"]).transpose(1, 2)
+                res = _conv1d(xc, P[p + ".downsample.weight"], P[p + ".downsample.bias"], 0, 1, tf32).transpose(1, 2)
             else:
                 res = x
             x = F.leaky_relu(h + res, LEAKY_SLOPE)
@@ -373,18 +412,19 @@ def trainable_names(sd: SD) -> List[str]:
 
 
 def train_step(sd: SD, feats: Dict[str, Tensor], labels: Tensor, modalities: Sequence[str], opt: dict,
-               opt_state: dict = None, seed=None, modal_dim: int = 32, num_heads: int = 2):
+               opt_state: dict = None, seed=None, modal_dim: int = 32, num_heads: int = 2, tf32: bool = False):
     """One optimisation step as trainer.py:365-391 does it (fp32, no AMP): mean cross-entropy over
     B*T frames (experiment.py:133), backward through the head only, one optimizer step.
     opt = {'name': 'sgd'|'adam'|'adamw', 'lr', 'weight_decay', ('momentum','dampening','nesterov') |
     ('beta1','beta2','eps')}; returns (loss, grads, new_sd, opt_state).  Optimizer arithmetic
-    follows torch.optim.{SGD,Adam,AdamW} (instantiators.py:60-100)."""
+    follows torch.optim.{SGD,Adam,AdamW} (instantiators.py:60-100).  tf32=True: the TCN convolutions' GEMMs
+    (forward, dgrad, wgrad) see TF32-rounded operands, as the kernels' precision="tf32" mode does."""
     names = trainable_names(sd)
     P = {k: sd[k].detach().clone().requires_grad_(True) for k in names}
     buffers = {k: v.detach().clone() for k, v in sd.items() if k.startswith("bn.") and k not in P}
     with torch.enable_grad():
         logits = head_forward_train(P, buffers, {m: v.squeeze(1) if v.dim() == 4 else v for m, v in feats.items()},
-                                    modalities, modal_dim, num_heads, seed)
+                                    modalities, modal_dim, num_heads, seed, tf32=tf32)
         loss = F.cross_entropy(logits.reshape(-1, logits.shape[-1]), labels.reshape(-1).long())
         grads = dict(zip(names, torch.autograd.grad(loss, [P[k] for k in names])))
     st = opt_state if opt_state is not None else {"step": 0, "m": {}, "v": {}}

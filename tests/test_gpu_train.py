@@ -366,58 +366,41 @@ def test_ce_loss_ignore_index_and_out_of_range_labels():
 
 
 # ----------------------------------------------------------------------------------------------
-# TF32 tensor-core mode (HeadTrainer's default).  Tolerances: products carry 10 mantissa bits, sums are
-# fp32; measured on B200 (CER_GRAD_STATS): see _tf32_close.
+# TF32 tensor-core mode (HeadTrainer's default: the TCN convolutions' GEMMs see TF32-rounded operands).
+# TF32 moves this model's gradients by a few per cent whoever computes them: the oracle with TF32-rounded
+# conv operands on the CPU (O.train_step(..., tf32=True)) differs from its own fp32 run by 2.5 % (median
+# over the tensors) to 7 % (worst) in relative L2 -- BatchNorm1d with batch statistics and LayerNorm
+# amplify the 5e-4 operand rounding ~30x on the way back.  So the TF32 kernels are pinned TIGHTLY against
+# the TF32 oracle (same rounding, cvt.rna), and LOOSELY (the amplification above) against the reference's
+# fp32 golden.
 # ----------------------------------------------------------------------------------------------
 _TF32_STATS = []
 
 
-def _tf32_close(mine, ref, norm=None, what=""):
-    """TF32 GEMMs vs fp32 CPU autograd: relative L2 error of a gradient tensor <= 1e-2 (products are
-    rounded to 10 mantissa bits: ~5e-4 per operand, averaged over the reduction)."""
+def _rel_l2(mine, ref, norm=None, what="", bar=5e-3):
     mine, ref = mine.double().flatten(), ref.double().flatten()
     norm = float(ref.norm()) if norm is None else norm
     rel = float((mine - ref).norm()) / max(norm, 1e-30)
-    _TF32_STATS.append(rel)
-    assert rel <= 1e-2, (what, rel)
+    _TF32_STATS.append((what, bar, rel))
+    assert rel <= bar, (what, rel)
     return rel
 
 
-def test_tf32_two_sgd_steps_vs_reference_golden(golden_dir):
-    """The default (TF32 tensor-core) training step against the reference's two SGD steps: loss within 2e-3,
-    every gradient within 1e-2 in relative L2, BatchNorm statistics within 1e-3, parameters after the update
-    within lr * 1e-2 * |g| of the reference's."""
-    from feature_vs_text_compound_emotion_b200.training import HeadTrainer
-    dev = _dev()
-    g = torch.load(os.path.join(golden_dir, "train_b2.pt"))
-    mods = g["modalities"]
-    m = _lfan(mods, dev, g["weights_seed"], p_drop=0.0, precision="tf32")
-    tr = HeadTrainer(m, 2, 300, optimizer=g["opt"])
-    assert tr.precision == "tf32"
-    X = {k: v.to(dev) for k, v in synthetic.feature_windows(2, 300, seed=g["x_seed"], modalities=mods).items()}
-    labels = torch.randint(0, 7, (2, 300, 1), generator=torch.Generator().manual_seed(g["label_seed"])).float().to(dev)
-    worst = 0.0
-    for step in g["steps"]:
-        loss = tr.step(X, labels)
-        assert abs(loss.item() - step["loss"]) < 2e-3
-        for k, gn in step["grad_norm"].items():
-            mine = tr.grad(k).cpu()
-            ref = step["grad_small"][k] if k in step["grad_small"] else step["grad_sample"][k]
-            got = mine if k in step["grad_small"] else mine.flatten()[::997]
-            if k in step["grad_small"]:
-                worst = max(worst, _tf32_close(got, ref, norm=gn, what=k))
-            else:                                # a 1/997 sample of a big tensor: compare against the sample's own norm
-                worst = max(worst, _tf32_close(got, ref, what=k))
-            assert abs(float(mine.double().norm()) - gn) <= 1e-2 * gn + 1e-7, k
-        sd = m.state_dict()
-        for k, v in step["bn"].items():
-            assert (sd[k].cpu().float() - v.float()).abs().max().item() < 1e-3, k
-    print("tf32 worst relative L2 gradient error", worst)
+@pytest.fixture(scope="module", autouse=True)
+def _dump_tf32_stats():
+    yield
+    path = os.environ.get("CER_GRAD_STATS")
+    if path and _TF32_STATS:
+        import json
+        with open(path.replace(".json", "_tf32.json"), "w") as f:
+            json.dump(_TF32_STATS, f)
 
 
-def test_tf32_dropout_forward_backward_vs_oracle_and_fp32_mode():
-    """TF32 mode with dropout ON against the oracle (same mask hash), and against this repo's exact fp32
-    mode on the same inputs: logits within 5e-3, loss within 2e-3, gradients within 1e-2 (relative L2)."""
+def test_tf32_step_vs_tf32_oracle_and_fp32_mode():
+    """TF32 mode, dropout ON, against the oracle run with TF32-rounded conv operands (same masks, same
+    rounding): logits within 2e-4, loss within 2e-5, every gradient within 5e-3 in relative L2 -- and
+    against this repo's exact fp32 mode on the same inputs at the TF32 deviation (logits 5e-3, loss 2e-3,
+    gradients 0.1)."""
     from feature_vs_text_compound_emotion_b200.training import HeadTrainer
     dev = _dev()
     sd = synthetic.lfan_state_dict(3, MODS)
@@ -432,11 +415,45 @@ def test_tf32_dropout_forward_backward_vs_oracle_and_fp32_mode():
         loss, dl = tr.cross_entropy(logits, labels.to(dev))
         tr.backward(dl)
         outs[prec] = (logits.cpu(), loss.item(), {k: tr.grad(k).cpu().clone() for k in tr.names})
-    ref_loss, grads, _, _ = O.train_step(sd, X, labels, MODS, {"name": "sgd", "lr": 0.0}, None, seed=seed)
     lt, losst, gt = outs["tf32"]
     lf, lossf, gf = outs["fp32"]
-    assert (lt - lf).abs().max().item() < 5e-3 and not torch.equal(lt, lf)
-    assert abs(losst - float(ref_loss)) < 2e-3 and abs(losst - lossf) < 2e-3
+    P = {k: sd[k] for k in O.trainable_names(sd)}
+    buffers = {k: v.clone() for k, v in sd.items() if k.startswith("bn.") and k not in P}
+    want = O.head_forward_train(P, buffers, {k: v.squeeze(1) for k, v in X.items()}, MODS, seed=seed, tf32=True)
+    assert (lt - want).abs().max().item() < 2e-4
+    ref_loss, grads, _, _ = O.train_step(sd, X, labels, MODS, {"name": "sgd", "lr": 0.0}, None, seed=seed, tf32=True)
+    assert abs(losst - float(ref_loss)) < 2e-5
     for k, g in grads.items():
-        _tf32_close(gt[k], g, what=k)
-        _tf32_close(gt[k], gf[k], what=k)
+        _rel_l2(gt[k], g, what="vs tf32 oracle: " + k, bar=5e-3)
+    assert (lt - lf).abs().max().item() < 5e-3 and not torch.equal(lt, lf)
+    assert abs(losst - lossf) < 2e-3
+    for k in grads:
+        _rel_l2(gt[k], gf[k], what="vs fp32 mode: " + k, bar=0.1)
+
+
+def test_tf32_two_sgd_steps_vs_reference_golden(golden_dir):
+    """The default (TF32) training step against the REFERENCE's two fp32 SGD steps: loss within 2e-3, gradient
+    norms within 5 %, gradients within 0.1 in relative L2 (the TF32 deviation explained above), BatchNorm
+    running statistics within 1e-3."""
+    from feature_vs_text_compound_emotion_b200.training import HeadTrainer
+    dev = _dev()
+    g = torch.load(os.path.join(golden_dir, "train_b2.pt"))
+    mods = g["modalities"]
+    m = _lfan(mods, dev, g["weights_seed"], p_drop=0.0, precision="tf32")
+    tr = HeadTrainer(m, 2, 300, optimizer=g["opt"])
+    assert tr.precision == "tf32"
+    X = {k: v.to(dev) for k, v in synthetic.feature_windows(2, 300, seed=g["x_seed"], modalities=mods).items()}
+    labels = torch.randint(0, 7, (2, 300, 1), generator=torch.Generator().manual_seed(g["label_seed"])).float().to(dev)
+    for step in g["steps"]:
+        loss = tr.step(X, labels)
+        assert abs(loss.item() - step["loss"]) < 2e-3
+        for k, gn in step["grad_norm"].items():
+            mine = tr.grad(k).cpu()
+            if k in step["grad_small"]:
+                _rel_l2(mine, step["grad_small"][k], norm=gn, what="vs reference golden: " + k, bar=0.1)
+            else:                                # a 1/997 sample of a big tensor: against the sample's own norm
+                _rel_l2(mine.flatten()[::997], step["grad_sample"][k], what="vs reference golden (sample): " + k, bar=0.15)
+            assert abs(float(mine.double().norm()) - gn) <= 5e-2 * gn + 1e-7, k
+        sd = m.state_dict()
+        for k, v in step["bn"].items():
+            assert (sd[k].cpu().float() - v.float()).abs().max().item() < 1e-3, k
