@@ -55,24 +55,48 @@ __global__ void __launch_bounds__(kFusThreads) fusion_head_kernel(cer_fusion_wei
   float* s_val = s_qkv + kFR * d.M * d.D3;
 
   const float* feats[CER_MAX_MODALS] = {f0, f1, f2, f3};
-  // weight staging dominates this kernel at small batches (150 KB per CTA for ~1 frame group per warp):
-  // 16-byte loads where the host verified alignment (D3 and E*E are multiples of 4 floats)
-  for (int m = 0; m < d.M; ++m) {
-    const int n4 = d.dim[m] * d.D3 / 4;
-    const float4* src = reinterpret_cast<const float4*>(w.wqkv[m]);
-    float4* dst = reinterpret_cast<float4*>(s_wqkv + d.doff[m] * d.D3);
-    for (int i = threadIdx.x; i < n4; i += kFusThreads) dst[i] = __ldg(src + i);
+  // Weight staging: ~145 KB per CTA.  A thread loop of LDG -> STS kept ~one load in flight per thread and took
+  // 130 of the kernel's 150 us (ncu: every top stall an STS waiting on its LDG, profiles/r01_full_fusion.txt);
+  // the TMA unit streams the same bytes with a handful of bulk copies onto one mbarrier (the host verified
+  // 16-byte alignment and sizes: D3 and E*E are multiples of 4 floats).
+  __shared__ __align__(8) unsigned long long s_bar;
+  const uint32_t bar = static_cast<uint32_t>(__cvta_generic_to_shared(&s_bar));
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  {
-    const float4* src = reinterpret_cast<const float4*>(w.wo);
-    float4* dst = reinterpret_cast<float4*>(s_wo);
-    for (int i = threadIdx.x; i < d.E * d.E / 4; i += kFusThreads) dst[i] = __ldg(src + i);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t total = static_cast<uint32_t>(d.E * d.E * 4);
+    for (int m = 0; m < d.M; ++m) total += static_cast<uint32_t>(d.dim[m] * d.D3 * 4);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(total) : "memory");
+    for (int m = 0; m <= d.M; ++m) {
+      const float* src = m < d.M ? w.wqkv[m] : w.wo;
+      float* dst = m < d.M ? s_wqkv + d.doff[m] * d.D3 : s_wo;
+      uint32_t left = static_cast<uint32_t>((m < d.M ? d.dim[m] * d.D3 : d.E * d.E) * 4);
+      uint32_t off = 0;
+      while (left > 0) {                                    // pieces of at most 64 KB
+        const uint32_t n = left < 65536u ? left : 65536u;
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(reinterpret_cast<char*>(dst) + off))),
+                       "l"(reinterpret_cast<const char*>(src) + off), "r"(n), "r"(bar)
+                     : "memory");
+        off += n; left -= n;
+      }
+    }
   }
   for (int i = threadIdx.x; i < (d.dim[0] + d.E) * d.n_out; i += kFusThreads) s_wr[i] = w.wr[i];
   for (int m = 0; m < d.M; ++m)
     for (int i = threadIdx.x; i < d.D3; i += kFusThreads) s_bqkv[m * d.D3 + i] = w.bqkv[m][i];
   for (int i = threadIdx.x; i < d.E; i += kFusThreads) { s_bo[i] = w.bo[i]; s_g[i] = w.ln_g[i]; s_b[i] = w.ln_b[i]; }
   if (threadIdx.x < d.n_out) s_br[threadIdx.x] = w.br[threadIdx.x];
+  {
+    uint32_t ok = 0;
+    while (!ok) {
+      asm volatile("{\n\t.reg .pred P;\n\tmbarrier.try_wait.parity.shared::cta.b64 P, [%1], 0;\n\tselp.b32 %0, 1, 0, P;\n\t}\n"
+                   : "=r"(ok) : "r"(bar) : "memory");
+    }
+  }
   __syncthreads();
 
   const float scale = rsqrtf((float)d.hd);

@@ -79,6 +79,7 @@ class _PackedModule(nn.Module):
         self.__dict__.pop("_preproc", None)
         self.__dict__.pop("_logmel", None)
         self.__dict__.pop("_head_graphs", None)
+        self.__dict__.pop("_head_streams", None)
         return super()._apply(fn, *a, **kw)
 
     def _device(self) -> torch.device:
@@ -578,12 +579,50 @@ class LFAN(_PackedModule):
     # static buffers and replayed; CER_HEAD_GRAPH=0 or any capture failure keeps the eager launches.
     head_cuda_graph = True
 
+    # The three TCN stacks are independent chains of 8 small launches (19-76 CTAs each, latency bound): they
+    # run on parallel streams (fork / join with events; inside the CUDA graph these become parallel branches)
+    # and only the fusion kernel waits for all of them.  CER_HEAD_STREAMS=0 serialises them (A/B timing).
+    head_parallel_streams = True
+
     def _forward_features_eager(self, feats: Dict[str, torch.Tensor]) -> torch.Tensor:
         tcn, fus = self._head_engines()
-        enc = []
-        for m in self.modality:
-            enc.append(tcn[m].forward(feats[m].float()))
-            feats[m] = enc[-1]
+        mods = list(self.modality)
+        dev = feats[mods[0]].device
+        enc = [None] * len(mods)
+        parallel = (self.head_parallel_streams and len(mods) > 1 and dev.type == "cuda"
+                    and os.environ.get("CER_HEAD_STREAMS", "1") != "0")
+        if not parallel:
+            for i, m in enumerate(mods):
+                enc[i] = tcn[m].forward(feats[m].float())
+        else:
+            main = torch.cuda.current_stream(dev)
+            side = self.__dict__.setdefault("_head_streams", {})
+            key = str(dev)
+            if key not in side:
+                side[key] = [torch.cuda.Stream(device=dev) for _ in range(len(mods) - 1)]
+            capturing = torch.cuda.is_current_stream_capturing()
+            fork = torch.cuda.Event()
+            fork.record(main)
+            joins = []
+            for i, m in enumerate(mods):
+                x = feats[m].float()
+                if i == 0:
+                    enc[0] = tcn[m].forward(x)
+                    continue
+                st = side[key][i - 1]
+                st.wait_event(fork)
+                with torch.cuda.stream(st):
+                    enc[i] = tcn[m].forward(x)
+                    ev = torch.cuda.Event()
+                    ev.record(st)
+                    joins.append(ev)
+                if not capturing:                     # a graph's private pool keeps its blocks; eager mode must tell the allocator
+                    x.record_stream(st)
+                    enc[i].record_stream(main)        # allocated on the side stream, consumed on the caller's
+            for ev in joins:
+                main.wait_event(ev)
+        for m, e in zip(mods, enc):
+            feats[m] = e
         B, T, _ = enc[0].shape
         logits = fus.forward([e.view(B * T, -1) for e in enc])
         return logits.view(B, T, -1)
