@@ -383,10 +383,11 @@ extern "C" int cer_fusion_head_forward(const cer_fusion_weights* w, const float*
                         (size_t)d.M * d.D3 + 3 * (size_t)d.E + kMaxOut +
                         (size_t)kFusWarps * kFR * (d.din_total + d.M * d.D3 + d.E);
   const size_t smem = floats * sizeof(float);
-  if (smem > 227 * 1024) return set_error(CER_ERR_INVALID, "fusion: weights do not fit in shared memory");
+  constexpr size_t kMaxDyn = 227 * 1024 - 64;                 // the kernel's static mbarrier shares the 227 KB
+  if (smem > kMaxDyn) return set_error(CER_ERR_INVALID, "fusion: weights do not fit in shared memory");
   static unsigned long long configured = 0;
   if (first_use_on_device(&configured))
-    CER_CUDA(cudaFuncSetAttribute(fusion_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CER_CUDA(cudaFuncSetAttribute(fusion_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDyn));
   int dev = 0, sms = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

@@ -286,7 +286,7 @@ class FusionEngine:
         fused_floats = (sum(self.dims) * 3 * fw["modal_dim"] + self.E * self.E + (self.dims[0] + self.E) * self.n_out
                         + fw["n_modals"] * 3 * fw["modal_dim"] + 3 * self.E + 16
                         + 4 * 4 * (sum(self.dims) + fw["n_modals"] * 3 * fw["modal_dim"] + self.E))
-        self.composed = fused_floats * 4 > 227 * 1024 or self.E > 128 or self.n_out > 16
+        self.composed = fused_floats * 4 > 227 * 1024 - 64 or self.E > 128 or self.n_out > 16
         if self.composed:
             d = lambda t: t.to(self.device).contiguous()
             self._c = {"wqkv": [d(t) for t in fw["wqkv_oi"]], "bqkv": [d(t) for t in fw["bqkv"]], "wo": d(fw["wo_oi"]),
