@@ -16,6 +16,17 @@
 // wrong results; profiles/r01_halo_conv.txt).
 // L2->SM traffic drops from 9 x 16 KB to 22.5 KB per tile; weights stay resident in smem.
 //
+// What bounds it (round 2, tools/umma_probe.cu + profiles/r02_halo64_conv1.txt): with both operands in shared
+// memory an M128 x N64 x K16 MMA cannot retire faster than one per 48 cycles (6 KB of operands at the 128 B/cycle
+// the tensor core reads shared memory; N = 128: 64 cycles = its tensor floor), against a 32-cycle tensor floor.
+// The kernel issues one per 58 cycles: the MMA warp is never idle (its stall samples sit ON the UTCHMMA
+// instructions), the halo producer waits 83 % of its time for a free slot, the accumulator is free when needed.
+// So the N = 64 layers are bound by the tensor core's shared-memory operand path, not by HBM (35 %), L2 or
+// the epilogue -- which is also why (a) fusing conv1 -> conv2 of a unit would not help (same MMAs, plus
+// halo recompute) and (b) an epilogue that transposes through shared memory to coalesce its stores made the
+// kernel 4 % SLOWER (it takes shared-memory bandwidth from the MMAs; tried, reverted).  What is left on the
+// table is the half-empty third band of a 40-row map (36000 instead of 30000 tiles per 2400 frames).
+//
 // Warps: 0-7 epilogue (shared with conv_igemm.cuh), 8 MMA issuer, 9 halo producer, 10 weight loader.
 #pragma once
 #include "conv_igemm.cuh"
@@ -37,10 +48,7 @@ struct HaloSmem {
   static constexpr int kNumBars = 2 * kStages + 5;
   static constexpr int kTableOffset = (kBarOffset + kNumBars * 8 + 16 + 15) & ~15;
   static constexpr int kTableFloats = 10 * BN;
-  // BN = 64: 2 KB per epilogue warp for the staged (coalescing) epilogue; BN = 128 has no room beside its 144 KB of weights
-  static constexpr bool kStaged = BN == 64;
-  static constexpr int kEpiStageOffset = kTableOffset + kTableFloats * 4;
-  static constexpr int kTotal = kEpiStageOffset + (kStaged ? kEpiWarps * 2048 : 0) + 1024;
+  static constexpr int kTotal = kTableOffset + kTableFloats * 4 + 1024;
 };
 
 __device__ __forceinline__ void tma_load_tile_4d(const CUtensorMap* m, uint32_t bar, uint32_t dst, int c, int w, int h, int n) {
@@ -190,13 +198,8 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
       }
       const bool pool_store = p.pool_xor && valid && !(oh & 1) && !(ow & 1);
       const size_t pool_off = ((static_cast<size_t>(n) * (p.Hout >> 1) + (oh >> 1)) * (p.Wout >> 1) + (ow >> 1)) * p.Cout + n0;
-      if (L::kStaged && !p.pool_xor)
-        conv_epilogue_core_staged<BN>(p, s_bias, s_alpha, tmem_base + acc * BN, n0, warp, tfull0 + acc * 8, acc_phase, valid, cls,
-                                      m * p.Cout + n0, tempty0 + acc * 8,
-                                      reinterpret_cast<uint4*>(smem + L::kEpiStageOffset + warp * 2048));
-      else
-        conv_epilogue_core<BN>(p, s_bias, s_alpha, tmem_base + acc * BN, n0, warp, tfull0 + acc * 8, acc_phase, valid, cls,
-                               m * p.Cout + n0, tempty0 + acc * 8, pool_store, pool_off);
+      conv_epilogue_core<BN>(p, s_bias, s_alpha, tmem_base + acc * BN, n0, warp, tfull0 + acc * 8, acc_phase, valid, cls,
+                             m * p.Cout + n0, tempty0 + acc * 8, pool_store, pool_off);
     }
   }
 

@@ -238,124 +238,6 @@ __device__ __forceinline__ void conv_epilogue_core(const ConvKernelParams& p, co
   }
 }
 
-// Staged variant of the epilogue for the kernels whose tiles are SHORT (Cin = 64 layers: 36 MMAs per tile).
-// In conv_epilogue_core every lane owns one pixel, so a warp-wide STG.128 / LDG.128 touches 32 different
-// 128-byte lines (16 B in each): 32 LSU wavefronts per instruction.  With 1728 tensor cycles per tile the
-// halo kernel was bound by exactly that (ncu: epilogue warps busy 88 % of the time, the MMA warp waiting 79 %
-// of its time for a free accumulator; profiles/r02_halo64_epilogue.txt).  Here each warp transposes its
-// 32 pixels x 32 channels (2 KB) through a warp-private shared-memory buffer so that global loads (residual)
-// and stores move 64 contiguous bytes per 4 lanes: 8 wavefronts per instruction instead of 32.
-//   thread layout  : lane = pixel, 4 x 16 B pieces of that pixel's 64-byte half row
-//   memory layout  : instruction s, lane l  ->  pixel 8 s + l / 4, piece l % 4
-// The buffer is swizzled (piece ^ (pixel >> 1) & 3) so both access patterns are bank-conflict free.
-// `stg` = this warp's 2 KB buffer.  No fused max-pool here (callers route pooling layers to the direct path).
-template <int BN>
-__device__ __forceinline__ void conv_epilogue_core_staged(const ConvKernelParams& p, const float* s_bias, const float* s_alpha,
-                                                          uint32_t tmem_acc, int n0, int warp, uint32_t tfull, uint32_t parity,
-                                                          bool valid, int cls, size_t out_off, uint32_t tempty, uint4* stg) {
-  constexpr int kHalf = BN / 2;
-  const int lane = threadIdx.x & 31;
-  const int quarter = warp & 3;
-  const int half = warp >> 2;
-  const uint32_t lane_addr = (static_cast<uint32_t>(quarter * 32) << 16);
-  const bool has_res = p.res != nullptr;
-  const bool has_alpha = p.alpha != nullptr;
-  const float* sb = s_bias + cls * p.Cout + n0;
-  const float* sal = s_alpha + n0;
-  const int q = lane & 3;                                  // 16-byte piece this lane moves in the memory layout
-  // element offsets / validity of the four pixels this lane touches in the memory layout
-  size_t moff[4];
-  bool mval[4];
-#pragma unroll
-  for (int s = 0; s < 4; ++s) {
-    const int src = s * 8 + (lane >> 2);
-    const uint32_t lo = __shfl_sync(0xffffffffu, static_cast<uint32_t>(out_off), src);
-    const uint32_t hi = __shfl_sync(0xffffffffu, static_cast<uint32_t>(out_off >> 32), src);
-    moff[s] = ((static_cast<size_t>(hi) << 32) | lo) + q * 8;
-    mval[s] = __shfl_sync(0xffffffffu, valid ? 1 : 0, src) != 0;
-  }
-  const int own = lane * 4, own_sw = (lane >> 1) & 3;      // this lane's row in the thread layout
-
-  uint4 rc[4];                                             // residual of the first chunk, memory layout, requested early
-  if (has_res) {
-#pragma unroll
-    for (int s = 0; s < 4; ++s) rc[s] = mval[s] ? __ldg(reinterpret_cast<const uint4*>(p.res + moff[s])) : make_uint4(0, 0, 0, 0);
-  }
-  mbar_wait_a(tfull, parity);
-  tc_fence_after();
-#pragma unroll
-  for (int c0 = 0; c0 < kHalf; c0 += 32) {
-    uint32_t v[32];
-    tmem_ld_32x32(tmem_acc + lane_addr + half * kHalf + c0, v);
-    uint4 rres[4];
-    if (has_res) {                                         // memory layout -> thread layout through the buffer
-#pragma unroll
-      for (int s = 0; s < 4; ++s) {
-        const int pix = s * 8 + (lane >> 2);
-        stg[pix * 4 + (q ^ ((pix >> 1) & 3))] = rc[s];
-      }
-      __syncwarp();
-#pragma unroll
-      for (int j = 0; j < 4; ++j) rres[j] = stg[own + (j ^ own_sw)];
-      __syncwarp();
-      if (c0 + 32 < kHalf) {
-#pragma unroll
-        for (int s = 0; s < 4; ++s)
-          rc[s] = mval[s] ? __ldg(reinterpret_cast<const uint4*>(p.res + moff[s] + c0 + 32)) : make_uint4(0, 0, 0, 0);
-      }
-    }
-    tmem_ld_wait();
-    if (c0 + 32 >= kHalf) {                                // accumulator is in registers: free it (see conv_epilogue_core)
-      tc_fence_before();
-      if (lane == 0) mbar_arrive_relaxed_cluster(tempty);
-    }
-    float f[32];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float4 b = *reinterpret_cast<const float4*>(sb + c0 + 4 * j);
-      f[4 * j + 0] = __uint_as_float(v[4 * j + 0]) + b.x;
-      f[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + b.y;
-      f[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + b.z;
-      f[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + b.w;
-    }
-    if (has_alpha) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float4 a = *reinterpret_cast<const float4*>(sal + c0 + 4 * j);
-        f[4 * j + 0] = f[4 * j + 0] >= 0.f ? f[4 * j + 0] : f[4 * j + 0] * a.x;
-        f[4 * j + 1] = f[4 * j + 1] >= 0.f ? f[4 * j + 1] : f[4 * j + 1] * a.y;
-        f[4 * j + 2] = f[4 * j + 2] >= 0.f ? f[4 * j + 2] : f[4 * j + 2] * a.z;
-        f[4 * j + 3] = f[4 * j + 3] >= 0.f ? f[4 * j + 3] : f[4 * j + 3] * a.w;
-      }
-    }
-    if (has_res) {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const uint32_t w[4] = {rres[j].x, rres[j].y, rres[j].z, rres[j].w};
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&w[k]);
-          f[8 * j + 2 * k + 0] += __bfloat162float(h.x);
-          f[8 * j + 2 * k + 1] += __bfloat162float(h.y);
-        }
-      }
-    }
-    // thread layout -> memory layout, then 64 contiguous bytes per 4 lanes
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-      stg[own + (j ^ own_sw)] = make_uint4(pack_bf16x2(f[8 * j + 0], f[8 * j + 1]), pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
-                                           pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), pack_bf16x2(f[8 * j + 6], f[8 * j + 7]));
-    __syncwarp();
-#pragma unroll
-    for (int s = 0; s < 4; ++s) {
-      const int pix = s * 8 + (lane >> 2);
-      const uint4 o = stg[pix * 4 + (q ^ ((pix >> 1) & 3))];
-      if (mval[s]) *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + moff[s] + c0) = o;
-    }
-    __syncwarp();
-  }
-}
-
 // ALIGNED = true: the host guarantees ksteps % STAGES == 0, so every tile walks the ring a whole
 // number of times.  Stage indices are then compile-time inside the unrolled role loops: barrier,
 // smem and descriptor addresses are base + immediate, which shrinks the MMA-issue loop from ~70 to

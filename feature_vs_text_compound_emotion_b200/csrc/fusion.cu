@@ -21,7 +21,7 @@
 
 namespace cer {
 
-constexpr int kFR = 4;          // frames per warp pass
+constexpr int kFRMin = 4, kFRMax = 8;   // frames per warp pass (template parameter kFR of the kernel, picked at launch)
 constexpr int kFusWarps = 4;
 constexpr int kFusThreads = kFusWarps * 32;
 constexpr int kMaxE = 128;      // modal_dim * n_modals
@@ -31,6 +31,7 @@ struct FusionDims {
   int M, E, D3, hd, H, n_out, din_total, dim[CER_MAX_MODALS], doff[CER_MAX_MODALS];
 };
 
+template <int kFR>
 __global__ void __launch_bounds__(kFusThreads) fusion_head_kernel(cer_fusion_weights w, FusionDims d,
                                                                   const float* f0, const float* f1, const float* f2,
                                                                   const float* f3, long long rows,
@@ -379,24 +380,39 @@ extern "C" int cer_fusion_head_forward(const cer_fusion_weights* w, const float*
     return set_error(CER_ERR_INVALID, "fusion: modal_dim must be a multiple of 4 and weights 16B aligned");
   for (int m = 0; m < d.M; ++m)
     if (reinterpret_cast<uintptr_t>(w->wqkv[m]) & 15) return set_error(CER_ERR_INVALID, "fusion: wqkv must be 16B aligned");
-  const size_t floats = (size_t)d.din_total * d.D3 + (size_t)d.E * d.E + (size_t)(d.dim[0] + d.E) * d.n_out +
-                        (size_t)d.M * d.D3 + 3 * (size_t)d.E + kMaxOut +
-                        (size_t)kFusWarps * kFR * (d.din_total + d.M * d.D3 + d.E);
-  const size_t smem = floats * sizeof(float);
-  constexpr size_t kMaxDyn = 227 * 1024 - 64;                 // the kernel's static mbarrier shares the 227 KB
-  if (smem > kMaxDyn) return set_error(CER_ERR_INVALID, "fusion: weights do not fit in shared memory");
-  static unsigned long long configured = 0;
-  if (first_use_on_device(&configured))
-    CER_CUDA(cudaFuncSetAttribute(fusion_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDyn));
   int dev = 0, sms = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const long long groups = (rows + kFR - 1) / kFR;
+  constexpr size_t kMaxDyn = 227 * 1024 - 64;                 // the kernel's static mbarrier shares the 227 KB
+  const size_t fixed = (size_t)d.din_total * d.D3 + (size_t)d.E * d.E + (size_t)(d.dim[0] + d.E) * d.n_out +
+                       (size_t)d.M * d.D3 + 3 * (size_t)d.E + kMaxOut;
+  const size_t per_frame = (size_t)kFusWarps * (d.din_total + d.M * d.D3 + d.E);
+  auto smem_for = [&](int fr) { return (fixed + per_frame * fr) * sizeof(float); };
+  if (smem_for(kFRMin) > kMaxDyn) return set_error(CER_ERR_INVALID, "fusion: weights do not fit in shared memory");
+  // Frames per warp pass: every weight is read from shared memory once per pass whatever the frame count, so a
+  // pass costs about the same for 4 or 8 frames.  Pick the smallest count for which ONE pass of the grid's
+  // warps covers all rows (2400 rows: 5 frames x 592 warps; with 4 frames eight warps ran a second pass and
+  // the kernel took twice as long, profiles/r02_fusion.txt), as far as shared memory allows.
+  int fr = kFRMin;
+  while (fr < kFRMax && (rows + fr - 1) / fr > (long long)sms * kFusWarps && smem_for(fr + 1) <= kMaxDyn) ++fr;
+  const size_t smem = smem_for(fr);
+  const long long groups = (rows + fr - 1) / fr;
   const int grid = (int)std::min<long long>((groups + kFusWarps - 1) / kFusWarps, sms);
   const float* f[CER_MAX_MODALS] = {nullptr, nullptr, nullptr, nullptr};
   for (int m = 0; m < d.M; ++m) f[m] = feats[m];
-  fusion_head_kernel<<<grid, kFusThreads, smem, static_cast<cudaStream_t>(stream)>>>(*w, d, f[0], f[1], f[2], f[3],
-                                                                                    (long long)rows, logits, fused_out);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+#define CER_FUSION_LAUNCH(FR)                                                                                              \
+  case FR: {                                                                                                               \
+    static unsigned long long configured = 0;                                                                              \
+    if (first_use_on_device(&configured))                                                                                  \
+      CER_CUDA(cudaFuncSetAttribute(fusion_head_kernel<FR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDyn));   \
+    fusion_head_kernel<FR><<<grid, kFusThreads, smem, st>>>(*w, d, f[0], f[1], f[2], f[3], (long long)rows, logits, fused_out); \
+  } break;
+  switch (fr) {
+    CER_FUSION_LAUNCH(4) CER_FUSION_LAUNCH(5) CER_FUSION_LAUNCH(6) CER_FUSION_LAUNCH(7) CER_FUSION_LAUNCH(8)
+    default: return set_error(CER_ERR_INVALID, "fusion: frames per pass out of range");
+  }
+#undef CER_FUSION_LAUNCH
   CER_CUDA(cudaGetLastError());
   return CER_OK;
 }
