@@ -20,7 +20,8 @@ Prints ONE JSON line (rank 0):
   roofline_hbm the memory-/latency-bound kernels (stem, TCN stacks, fusion head, eval transform): GB/s of
                algorithmic bytes against the measured HBM peak
   ir50 / ir50_layers   the whole backbone and every layer class timed in place (cer_ir50_run_ops)
-  head_only / train / full   compact records of BASELINE configs[0] / [3] / [2] on the same box
+  head_only / train / full / sweep / alt_heads   compact records of BASELINE configs[0] / [3] / [2] / [4] and of the
+               CAN / JMT / MT heads on the same box
   library_bar  the reference's own IR-50 through cuDNN (channels_last, cudnn.benchmark, bf16/fp16 autocast)
   cpu_baseline the reference's own LFAN.forward (oracle/_ref) on this box's host cores, bounded sample
 """
@@ -661,11 +662,18 @@ def run_infer(args, dev, world, rank, local, dist):
                         "frames_per_s": tr["value"], "ms_per_step": tr["ms_per_step"], "steps": 5, "precision": tr["precision"],
                         "loss_first_last": tr["loss_first_last"]}
         torch.cuda.empty_cache()
-        fv = measure_videos(dev, world, rank, local, dist, 8 * world, 2, 1, with_e2e=False)
+        vm = build_model(dev, ["video", "logmel", "bert"])
+        fv = measure_videos(dev, world, rank, local, dist, 8 * world, 2, 1, with_e2e=False, model=vm)
         sub["full"] = {"workload": f"configs[2]: {8 * world} whole videos (T_v~U[150,3000]) from stored uint8 crops + log-mel + BERT "
                                    "-> eval transform -> IR-50 / VGGish -> TCN -> fusion -> stitch -> vote",
                        "unique_frames_per_s": fv["value"], "ms_per_pass": fv["ms_per_step"], "unique_frames": fv["frames_total"],
                        "windows": fv["windows"], "example_vote": fv.get("example_vote")}
+        sv = measure_videos(dev, world, rank, local, dist, 128, 1, 1, with_e2e=False, model=vm)
+        del vm
+        sub["sweep"] = {"workload": "configs[4] (reduced): 128 whole videos sharded over the ranks, longest first (STRONG scaling: the "
+                                    "total is fixed; bench.py --workload sweep runs the 1000-video version)",
+                        "unique_frames_per_s": sv["value"], "ms_per_pass": sv["ms_per_step"], "unique_frames": sv["frames_total"],
+                        "windows": sv["windows"]}
         torch.cuda.empty_cache()
 
     if rank != 0:

@@ -192,3 +192,61 @@ def test_attention_maps_match_reference(golden_dir):
     x = {m: torch.randn(2, g["T"], d, generator=torch.Generator().manual_seed(g["seed"])) for m, d in zip(mods, (128, 32, 128))}
     maps = O.attention_maps(sd, "fusion.", x, mods)
     assert maps.shape == (2, 2, g["T"], 3, 3) and (maps - g["maps"]).abs().max().item() < 1e-6
+
+
+def test_alternative_heads_match_reference_at_window_length(golden_dir):
+    """The oracle's CAN / JMT / MT restatements against the reference at its own window length (B = 2 x T = 300:
+    sequence attention over 300 positions, final encoder over 600) -- the fixture the GPU parity test uses."""
+    g = torch.load(os.path.join(golden_dir, "heads_t300.pt"))
+    for name in ("CAN", "JMT", "MT"):
+        h = g[name]
+        mods, T = h["modalities"], h["T"]
+        assert T == 300 and tuple(h["out"].shape) == (2, 300, 7)
+        sd = synthetic.can_state_dict(0, mods) if name == "CAN" else synthetic.jmt_state_dict(0, mods, model_name=name)
+        X = {"video": synthetic.frames(2 * T, seed=h["frame_seed"]).view(2, T, 3, 40, 40)}
+        X.update(synthetic.feature_windows(2, T, seed=h["feat_seed"], modalities=[m for m in mods if m != "video"]))
+        out = O.can_forward(sd, X, mods) if name == "CAN" else O.jmt_forward(sd, X, mods, model_name=name)
+        assert (out - h["out"]).abs().max().item() < 1e-4, name
+
+
+def test_tf32_rounding_emulation_and_tf32_train_step():
+    """tf32_round restates PTX cvt.rna.tf32.f32 (10 mantissa bits, round to nearest, ties away from zero); the
+    tf32 train step is the fp32 one with rounded conv operands: same loss to 1e-4, gradients a few per cent away
+    (the deviation the GPU's TF32 mode is allowed, tests/test_gpu_train.py)."""
+    x = torch.tensor([1.0, 1.0 + 2 ** -11, 1.0 + 2 ** -10, -(1.0 + 2 ** -11), 3.14159274, 1e-30, 0.0])
+    r = O.tf32_round(x)
+    assert r[0] == 1.0 and r[1] == 1.0 + 2 ** -10 and r[2] == 1.0 + 2 ** -10 and r[3] == -(1.0 + 2 ** -10)   # ties away
+    assert (r.view(torch.int32) & 0x1FFF).abs().sum() == 0
+    assert ((r - x).abs() <= x.abs() * 2 ** -11 + 1e-45).all()
+    mods = ["vggish", "bert"]
+    sd = synthetic.lfan_state_dict(1, mods)
+    X = synthetic.feature_windows(2, 60, seed=31, modalities=mods)
+    y = torch.randint(0, 7, (2, 60, 1), generator=torch.Generator().manual_seed(32)).float()
+    l0, g0, _, _ = O.train_step(sd, X, y, mods, {"name": "sgd", "lr": 0.0}, None)
+    l1, g1, _, _ = O.train_step(sd, X, y, mods, {"name": "sgd", "lr": 0.0}, None, tf32=True)
+    assert abs(float(l0) - float(l1)) < 1e-3 and float(l0) != float(l1)
+    rel = sorted(float((g1[k] - g0[k]).norm() / g0[k].norm()) for k in g0)
+    assert rel[-1] < 0.5 and rel[len(rel) // 2] < 0.1 and rel[-1] > 1e-4
+
+
+def test_staged_reference_matches_manifest_and_oracle():
+    """oracle/_ref (staged by oracle/build_ref.py; what bench.py's reference arm runs on the GPU box): the manifest
+    hashes hold, and the staged reference LFAN head agrees with the oracle.  Skipped where nothing is staged."""
+    from oracle import build_ref
+    build_ref.stage()
+    if not build_ref.available():
+        pytest.skip("oracle/_ref not staged (no /root/reference here)")
+    ref = build_ref.load()
+    mods = ["cnn_res50", "vggish", "bert"]
+    m = ref.LFAN(backbone_settings={"visual_state_dict": "res50_ir_0.887", "audio_state_dict": "vggish"}, output_dim=7,
+                 task="CLASSIFICATION", modality=mods, kernel_size=5, example_length=300, tcn_channel=synthetic.TCN_CHANNELS,
+                 modal_dim=32, num_heads=2, root_dir="", device="cpu")
+    m.init()
+    sd = synthetic.lfan_state_dict(0, mods)
+    m.load_state_dict(sd, strict=True)
+    m.eval()
+    X = synthetic.feature_windows(1, 300, seed=5, modalities=mods)
+    with torch.no_grad():
+        want = m({k: v.clone() for k, v in X.items()})
+    got = O.lfan_forward(sd, X, mods)
+    assert (got - want).abs().max().item() < 5e-5
