@@ -16,6 +16,8 @@ struct ConvOp {
   int hw_out;      // output pixels per frame
   CUtensorMap tmap_halo;     // tiled 4-D map with an 18 x 10 pixel box (conv_halo_kernel); valid iff halo_ok
   int halo_ok;               // 3x3 / stride 1 / pad 1, Cin = 64, Cout in {64, 128}, W % 8 == 0
+  CUtensorMap tmap_strip;    // tiled 4-D map with an 8-row x 10-pixel box (conv_strip_kernel); valid iff strip_ok
+  int strip_ok;              // halo_ok, Cout = 64, H % 8 == 0, no fused pooling
 };
 
 struct ConvGeom {

@@ -16,6 +16,7 @@
 #include "conv_igemm2.cuh"
 #include "conv_halo.cuh"
 #include "stem_tc.cuh"
+#include "conv_strip.cuh"
 #include <cstdlib>
 
 namespace cer {
@@ -229,6 +230,23 @@ static int make_halo_map(CUtensorMap* map, const void* base, int N, int H, int W
   return CER_OK;
 }
 
+// The same activation with an 8-row x (8+2)-pixel box: one half tile of one filter row of conv_strip_kernel.
+static int make_strip_map(CUtensorMap* map, const void* base, int N, int H, int W, int C) {
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  cuuint32_t box[4] = {64, (cuuint32_t)(kHaloTileW + 2), (cuuint32_t)kStripBoxRows, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = g_encode_tiled(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char buf[128];
+    snprintf(buf, sizeof buf, "cuTensorMapEncodeTiled (strip) failed (%d) N=%d H=%d W=%d C=%d", (int)r, N, H, W, C);
+    return set_error(CER_ERR_CUDA, buf);
+  }
+  return CER_OK;
+}
+
 // Generic helpers shared with the TCN tensor-core path (tcn_tc.cu).
 int make_im2col_map_generic(CUtensorMap* map, CUtensorMapDataType dt, int elem_bytes, const void* base, int N, int H,
                             int W, int C, const int lower[2], const int upper[2], int stride, int channels_per_pixel) {
@@ -339,6 +357,11 @@ int build_conv_op(ConvOp* op, const ConvGeom& g, int n_cap) {
     rc = make_halo_map(&op->tmap_halo, g.src, n_cap, g.H, g.W, g.Cin);
     if (rc) return rc;
   }
+  op->strip_ok = op->halo_ok && g.Cout == 64 && g.H % kStripBoxRows == 0 && !g.pool;
+  if (op->strip_ok) {
+    rc = make_strip_map(&op->tmap_strip, g.src, n_cap, g.H, g.W, g.Cin);
+    if (rc) return rc;
+  }
   return CER_OK;
 }
 
@@ -388,6 +411,25 @@ static int launch_halo_inst(const ConvKernelParams& p, int num_sms, cudaStream_t
   }
   const int tiles = p.halo_frames * p.halo_bands * p.halo_cts;
   return launch_conv_kernel(conv_halo_kernel<BN>, std::min(tiles, num_sms), kHaloThreads, L::kTotal, st, 1, p);
+}
+
+static int launch_strip_inst(const ConvKernelParams& p, int num_sms, cudaStream_t st) {
+  using L = StripSmem;
+  static_assert(L::kTotal <= 232448, "strip conv kernel shared memory exceeds 227 KB");
+  static unsigned long long configured = 0;
+  if (first_use_on_device(&configured)) {
+    CER_CUDA(cudaFuncSetAttribute(conv_strip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
+  }
+  const long long vrows = (long long)p.halo_frames * p.halo_cts * p.Hout;
+  const int tiles = (int)((vrows + 15) / 16);
+  return launch_conv_kernel(conv_strip_kernel, std::min(tiles, num_sms), kHaloThreads, L::kTotal, st, 1, p);
+}
+
+// CER_STRIP=0: keep the halo kernel for the 64 -> 64 layers (A/B timing).
+static bool strip_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("CER_STRIP"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v == 1;
 }
 
 // CER_HALO: unset/1 = halo kernel for the Cin = 64 layers, 0 = im2col kernel (A/B timing).
@@ -455,11 +497,11 @@ static bool pair_mode_enabled() {
 // launching so that the plan can REPORT its choice (cer_ir50_op_variant / cer_conv_last_variant):
 // bench.py labels its roofline line with the variant that actually ran.
 enum ConvVariant {
-  kVarNone = 0, kVarHalo64, kVarHalo128, kVarPairBres128, kVarPair256, kVarPair128,
+  kVarNone = 0, kVarStrip64, kVarHalo64, kVarHalo128, kVarPairBres128, kVarPair256, kVarPair128,
   kVar256Aligned, kVar256, kVar128Bres, kVar128Aligned, kVar128, kVar64Bres9, kVar64Aligned, kVar64
 };
 static const char* const kVariantNames[] = {
-  "none", "conv_halo_kernel<64>", "conv_halo_kernel<128>", "conv_igemm2_bres_kernel<128,4,18>",
+  "none", "conv_strip_kernel", "conv_halo_kernel<64>", "conv_halo_kernel<128>", "conv_igemm2_bres_kernel<128,4,18>",
   "conv_igemm2_kernel<256,6>", "conv_igemm2_kernel<128,6>", "conv_igemm_kernel<256,4,0,1>", "conv_igemm_kernel<256,4,0,0>",
   "conv_igemm_kernel<128,4,1,0>", "conv_igemm_kernel<128,6,0,1>", "conv_igemm_kernel<128,6,0,0>",
   "conv_igemm_kernel<64,9,1,1>", "conv_igemm_kernel<64,8,0,1>", "conv_igemm_kernel<64,8,0,0>"};
@@ -469,8 +511,10 @@ static ConvVariant select_conv_variant(const ConvOp& op, int frames, int num_sms
   const int num_m_tiles = (frames * op.hw_out + kBlockM - 1) / kBlockM;
   const int tiles = num_m_tiles * p.num_n_tiles;
   if (tiles == 0) return kVarNone;
-  if (op.halo_ok && ((halo_mode() != 0 && tiles >= 2 * num_sms) || (p.pool_xor && p.cin_chunks == 1)))
+  if (op.halo_ok && ((halo_mode() != 0 && tiles >= 2 * num_sms) || (p.pool_xor && p.cin_chunks == 1))) {
+    if (op.strip_ok && !p.pool_xor && strip_enabled() && halo_mode() != 0 && tiles >= 2 * num_sms) return kVarStrip64;
     return op.bn == 64 ? kVarHalo64 : kVarHalo128;
+  }
   const int grid = std::min(tiles, num_sms);
   const int ksteps = p.ksteps_main + p.ksteps2;
   // CTA-pair (cta_group::2) variant: plain 3x3 / 1x1 layers whose k-steps fill the 6-stage ring a whole
@@ -505,6 +549,11 @@ int launch_conv(const ConvOp& op, int frames, int num_sms, cudaStream_t st) {
   const int grid = std::min(tiles, num_sms);
   switch (var) {
     case kVarNone: return CER_OK;
+    case kVarStrip64:
+      p.tmap_a = op.tmap_strip;
+      p.halo_frames = frames;
+      p.halo_cts = p.Wout / kHaloTileW;
+      return launch_strip_inst(p, num_sms, st);
     case kVarHalo64:
     case kVarHalo128:
       p.tmap_a = op.tmap_halo;

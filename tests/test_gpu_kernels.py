@@ -75,6 +75,9 @@ CONV_CASES = [
     (48, 40, 64, 64, 3, 1, 9, True, False, False),      # 600 tiles >= 4 waves: weights-resident variant, BN = 64
     (48, 40, 64, 64, 3, 1, 1, False, True, False),      # same with residual epilogue
     (48, 40, 64, 128, 3, 1, 9, True, False, False),     # weights-resident variant, BN = 128
+    (49, 40, 64, 64, 3, 1, 9, True, False, False),      # strip kernel, odd frame count: the last tile is half empty
+    (49, 40, 64, 64, 3, 1, 1, False, True, False),      # same with residual
+    (21, 56, 64, 64, 3, 1, 9, True, False, False),      # strip kernel on a 56-row map: tiles cross strips and frames mid-tile
     (800, 10, 256, 256, 3, 1, 9, True, False, False),   # 625 tiles (odd): CTA-pair (cta_group::2) variant, ragged last pair
     (800, 10, 256, 256, 3, 1, 1, False, True, False),   # CTA-pair variant with residual epilogue
     (200, 20, 128, 128, 3, 1, 9, True, False, False),   # CTA-pair variant, BN = 128
