@@ -245,6 +245,11 @@ __global__ void __launch_bounds__(256) add_layernorm_kernel(const float* __restr
     out[(long long)r * dim + i] = (xp[i] + (rp ? rp[i] : 0.f) - mean) * rstd * gamma[i] + beta[i];
 }
 
+// a += b (gradient accumulation where two branches meet)
+__global__ void add_inplace_kernel(float* __restrict__ a, const float* __restrict__ b, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) a[i] += b[i];
+}
+
 // y = tanh(y) in place (the REGRESSION task's output squashing, models/model.py:523, :682, :1165)
 __global__ void tanh_inplace_kernel(float* __restrict__ y, long long n) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
@@ -342,6 +347,15 @@ extern "C" int cer_add_layernorm(const float* x_dev, const float* res_dev, int64
   if (rows == 0) return CER_OK;
   add_layernorm_kernel<<<(int)((rows + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(x_dev, res_dev, (int)rows, dim,
                                                                                             gamma_dev, beta_dev, eps, out_dev);
+  CER_CUDA(cudaGetLastError());
+  return CER_OK;
+}
+
+extern "C" int cer_add_inplace(float* a_dev, const float* b_dev, int64_t n, void* stream) {
+  if (!a_dev || !b_dev || n < 0) return set_error(CER_ERR_INVALID, "cer_add_inplace: bad argument");
+  if (n == 0) return CER_OK;
+  const int blocks = (int)((n + 255) / 256 < 148 * 8 ? (n + 255) / 256 : 148 * 8);
+  add_inplace_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(a_dev, b_dev, (long long)n);
   CER_CUDA(cudaGetLastError());
   return CER_OK;
 }

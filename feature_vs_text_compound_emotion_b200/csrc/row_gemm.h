@@ -30,6 +30,7 @@ struct RowGemm {
   float* aux; int ld_aux;                   // BLOCK_OUT: h2d out; DGRAD_ACT: saved activation in
   Drop drop;
   int tf32;                                 // 1: TF32 tensor-core kernel (mma.sync, fp32 accumulate); 0: exact fp32 FFMA2
+  int ldb;                                  // row pitch of B (0 = dense: K for [N][K] storage, N for [K][N])
 };
 
 

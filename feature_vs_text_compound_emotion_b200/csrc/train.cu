@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(2 * BM) row_gemm_kernel(const RowGemm g) {
   // B tile: 16 k x 64 n = 256 float4; threads beyond 256 float4 slots (none) / fewer threads loop twice (BM = 64).
   // [K][N] storage: slot -> one k, 4 consecutive n;  [N][K] storage: one n, 4 consecutive k.
   constexpr int BP = 256 / NT;                           // B float4 slots per thread (1 or 2)
-  const int b_ld = B_KN ? g.N : g.K;
+  const int b_ld = g.ldb ? g.ldb : (B_KN ? g.N : g.K);
   const bool b_vec = (b_ld & 3) == 0 && (reinterpret_cast<uintptr_t>(g.B) & 15) == 0 && (g.b_tap_stride & 3) == 0;
 
   const int ksteps = (g.K + kGK - 1) / kGK;
@@ -136,7 +136,7 @@ __global__ void __launch_bounds__(2 * BM) row_gemm_kernel(const RowGemm g) {
       float4& rb = rbv[u];
       if (B_KN) {
         const int k = k0 + b_a, n = col0 + b_b;
-        const float* q = bp + (long long)k * g.N + n;
+        const float* q = bp + (long long)k * (g.ldb ? g.ldb : g.N) + n;
         if (k < g.K && b_vec && n + 3 < g.N) rb = __ldg(reinterpret_cast<const float4*>(q));
         else {
           rb.x = (k < g.K && n + 0 < g.N) ? __ldg(q + 0) : 0.f;
@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(2 * BM) row_gemm_kernel(const RowGemm g) {
         }
       } else {
         const int n = col0 + b_a, k = k0 + b_b;
-        const float* q = bp + (long long)n * g.K + k;
+        const float* q = bp + (long long)n * (g.ldb ? g.ldb : g.K) + k;
         if (n < g.N && b_vec && k + 3 < g.K) rb = __ldg(reinterpret_cast<const float4*>(q));
         else {
           rb.x = (n < g.N && k + 0 < g.K) ? __ldg(q + 0) : 0.f;
@@ -294,7 +294,7 @@ __global__ void __launch_bounds__(2 * BM) row_gemm_tf32_kernel(const RowGemm g) 
 #pragma unroll
   for (int h = 0; h < 2; ++h) { const int r = row0 + a_r + AH * h; a_t[h] = r < g.R ? r % g.T : -(1 << 30); }
   constexpr int BP = 256 / NT;
-  const int b_ld = B_KN ? g.N : g.K;
+  const int b_ld = g.ldb ? g.ldb : (B_KN ? g.N : g.K);
   const bool b_vec = (b_ld & 3) == 0 && (reinterpret_cast<uintptr_t>(g.B) & 15) == 0 && (g.b_tap_stride & 3) == 0;
   const int ksteps = (g.K + kGK - 1) / kGK;
   const int total = g.taps * ksteps;
@@ -324,7 +324,7 @@ __global__ void __launch_bounds__(2 * BM) row_gemm_tf32_kernel(const RowGemm g) 
       float4& rb = rbv[u];
       if (B_KN) {
         const int k = k0 + b_a, n = col0 + b_b;
-        const float* q = bp + (long long)k * g.N + n;
+        const float* q = bp + (long long)k * (g.ldb ? g.ldb : g.N) + n;
         if (k < g.K && b_vec && n + 3 < g.N) rb = __ldg(reinterpret_cast<const float4*>(q));
         else {
           rb.x = (k < g.K && n + 0 < g.N) ? __ldg(q + 0) : 0.f;
@@ -334,7 +334,7 @@ __global__ void __launch_bounds__(2 * BM) row_gemm_tf32_kernel(const RowGemm g) 
         }
       } else {
         const int n = col0 + b_a, k = k0 + b_b;
-        const float* q = bp + (long long)n * g.K + k;
+        const float* q = bp + (long long)n * (g.ldb ? g.ldb : g.K) + k;
         if (n < g.N && b_vec && k + 3 < g.K) rb = __ldg(reinterpret_cast<const float4*>(q));
         else {
           rb.x = (n < g.N && k + 0 < g.K) ? __ldg(q + 0) : 0.f;
@@ -449,7 +449,7 @@ __global__ void __launch_bounds__(128 * kSplitG) row_gemm_splitk_kernel(const Ro
 #pragma unroll
   for (int h = 0; h < 2; ++h) { const int r = row0 + a_r + AH * h; a_t[h] = r < g.R ? r % g.T : -(1 << 30); }
   constexpr int BP = 256 / NT;
-  const int b_ld = B_KN ? g.N : g.K;
+  const int b_ld = g.ldb ? g.ldb : (B_KN ? g.N : g.K);
   const bool b_vec = (b_ld & 3) == 0 && (reinterpret_cast<uintptr_t>(g.B) & 15) == 0 && (g.b_tap_stride & 3) == 0;
   const int ksteps = (g.K + kGK - 1) / kGK;
   const int total = g.taps * ksteps;
@@ -479,7 +479,7 @@ __global__ void __launch_bounds__(128 * kSplitG) row_gemm_splitk_kernel(const Ro
       float4& rb = rbv[u];
       if (B_KN) {
         const int k = k0 + b_a, n = col0 + b_b;
-        const float* q = bp + (long long)k * g.N + n;
+        const float* q = bp + (long long)k * (g.ldb ? g.ldb : g.N) + n;
         if (k < g.K && b_vec && n + 3 < g.N) rb = __ldg(reinterpret_cast<const float4*>(q));
         else {
           rb.x = (k < g.K && n + 0 < g.N) ? __ldg(q + 0) : 0.f;
@@ -489,7 +489,7 @@ __global__ void __launch_bounds__(128 * kSplitG) row_gemm_splitk_kernel(const Ro
         }
       } else {
         const int n = col0 + b_a, k = k0 + b_b;
-        const float* q = bp + (long long)n * g.K + k;
+        const float* q = bp + (long long)n * (g.ldb ? g.ldb : g.K) + k;
         if (n < g.N && b_vec && k + 3 < g.K) rb = __ldg(reinterpret_cast<const float4*>(q));
         else {
           rb.x = (n < g.N && k + 0 < g.K) ? __ldg(q + 0) : 0.f;
@@ -610,6 +610,7 @@ struct WGrad {
   int k_tiles;
   int rows_per_split;
   int tf32;                                 // 1: TF32 tensor-core kernel
+  int ldw;                                  // row pitch of dW (0 = dense, K)
 };
 
 __global__ void __launch_bounds__(256) wgrad_kernel(const WGrad g) {
@@ -684,7 +685,7 @@ __global__ void __launch_bounds__(256) wgrad_kernel(const WGrad g) {
       for (int q = 0; q < 4; ++q) {
         const int k = k0 + tx * 4 + q;
         const float2 pr = unpack2(acc[i][q]);
-        if (k < g.K) atomicAdd(wp + (long long)n * g.K + k, half ? pr.y : pr.x);
+        if (k < g.K) atomicAdd(wp + (long long)n * (g.ldw ? g.ldw : g.K) + k, half ? pr.y : pr.x);
       }
     }
   }
@@ -767,7 +768,7 @@ __global__ void __launch_bounds__(256) wgrad_tf32_kernel(const WGrad g) {
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
           const int k = k0 + wn + ni * 8 + 2 * tq + c;
-          if (k < g.K) atomicAdd(wp + (long long)n * g.K + k, acc[mi][ni][2 * half + c]);
+          if (k < g.K) atomicAdd(wp + (long long)n * (g.ldw ? g.ldw : g.K) + k, acc[mi][ni][2 * half + c]);
         }
     }
 }
@@ -1434,8 +1435,41 @@ extern "C" void cer_head_train_destroy(cer_head_train* p) {
 
 #define RC(x) do { int _rc = (x); if (_rc) return _rc; } while (0)
 
+static int head_train_forward_impl(cer_head_train* p, const float* const* feats, uint32_t seed, float* logits, float* const* z_out,
+                                   void* stream);
+static int head_train_backward_impl(cer_head_train* p, const float* const* feats, const float* dlogits, const float* const* dz,
+                                    void* stream);
+
 extern "C" int cer_head_train_forward(cer_head_train* p, const float* const* feats, uint32_t seed, float* logits, void* stream) {
-  if (!p || !feats || !logits) return set_error(CER_ERR_INVALID, "cer_head_train_forward: bad argument");
+  if (!logits) return set_error(CER_ERR_INVALID, "cer_head_train_forward: bad argument");
+  return head_train_forward_impl(p, feats, seed, logits, nullptr, stream);
+}
+
+// TemporalConvNet + BatchNorm1d of every modality only (what CAN / JMT / MT share with LFAN, models/model.py:672-676,
+// :1155-1159): z_out[m] receives fp32 [batch*length][c_last[m]] (dense).
+extern "C" int cer_head_train_tcn_forward(cer_head_train* p, const float* const* feats, uint32_t seed, float* const* z_out,
+                                          void* stream) {
+  if (!z_out) return set_error(CER_ERR_INVALID, "cer_head_train_tcn_forward: bad argument");
+  return head_train_forward_impl(p, feats, seed, nullptr, z_out, stream);
+}
+
+extern "C" int cer_head_train_backward(cer_head_train* p, const float* const* feats, const float* dlogits, void* stream) {
+  if (!dlogits) return set_error(CER_ERR_INVALID, "cer_head_train_backward: bad argument");
+  return head_train_backward_impl(p, feats, dlogits, nullptr, stream);
+}
+
+// Backward of cer_head_train_tcn_forward: dz[m] = d loss / d z[m].  Does NOT clear the flat gradient buffer (the
+// caller zeroes it once per step and other blocks add their gradients to it); bias / downsample gradients are
+// accumulated, weight_g / weight_v / BatchNorm gradients are written.
+extern "C" int cer_head_train_tcn_backward(cer_head_train* p, const float* const* feats, const float* const* dz, void* stream) {
+  if (!dz) return set_error(CER_ERR_INVALID, "cer_head_train_tcn_backward: bad argument");
+  return head_train_backward_impl(p, feats, nullptr, dz, stream);
+}
+
+static int head_train_forward_impl(cer_head_train* p, const float* const* feats, uint32_t seed, float* logits, float* const* z_out,
+                                   void* stream) {
+  if (!p || !feats) return set_error(CER_ERR_INVALID, "cer_head_train_forward: bad argument");
+  const bool tcn_only = z_out != nullptr;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const cer_head_train_spec& s = p->s;
   const int R = p->R, T = p->T, k = s.kernel_size;
@@ -1482,9 +1516,15 @@ extern "C" int cer_head_train_forward(cer_head_train* p, const float* const* fea
       x = bb.y;
     }
     const int C = M.blocks[M.n_blocks - 1].c_out;
-    bn_train_fwd_kernel<<<(C + 31) / 32, dim3(32, 8), 0, st>>>(x, C, R, C, M.bn_w, M.bn_b, mb.z, mb.ld_z, mb.bn_mean,
-                                                                mb.bn_invstd, M.bn_mean, M.bn_var, (float)s.bn_momentum);
+    if (tcn_only && !z_out[m]) return set_error(CER_ERR_INVALID, "cer_head_train_tcn_forward: null output pointer");
+    bn_train_fwd_kernel<<<(C + 31) / 32, dim3(32, 8), 0, st>>>(x, C, R, C, M.bn_w, M.bn_b, tcn_only ? z_out[m] : mb.z,
+                                                                tcn_only ? C : mb.ld_z, mb.bn_mean, mb.bn_invstd, M.bn_mean,
+                                                                M.bn_var, (float)s.bn_momentum);
     CER_CUDA(cudaGetLastError());
+    if (tcn_only) {
+      if (m > 0) CER_CUDA(cudaEventRecord(p->ev_join[m], st));
+      continue;
+    }
     RowGemm q{};
     q.R = R; q.T = T; q.taps = 1; q.A = mb.z; q.lda = mb.ld_z; q.K = C; q.B = M.wqkv; q.C = mb.qkv; q.ldc = p->md3;
     q.N = p->md3; q.bias = M.bqkv; q.epi = EPI_LINEAR;
@@ -1493,6 +1533,7 @@ extern "C" int cer_head_train_forward(cer_head_train* p, const float* const* fea
   }
   st = main_st;
   for (int m = 1; m < s.n_modals; ++m) CER_CUDA(cudaStreamWaitEvent(st, p->ev_join[m], 0));
+  if (tcn_only) return CER_OK;
   AttnArgs a{};
   for (int m = 0; m < s.n_modals; ++m) a.qkv[m] = p->mod[m].qkv;
   a.vals = p->vals; a.R = R; a.M = s.n_modals; a.H = s.num_heads; a.hd = s.modal_dim / s.num_heads;
@@ -1513,14 +1554,17 @@ extern "C" int cer_head_train_forward(cer_head_train* p, const float* const* fea
   return CER_OK;
 }
 
-extern "C" int cer_head_train_backward(cer_head_train* p, const float* const* feats, const float* dlogits, void* stream) {
-  if (!p || !feats || !dlogits) return set_error(CER_ERR_INVALID, "cer_head_train_backward: bad argument");
+static int head_train_backward_impl(cer_head_train* p, const float* const* feats, const float* dlogits, const float* const* dz,
+                                    void* stream) {
+  if (!p || !feats) return set_error(CER_ERR_INVALID, "cer_head_train_backward: bad argument");
+  const bool tcn_only = dz != nullptr;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const cer_head_train_spec& s = p->s;
   const int R = p->R, T = p->T, k = s.kernel_size, E = p->E, c0 = p->ld_cat - E, sms = p->num_sms;
   const uint32_t seed = p->seed;
-  CER_CUDA(cudaMemsetAsync(s.grad_flat, 0, (size_t)s.grad_count * 4, st));
+  if (!tcn_only) CER_CUDA(cudaMemsetAsync(s.grad_flat, 0, (size_t)s.grad_count * 4, st));
   CER_CUDA(cudaMemsetAsync(p->scratch_zero, 0, p->scratch_zero_bytes, st));
+  if (!tcn_only) {
 
   // classifier: logits = cat Wr^T + br
   { WGrad w{}; w.G = dlogits; w.ldg = s.n_out; w.A = p->cat; w.lda = p->ld_cat; w.dW = s.dwr; w.R = R; w.T = T; w.N = s.n_out;
@@ -1545,6 +1589,7 @@ extern "C" int cer_head_train_backward(cer_head_train* p, const float* const* fe
     a.gvals = p->gvals; a.R = R; a.M = s.n_modals; a.H = s.num_heads; a.hd = s.modal_dim / s.num_heads;
     attn_bwd_kernel<<<(R * a.H + 127) / 128, 128, 0, st>>>(a);
     CER_CUDA(cudaGetLastError()); }
+  }   // !tcn_only
 
   cudaStream_t main_st = st;
   CER_CUDA(cudaEventRecord(p->ev_fork, main_st));
@@ -1554,15 +1599,20 @@ extern "C" int cer_head_train_backward(cer_head_train* p, const float* const* fe
     const int C = M.blocks[M.n_blocks - 1].c_out;
     st = m == 0 ? main_st : p->side[m];
     if (m > 0) CER_CUDA(cudaStreamWaitEvent(st, p->ev_fork, 0));
+    const float* gz = mb.ga;        // [R][C]
+    if (tcn_only) {
+      if (!dz[m]) return set_error(CER_ERR_INVALID, "cer_head_train_tcn_backward: null gradient pointer");
+      gz = dz[m];
+    } else {
     // qkv projection
     { WGrad w{}; w.G = mb.gqkv; w.ldg = p->md3; w.A = mb.z; w.lda = mb.ld_z; w.dW = M.dwqkv; w.R = R; w.T = T; w.N = p->md3;
       w.K = C; w.taps = 1; RC(launch_wgrad(w, sms, st)); }
     RC(launch_colsum(mb.gqkv, p->md3, R, p->md3, M.dbqkv, st));
-    float* gz = mb.ga;        // [R][C]
-    { RowGemm g{}; g.R = R; g.T = T; g.taps = 1; g.A = mb.gqkv; g.lda = p->md3; g.K = p->md3; g.B = M.wqkv; g.C = gz; g.ldc = C;
+    { RowGemm g{}; g.R = R; g.T = T; g.taps = 1; g.A = mb.gqkv; g.lda = p->md3; g.K = p->md3; g.B = M.wqkv; g.C = mb.ga; g.ldc = C;
       g.N = C; g.epi = EPI_LINEAR;
       if (m == 0) { g.addend = p->gcat; g.ld_add = p->ld_cat; }        // the leader also feeds the classifier directly
       RC(launch_row_gemm(g, true, st)); }
+    }
     // BatchNorm1d
     float* gy = mb.gb;
     bn_train_bwd_kernel<<<(C + 31) / 32, dim3(32, 8), 0, st>>>(gz, C, mb.blk[M.n_blocks - 1].y, C, R, C, M.bn_w, mb.bn_mean,
@@ -1691,5 +1741,290 @@ extern "C" int cer_modal_attention_forward(const float* const* qkv_dev, int64_t 
   a.vals = vals_out_dev; a.R = (int)rows; a.M = n_modals; a.H = num_heads; a.hd = head_dim;
   attn_fwd_kernel<<<(int)((rows * num_heads + 127) / 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(a);
   CER_CUDA(cudaGetLastError());
+  return CER_OK;
+}
+
+// ==========================================================================================
+// Building blocks WITH backward for training the alternative heads CAN / JMT / MT
+// (models/model.py:529-684, :709-750, :895-1167; the reference trains them through the same loop as LFAN,
+// experiment.py:317-347).  The host side (heads_training.py) composes them into forward / backward; every GEMM
+// runs in the kernels above (row GEMM, weight gradient with fp32 atomics, column sums).
+// Gradients of PARAMETERS are accumulated (+=) into buffers the caller zeroes once per step; gradients of
+// ACTIVATIONS are written unless stated otherwise.
+// ==========================================================================================
+namespace {
+
+// dx = dy * act'(.) where the sign of the saved OUTPUT decides (LeakyReLU and ReLU keep the sign of their input)
+__global__ void act_bwd_kernel(int act, const float* __restrict__ y, const float* __restrict__ dy, long long n, float* __restrict__ dx) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    dx[i] = dy[i] * (y[i] > 0.f ? 1.f : (act == 1 ? kLeaky : 0.f));
+}
+__global__ void leaky_fwd_kernel(const float* __restrict__ x, long long n, float* __restrict__ y) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) y[i] = lrelu(x[i]);
+}
+
+// y = softmax(gate) * feat  =>  dfeat = dy * s,  dgate = s * (t - sum(t * s)),  t = dy * feat   (one warp per row)
+__global__ void __launch_bounds__(256) softmax_gate_bwd_kernel(const float* __restrict__ gate, const float* __restrict__ feat,
+                                                               const float* __restrict__ dy, int rows, int dim,
+                                                               float* __restrict__ dgate, float* __restrict__ dfeat) {
+  const int r = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (r >= rows) return;
+  const long long o = (long long)r * dim;
+  float mx = -3.4e38f;
+  for (int i = lane; i < dim; i += 32) mx = fmaxf(mx, gate[o + i]);
+#pragma unroll
+  for (int k = 16; k > 0; k >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, k));
+  float den = 0.f;
+  for (int i = lane; i < dim; i += 32) den += expf(gate[o + i] - mx);
+#pragma unroll
+  for (int k = 16; k > 0; k >>= 1) den += __shfl_xor_sync(0xffffffffu, den, k);
+  const float inv = 1.f / den;
+  float dot = 0.f;
+  for (int i = lane; i < dim; i += 32) dot += dy[o + i] * feat[o + i] * expf(gate[o + i] - mx) * inv;
+#pragma unroll
+  for (int k = 16; k > 0; k >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, k);
+  for (int i = lane; i < dim; i += 32) {
+    const float sm = expf(gate[o + i] - mx) * inv;
+    dfeat[o + i] = dy[o + i] * sm;
+    dgate[o + i] = sm * (dy[o + i] * feat[o + i] - dot);
+  }
+}
+
+// y = LayerNorm(x + res) * gamma + beta  =>  dx (= dres), dgamma +=, dbeta +=.  One warp per row, lanes own the columns
+// lane, lane + 32, ... (dim <= 512); a block walks `rpb` rows and adds its column sums with one atomic per column.
+constexpr int kLnMaxCols = 16;
+__global__ void __launch_bounds__(256) add_ln_bwd_kernel(const float* __restrict__ x, const float* __restrict__ res, int rows, int dim,
+                                                         const float* __restrict__ gamma, float eps, const float* __restrict__ dy,
+                                                         float* __restrict__ dx, float* __restrict__ dgamma,
+                                                         float* __restrict__ dbeta, int rpb) {
+  __shared__ float s_g[512], s_b[512];
+  for (int i = threadIdx.x; i < dim; i += blockDim.x) { s_g[i] = 0.f; s_b[i] = 0.f; }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float ag[kLnMaxCols], ab[kLnMaxCols];
+#pragma unroll
+  for (int j = 0; j < kLnMaxCols; ++j) { ag[j] = 0.f; ab[j] = 0.f; }
+  const int r_end = min(rows, (blockIdx.x + 1) * rpb);
+  for (int r = blockIdx.x * rpb + warp; r < r_end; r += 8) {
+    const long long o = (long long)r * dim;
+    float h[kLnMaxCols], g[kLnMaxCols];
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < kLnMaxCols; ++j) {
+      const int c = lane + 32 * j;
+      h[j] = c < dim ? x[o + c] + (res ? res[o + c] : 0.f) : 0.f;
+      s += h[j];
+    }
+#pragma unroll
+    for (int k = 16; k > 0; k >>= 1) s += __shfl_xor_sync(0xffffffffu, s, k);
+    const float mean = s / dim;
+    float ss = 0.f;
+#pragma unroll
+    for (int j = 0; j < kLnMaxCols; ++j) { const int c = lane + 32 * j; if (c < dim) { const float d = h[j] - mean; ss += d * d; } }
+#pragma unroll
+    for (int k = 16; k > 0; k >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, k);
+    const float rstd = 1.f / sqrtf(ss / dim + eps);
+    float sg = 0.f, sgx = 0.f;
+#pragma unroll
+    for (int j = 0; j < kLnMaxCols; ++j) {
+      const int c = lane + 32 * j;
+      if (c < dim) {
+        const float xh = (h[j] - mean) * rstd, d = dy[o + c];
+        h[j] = xh;
+        g[j] = d * gamma[c];
+        sg += g[j]; sgx += g[j] * xh;
+        ag[j] += d * xh; ab[j] += d;
+      } else { g[j] = 0.f; }
+    }
+#pragma unroll
+    for (int k = 16; k > 0; k >>= 1) { sg += __shfl_xor_sync(0xffffffffu, sg, k); sgx += __shfl_xor_sync(0xffffffffu, sgx, k); }
+    const float mg = sg / dim, mgx = sgx / dim;
+#pragma unroll
+    for (int j = 0; j < kLnMaxCols; ++j) { const int c = lane + 32 * j; if (c < dim) dx[o + c] = rstd * (g[j] - mg - h[j] * mgx); }
+  }
+#pragma unroll
+  for (int j = 0; j < kLnMaxCols; ++j) { const int c = lane + 32 * j; if (c < dim) { atomicAdd(&s_g[c], ag[j]); atomicAdd(&s_b[c], ab[j]); } }
+  __syncthreads();
+  for (int i = threadIdx.x; i < dim; i += blockDim.x) { atomicAdd(dgamma + i, s_g[i]); atomicAdd(dbeta + i, s_b[i]); }
+}
+
+// P = softmax(S * scale) row-wise, in place; one warp per row
+__global__ void __launch_bounds__(256) softmax_rows_kernel(float* __restrict__ S, int rows, int cols, int ld, float scale) {
+  const int r = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (r >= rows) return;
+  float* p = S + (long long)r * ld;
+  float mx = -3.4e38f;
+  for (int i = lane; i < cols; i += 32) mx = fmaxf(mx, p[i] * scale);
+#pragma unroll
+  for (int k = 16; k > 0; k >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, k));
+  float den = 0.f;
+  for (int i = lane; i < cols; i += 32) { const float e = expf(p[i] * scale - mx); p[i] = e; den += e; }
+#pragma unroll
+  for (int k = 16; k > 0; k >>= 1) den += __shfl_xor_sync(0xffffffffu, den, k);
+  const float inv = 1.f / den;
+  for (int i = lane; i < cols; i += 32) p[i] *= inv;
+}
+// dS = P * (dP - sum(dP * P)) * scale row-wise, written over dP
+__global__ void __launch_bounds__(256) softmax_bwd_rows_kernel(const float* __restrict__ P, float* __restrict__ dP, int rows, int cols,
+                                                               int ld, float scale) {
+  const int r = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (r >= rows) return;
+  const float* p = P + (long long)r * ld;
+  float* d = dP + (long long)r * ld;
+  float dot = 0.f;
+  for (int i = lane; i < cols; i += 32) dot += d[i] * p[i];
+#pragma unroll
+  for (int k = 16; k > 0; k >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, k);
+  for (int i = lane; i < cols; i += 32) d[i] = p[i] * (d[i] - dot) * scale;
+}
+
+int block_sms() {
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  return sms;
+}
+
+}  // namespace
+
+extern "C" int cer_linear_backward(const float* x, int64_t rows, int32_t in_dim, int32_t ldx, const float* w, const float* dy,
+                                   int32_t out_dim, int32_t lddy, float* dx, int32_t lddx, int32_t dx_accumulate, float* dw, float* db,
+                                   void* stream) {
+  if (!dy || rows <= 0 || in_dim <= 0 || out_dim <= 0 || lddy < out_dim || rows > (1 << 24) || (dx && (!w || lddx < in_dim)) ||
+      (dw && (!x || ldx < in_dim)))
+    return set_error(CER_ERR_INVALID, "cer_linear_backward: bad argument");
+  int rc = cer_check_device();
+  if (rc) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dx) {      // dx = dy W  (W [out][in] read as [K = out][N = in])
+    RowGemm g{}; g.R = (int)rows; g.T = (int)rows; g.taps = 1; g.A = dy; g.lda = lddy; g.K = out_dim; g.B = w; g.C = dx; g.ldc = lddx;
+    g.N = in_dim; g.epi = EPI_LINEAR; g.accumulate = dx_accumulate ? 1 : 0;
+    RC(launch_row_gemm(g, true, st));
+  }
+  if (dw) {      // dw[out][in] += sum_r dy[r][out] x[r][in]
+    WGrad wg{}; wg.G = dy; wg.ldg = lddy; wg.A = x; wg.lda = ldx; wg.dW = dw; wg.R = (int)rows; wg.T = (int)rows; wg.N = out_dim;
+    wg.K = in_dim; wg.taps = 1;
+    RC(launch_wgrad(wg, block_sms(), st));
+  }
+  if (db) RC(launch_colsum(dy, lddy, (int)rows, out_dim, db, st));
+  return CER_OK;
+}
+
+extern "C" int cer_act_backward(int32_t act, const float* y, const float* dy, int64_t n, float* dx, void* stream) {
+  if (!y || !dy || !dx || n < 0 || (act != 1 && act != 2)) return set_error(CER_ERR_INVALID, "cer_act_backward: bad argument");
+  if (n == 0) return CER_OK;
+  act_bwd_kernel<<<(int)std::min<int64_t>((n + 255) / 256, 148 * 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(act, y, dy, n, dx);
+  CER_CUDA(cudaGetLastError());
+  return CER_OK;
+}
+
+extern "C" int cer_leaky_relu_forward(const float* x, int64_t n, float* y, void* stream) {
+  if (!x || !y || n < 0) return set_error(CER_ERR_INVALID, "cer_leaky_relu_forward: bad argument");
+  if (n == 0) return CER_OK;
+  leaky_fwd_kernel<<<(int)std::min<int64_t>((n + 255) / 256, 148 * 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, n, y);
+  CER_CUDA(cudaGetLastError());
+  return CER_OK;
+}
+
+extern "C" int cer_softmax_gate_backward(const float* gate, const float* feat, const float* dy, int64_t rows, int32_t dim, float* dgate,
+                                         float* dfeat, void* stream) {
+  if (!gate || !feat || !dy || !dgate || !dfeat || rows < 0 || dim <= 0 || rows > (1 << 30))
+    return set_error(CER_ERR_INVALID, "cer_softmax_gate_backward: bad argument");
+  if (rows == 0) return CER_OK;
+  softmax_gate_bwd_kernel<<<(int)((rows + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(gate, feat, dy, (int)rows, dim, dgate, dfeat);
+  CER_CUDA(cudaGetLastError());
+  return CER_OK;
+}
+
+extern "C" int cer_add_layernorm_backward(const float* x, const float* res, int64_t rows, int32_t dim, const float* gamma, float eps,
+                                          const float* dy, float* dx, float* dgamma, float* dbeta, void* stream) {
+  if (!x || !gamma || !dy || !dx || !dgamma || !dbeta || rows <= 0 || dim <= 0 || dim > 32 * kLnMaxCols || rows > (1 << 30))
+    return set_error(CER_ERR_INVALID, "cer_add_layernorm_backward: bad argument (dim <= 512)");
+  const int sms = block_sms();
+  const int rpb = (int)std::max<int64_t>(8, (rows + 4 * sms - 1) / (4 * sms));
+  add_ln_bwd_kernel<<<(int)((rows + rpb - 1) / rpb), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, res, (int)rows, dim, gamma, eps, dy, dx,
+                                                                                             dgamma, dbeta, rpb);
+  CER_CUDA(cudaGetLastError());
+  return CER_OK;
+}
+
+extern "C" int cer_bn1d_train_forward(const float* x, int64_t rows, int32_t c, const float* w, const float* b, float* y, float* save_mean,
+                                      float* save_invstd, float* running_mean, float* running_var, float momentum, void* stream) {
+  if (!x || !w || !b || !y || !save_mean || !save_invstd || !running_mean || !running_var || rows <= 0 || c <= 0 || rows > (1 << 24))
+    return set_error(CER_ERR_INVALID, "cer_bn1d_train_forward: bad argument");
+  bn_train_fwd_kernel<<<(c + 31) / 32, dim3(32, 8), 0, static_cast<cudaStream_t>(stream)>>>(x, c, (int)rows, c, w, b, y, c, save_mean,
+                                                                                        save_invstd, running_mean, running_var, momentum);
+  CER_CUDA(cudaGetLastError());
+  return CER_OK;
+}
+
+extern "C" int cer_bn1d_train_backward(const float* dy, const float* x, int64_t rows, int32_t c, const float* w, const float* save_mean,
+                                       const float* save_invstd, float* dx, float* dw, float* db, void* stream) {
+  if (!dy || !x || !w || !save_mean || !save_invstd || !dx || !dw || !db || rows <= 0 || c <= 0 || rows > (1 << 24))
+    return set_error(CER_ERR_INVALID, "cer_bn1d_train_backward: bad argument");
+  bn_train_bwd_kernel<<<(c + 31) / 32, dim3(32, 8), 0, static_cast<cudaStream_t>(stream)>>>(dy, c, x, c, (int)rows, c, w, save_mean, save_invstd,
+                                                                                        dx, c, dw, db);
+  CER_CUDA(cudaGetLastError());
+  return CER_OK;
+}
+
+// Single-head attention with the probabilities kept for backward (exact fp32 GEMMs):
+//   probs[b] = softmax(q[b] k[b]^T / sqrt(dim))  [len_q][len_k],   out[b] = probs[b] v[b].
+extern "C" int cer_sdpa_train_forward(const float* q, int32_t ldq, const float* k, int32_t ldk, const float* v, int32_t ldv, int32_t batch,
+                                      int32_t len_q, int32_t len_k, int32_t dim, float* out, int32_t ldo, float* probs, void* stream) {
+  if (!q || !k || !v || !out || !probs || batch <= 0 || len_q <= 0 || len_k <= 0 || dim <= 0 || ldq < dim || ldk < dim || ldv < dim || ldo < dim)
+    return set_error(CER_ERR_INVALID, "cer_sdpa_train_forward: bad argument");
+  int rc = cer_check_device();
+  if (rc) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const float scale = 1.f / sqrtf((float)dim);
+  for (int b = 0; b < batch; ++b) {
+    float* P = probs + (size_t)b * len_q * len_k;
+    { RowGemm g{}; g.R = len_q; g.T = len_q; g.taps = 1; g.A = q + (size_t)b * len_q * ldq; g.lda = ldq; g.K = dim;
+      g.B = k + (size_t)b * len_k * ldk; g.ldb = ldk; g.C = P; g.ldc = len_k; g.N = len_k; g.epi = EPI_LINEAR;
+      RC(launch_row_gemm(g, false, st)); }
+    softmax_rows_kernel<<<(len_q + 7) / 8, 256, 0, st>>>(P, len_q, len_k, len_k, scale);
+    CER_CUDA(cudaGetLastError());
+    { RowGemm g{}; g.R = len_q; g.T = len_q; g.taps = 1; g.A = P; g.lda = len_k; g.K = len_k; g.B = v + (size_t)b * len_k * ldv;
+      g.ldb = ldv; g.C = out + (size_t)b * len_q * ldo; g.ldc = ldo; g.N = dim; g.epi = EPI_LINEAR;
+      RC(launch_row_gemm(g, true, st)); }
+  }
+  return CER_OK;
+}
+
+// Backward of cer_sdpa_train_forward.  dq is written; dk / dv are ACCUMULATED (zero them first, e.g. as part of a packed
+// d(qkv) buffer); scratch: [batch][len_q][len_k] floats.
+extern "C" int cer_sdpa_backward(const float* q, int32_t ldq, const float* k, int32_t ldk, const float* v, int32_t ldv, const float* probs,
+                                 const float* dout, int32_t lddo, int32_t batch, int32_t len_q, int32_t len_k, int32_t dim, float* dq,
+                                 int32_t lddq, float* dk, int32_t lddk, float* dv, int32_t lddv, float* scratch, void* stream) {
+  if (!q || !k || !v || !probs || !dout || !dq || !dk || !dv || !scratch || batch <= 0 || len_q <= 0 || len_k <= 0 || dim <= 0)
+    return set_error(CER_ERR_INVALID, "cer_sdpa_backward: bad argument");
+  int rc = cer_check_device();
+  if (rc) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int sms = block_sms();
+  const float scale = 1.f / sqrtf((float)dim);
+  for (int b = 0; b < batch; ++b) {
+    const float* P = probs + (size_t)b * len_q * len_k;
+    float* dS = scratch + (size_t)b * len_q * len_k;
+    const float* qb = q + (size_t)b * len_q * ldq;
+    const float* kb = k + (size_t)b * len_k * ldk;
+    const float* vb = v + (size_t)b * len_k * ldv;
+    const float* dob = dout + (size_t)b * len_q * lddo;
+    // dv[key][e] += sum_q P[q][key] dout[q][e]
+    { WGrad w{}; w.G = P; w.ldg = len_k; w.A = dob; w.lda = lddo; w.dW = dv + (size_t)b * len_k * lddv; w.ldw = lddv; w.R = len_q;
+      w.T = len_q; w.N = len_k; w.K = dim; w.taps = 1; RC(launch_wgrad(w, sms, st)); }
+    // dP = dout v^T
+    { RowGemm g{}; g.R = len_q; g.T = len_q; g.taps = 1; g.A = dob; g.lda = lddo; g.K = dim; g.B = vb; g.ldb = ldv; g.C = dS;
+      g.ldc = len_k; g.N = len_k; g.epi = EPI_LINEAR; RC(launch_row_gemm(g, false, st)); }
+    softmax_bwd_rows_kernel<<<(len_q + 7) / 8, 256, 0, st>>>(P, dS, len_q, len_k, len_k, scale);
+    CER_CUDA(cudaGetLastError());
+    // dq = dS k
+    { RowGemm g{}; g.R = len_q; g.T = len_q; g.taps = 1; g.A = dS; g.lda = len_k; g.K = len_k; g.B = kb; g.ldb = ldk;
+      g.C = dq + (size_t)b * len_q * lddq; g.ldc = lddq; g.N = dim; g.epi = EPI_LINEAR; RC(launch_row_gemm(g, true, st)); }
+    // dk[key][e] += sum_q dS[q][key] q[q][e]
+    { WGrad w{}; w.G = dS; w.ldg = len_k; w.A = qb; w.lda = ldq; w.dW = dk + (size_t)b * len_k * lddk; w.ldw = lddk; w.R = len_q;
+      w.T = len_q; w.N = len_k; w.K = dim; w.taps = 1; RC(launch_wgrad(w, sms, st)); }
+  }
   return CER_OK;
 }

@@ -513,3 +513,12 @@ def tanh_(y: torch.Tensor) -> torch.Tensor:
     with torch.cuda.device(y.device):
         check(lib().cer_tanh_inplace(y.data_ptr(), y.numel(), _capi.current_stream_ptr()), "cer_tanh_inplace")
     return y
+
+
+def add_(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """a += b on contiguous fp32 CUDA tensors of equal size (cer_add_inplace)."""
+    if not (a.is_contiguous() and b.is_contiguous()) or a.numel() != b.numel() or a.dtype != torch.float32 or b.dtype != torch.float32:
+        raise ValueError("add_: contiguous fp32 tensors of equal size expected")
+    with torch.cuda.device(a.device):
+        check(lib().cer_add_inplace(a.data_ptr(), b.data_ptr(), a.numel(), _capi.current_stream_ptr()), "cer_add_inplace")
+    return a

@@ -4,7 +4,8 @@ and JMT / MT (:709-750, :895-1167), selected by ``--model_name`` (experiment.py:
 Same constructors, ``forward`` signatures and ``state_dict()`` layouts as the reference (checked
 key by key against listings produced by the reference: tests/golden/heads.pt).  The torch
 sub-modules are parameter containers; forward runs the shared backbones / TCN engines and the fp32
-building blocks of csrc/heads.cu through the C-ABI.  Inference only.
+building blocks of csrc/heads.cu through the C-ABI.  Training (model.train() with grad enabled, or
+heads_training.AltHeadTrainer.step) runs the hand-written backward of the same blocks.
 
 Two exact savings over the reference's arithmetic (JMT / MT):
   * only the LAST slot of the stacked cross-attention outputs is returned (``out_feats[:, :, -1, :]``,
@@ -160,6 +161,8 @@ class _FeatureHead(_PackedModule):
             self.spatial["audio"] = vggish
 
     def _engines(self):
+        if self.__dict__.pop("_dirty", False):
+            self.repack()                      # a training forward moved the BatchNorm statistics (and weights usually follow)
         eng = self._fresh_engine()
         if eng is None:
             dev = self.fc2.weight.device
@@ -174,9 +177,8 @@ class _FeatureHead(_PackedModule):
             eng = self._set_engine((tcn, w, b))
         return eng
 
-    def _encode(self, X) -> Dict[str, torch.Tensor]:
-        """X as the reference receives it -> z[m] [B, T, C_m] (TCN + BatchNorm1d), time-major."""
-        self._check_inference()
+    def _backbones(self, X) -> Dict[str, torch.Tensor]:
+        """X as the reference receives it -> feats[m] [B, T, D_m]: the frozen backbones' inference kernels."""
         if 'video' in X:
             B, T = X['video'].shape[:2]
             X['video'] = self.spatial["visual"](X['video'].reshape(B * T, *X['video'].shape[2:])).view(B, T, -1).unsqueeze(1)
@@ -184,7 +186,25 @@ class _FeatureHead(_PackedModule):
             B, hh, T, ww = X['logmel'].shape
             patches = X['logmel'].permute(0, 2, 3, 1).contiguous().view(-1, ww, hh)
             X['logmel'] = self.spatial["audio"](patches).view(B, T, -1).unsqueeze(1)
-        return self._encode_features({m: X[m].squeeze(1) for m in X})
+        return {m: X[m].squeeze(1) for m in X}
+
+    def _encode(self, X) -> Dict[str, torch.Tensor]:
+        """X as the reference receives it -> z[m] [B, T, C_m] (TCN + BatchNorm1d), time-major."""
+        return self._encode_features(self._backbones(X))
+
+    def _training_forward(self, X):
+        """model.train() + grad enabled (trainer.py:365-391): the frozen backbones run their inference kernels under
+        no_grad (i.e. stay in eval mode), the head runs heads_training.AltHeadTrainer and is attached
+        to autograd."""
+        from . import heads_training
+        with torch.no_grad():
+            feats = self._backbones(X)
+        self.__dict__["_dirty"] = True
+        out = heads_training.forward_with_grad(self, feats)
+        return torch.tanh(out) if self.task == "REGRESSION" else out
+
+    def _is_training_call(self) -> bool:
+        return self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
 
     def _encode_features(self, feats) -> Dict[str, torch.Tensor]:
         """feats[m] [B, T, D_m] (visual = 512-d IR-50 embeddings) -> z[m] [B, T, C_m]."""
@@ -222,6 +242,8 @@ class CAN(_FeatureHead):
         self._load_backbones(modalities, visual_state_dict, audio_state_dict)
 
     def forward(self, X):
+        if self._is_training_call():
+            return self._training_forward(X)
         return self._fuse(self._encode(X))
 
     def _fuse(self, z):
@@ -257,6 +279,8 @@ class JMT(_FeatureHead):
         self._load_backbones(modalities, visual_state_dict, audio_state_dict)
 
     def forward(self, X):
+        if self._is_training_call():
+            return self._training_forward(X)
         return self._fuse(self._encode(X))
 
     def _fuse(self, z):

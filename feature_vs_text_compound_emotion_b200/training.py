@@ -126,7 +126,7 @@ class HeadTrainer:
             net = m.temporal[mod].network
             tm.in_dim, tm.n_blocks = m.embedding_dim[mod], len(net)
             if len(net) > _capi.CER_MAX_TCN_BLOCKS:
-                raise ValueError("at most 4 TemporalBlocks per modality")
+                raise ValueError(f"at most {_capi.CER_MAX_TCN_BLOCKS} TemporalBlocks per modality")
             for i, blk in enumerate(net):
                 b = tm.blocks[i]
                 p = f"temporal.{mod}.network.{i}."

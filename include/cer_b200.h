@@ -246,7 +246,7 @@ int cer_fusion_head_forward(const cer_fusion_weights* w, const float* const* fea
  * Dropout masks come from a counter hash of (seed, site, element) that oracle/lfan_oracle.py
  * restates; p_tcn = p_fusion = 0 disables dropout.
  * ------------------------------------------------------------------------------------------ */
-#define CER_MAX_TCN_BLOCKS 4
+#define CER_MAX_TCN_BLOCKS 6
 typedef struct cer_train_conv {
   const float *g, *v, *bias;        /* weight_g [cout], weight_v [cout][cin][k], bias [cout]       */
   float *dg, *dv, *dbias;
@@ -293,6 +293,46 @@ int cer_head_train_forward(cer_head_train* plan, const float* const* feats_dev, 
 /* dlogits_dev: fp32 [batch*length][n_out] = d loss / d logits; writes every gradient of the spec. */
 int cer_head_train_backward(cer_head_train* plan, const float* const* feats_dev, const float* dlogits_dev, void* stream);
 void cer_head_train_destroy(cer_head_train* plan);
+/* The TemporalConvNet + BatchNorm1d part of the plan alone -- what CAN / JMT / MT share with LFAN
+ * (models/model.py:672-676, :1155-1159): z_dev[m] receives fp32 [batch*length][c_last[m]] (dense).  The fusion
+ * fields of the spec (wo ... dbr, wqkv ...) may be NULL in a plan that is only used through these two calls. */
+int cer_head_train_tcn_forward(cer_head_train* plan, const float* const* feats_dev, uint32_t seed, float* const* z_dev, void* stream);
+/* dz_dev[m] = d loss / d z[m].  Unlike cer_head_train_backward this does NOT clear the flat gradient buffer: the caller
+ * zeroes it once per step and the other blocks of the head add into it. */
+int cer_head_train_tcn_backward(cer_head_train* plan, const float* const* feats_dev, const float* const* dz_dev, void* stream);
+
+/* ---- building blocks WITH backward, for training CAN / JMT / MT (experiment.py:317-347 trains them through the same loop).
+ * Parameter gradients are ACCUMULATED (+=) into caller-zeroed buffers; activation gradients are written. ---- */
+/* y = x W^T + b: dx[rows][in] (= or += if dx_accumulate) = dy W; dw[out][in] += dy^T x; db[out] += column sums of dy.
+ * Any of dx / dw / db may be NULL. */
+int cer_linear_backward(const float* x_dev, int64_t rows, int32_t in_dim, int32_t ldx, const float* w_dev, const float* dy_dev,
+                        int32_t out_dim, int32_t lddy, float* dx_dev, int32_t lddx, int32_t dx_accumulate, float* dw_dev, float* db_dev,
+                        void* stream);
+/* dx = dy * act'(.) from the saved OUTPUT y of the activation: act 1 = LeakyReLU(0.01), 2 = ReLU. */
+int cer_act_backward(int32_t act, const float* y_dev, const float* dy_dev, int64_t n, float* dx_dev, void* stream);
+int cer_leaky_relu_forward(const float* x_dev, int64_t n, float* y_dev, void* stream);
+/* backward of cer_softmax_gate (AttentionFusion, model.py:563-567) */
+int cer_softmax_gate_backward(const float* gate_dev, const float* feat_dev, const float* dy_dev, int64_t rows, int32_t dim,
+                              float* dgate_dev, float* dfeat_dev, void* stream);
+/* backward of cer_add_layernorm: dx (which is also d res), dgamma +=, dbeta +=; dim <= 512 */
+int cer_add_layernorm_backward(const float* x_dev, const float* res_dev, int64_t rows, int32_t dim, const float* gamma_dev, float eps,
+                               const float* dy_dev, float* dx_dev, float* dgamma_dev, float* dbeta_dev, void* stream);
+/* nn.BatchNorm1d in training mode over [rows][c] (batch statistics, running-stat update with the unbiased variance) */
+int cer_bn1d_train_forward(const float* x_dev, int64_t rows, int32_t c, const float* w_dev, const float* b_dev, float* y_dev,
+                           float* save_mean_dev, float* save_invstd_dev, float* running_mean_dev, float* running_var_dev, float momentum,
+                           void* stream);
+int cer_bn1d_train_backward(const float* dy_dev, const float* x_dev, int64_t rows, int32_t c, const float* w_dev,
+                            const float* save_mean_dev, const float* save_invstd_dev, float* dx_dev, float* dw_dev, float* db_dev,
+                            void* stream);
+/* single-head attention keeping the probabilities [batch][len_q][len_k] for backward (exact fp32 GEMMs) */
+int cer_sdpa_train_forward(const float* q_dev, int32_t ldq, const float* k_dev, int32_t ldk, const float* v_dev, int32_t ldv,
+                           int32_t batch, int32_t len_q, int32_t len_k, int32_t dim, float* out_dev, int32_t ldo, float* probs_dev,
+                           void* stream);
+/* dq is written, dk / dv are accumulated (zero them first); scratch_dev: [batch][len_q][len_k] floats */
+int cer_sdpa_backward(const float* q_dev, int32_t ldq, const float* k_dev, int32_t ldk, const float* v_dev, int32_t ldv,
+                      const float* probs_dev, const float* dout_dev, int32_t lddo, int32_t batch, int32_t len_q, int32_t len_k,
+                      int32_t dim, float* dq_dev, int32_t lddq, float* dk_dev, int32_t lddk, float* dv_dev, int32_t lddv,
+                      float* scratch_dev, void* stream);
 
 /* Mean cross-entropy over `rows` rows (<= 2^20) and (optionally) its gradient w.r.t. the logits
  * (nn.CrossEntropyLoss(reduction="mean"), experiment.py:133).  labels: int64 [rows].  Rows whose label is
@@ -347,6 +387,8 @@ int cer_sdpa_forward(const float* q_dev, int32_t ldq, const float* k_dev, int32_
 int cer_sdpa_tc_forward(const float* q_dev, int32_t ldq, const float* k_dev, int32_t ldk, const float* v_dev, int32_t ldv,
                         int32_t batch, int32_t len_q, int32_t len_k, int32_t dim, float* out_dev, int32_t ldo, void* stream);
 /* y = tanh(y) in place: the output squashing of task == REGRESSION (models/model.py:523, :682, :1165). */
+/* a += b over n contiguous fp32 values (where the gradients of two branches meet) */
+int cer_add_inplace(float* a_dev, const float* b_dev, int64_t n, void* stream);
 int cer_tanh_inplace(float* y_dev, int64_t n, void* stream);
 int cer_add_layernorm(const float* x_dev, const float* res_dev, int64_t rows, int32_t dim, const float* gamma_dev,
                       const float* beta_dev, float eps, float* out_dev, void* stream);

@@ -16,6 +16,7 @@ reference modules, imported as they are, are the source of truth):
   * logmel.pt       -- mel_features.log_mel_spectrogram + my_frame (the reference code) on a seeded 3 s waveform
   * heads.pt        -- CAN / JMT / MT forward from pixels (B=2 x T=24) and their state_dict key listings
   * heads_t300.pt   -- the same heads at the reference's window length (B=2 x T=300)
+  * heads_train.pt  -- one training step (loss, gradients, BatchNorm statistics) of CAN / JMT / MT on pre-encoded features
   * attention_maps.pt -- MultimodalTransformerEncoder.get_attention_maps on seeded encoder outputs
   * windowing.json  -- Trainer.windowing outputs for a set of lengths
 Weights are NOT stored: they are regenerated from the seed by
@@ -75,6 +76,72 @@ def _heads(TH, ref_configs, tmp, with_keys=True):
         if with_keys:
             heads[name]["keys"] = {k: list(v.shape) for k, v in jm.state_dict().items()}
     return heads
+
+
+def _heads_train(ref_configs, tmp):
+    """One training step (model.train(), mean cross-entropy, backward) of the REFERENCE CAN / JMT / MT on pre-encoded
+    features, B = 2 x T = 40.  The frozen visual backbone is replaced by a Flatten stub fed with [B, T, 512, 1, 1]
+    "frames", so that the head sees exactly the 512-d embeddings this repo's training path is given (the reference
+    would otherwise also flip IR-50's BatchNorms to batch statistics); Dropout p = 0 (torch's Philox masks cannot be
+    reproduced -- dropout ON is checked against the oracle, which restates the kernels' mask hash)."""
+    import torch.nn.functional as F
+    from models.model import CAN, JMT
+    ts = ref_configs.config["tcn_settings"]
+    out = {}
+    for name in ("CAN", "JMT", "MT"):
+        mods = ["video", "vggish", "bert"] if name == "CAN" else ["video", "vggish"]
+        if name == "CAN":
+            m = CAN(task="CLASSIFICATION", modalities=mods, tcn_settings=ts, backbone_settings=ref_configs.config["backbone_settings"],
+                    output_dim=7, root_dir=tmp, device="cpu")
+            sd = synthetic.can_state_dict(0, mods)
+        else:
+            m = JMT(task="CLASSIFICATION", modalities=mods, tcn_settings=ts, backbone_settings=ref_configs.config["backbone_settings"],
+                    output_dim=7, root_dir=tmp, device="cpu", model_name=name)
+            sd = synthetic.jmt_state_dict(0, mods, model_name=name)
+        m.load_state_dict(sd, strict=True)
+        m.spatial["visual"] = torch.nn.Flatten()
+        m.train()
+        for mod in m.modules():
+            if isinstance(mod, torch.nn.Dropout):
+                mod.p = 0.0
+        B, T = 2, 40
+        g = torch.Generator().manual_seed(811)
+        dims = {"video": 512, "vggish": 128, "bert": 768}
+        feats = {k: torch.randn(B, T, dims[k], generator=g) for k in mods}
+        labels = torch.randint(0, 7, (B, T, 1), generator=g)
+        X = {k: (v.view(B, T, 512, 1, 1) if k == "video" else v.unsqueeze(1)).clone() for k, v in feats.items()}
+        with torch.enable_grad():
+            logits = m(X)
+            loss = F.cross_entropy(logits.reshape(-1, 7), labels.reshape(-1))
+            loss.backward()
+        rec = {"modalities": mods, "seed": 811, "B": B, "T": T, "loss": float(loss), "logits": logits.detach().clone(),
+               "grad_norm": {}, "grad_small": {}, "grad_sample": {}, "none_grad": [], "bn": {}}
+        for k, p in m.named_parameters():
+            if k.startswith("spatial.") or ".net." in k:
+                continue
+            if p.grad is None:
+                rec["none_grad"].append(k)
+                continue
+            rec["grad_norm"][k] = float(p.grad.double().norm())
+            if p.grad.numel() <= 4096:
+                rec["grad_small"][k] = p.grad.detach().clone()
+            else:
+                rec["grad_sample"][k] = p.grad.detach().flatten()[::97].clone()
+        for k, v in m.state_dict().items():
+            if (k.startswith("bn.") or k.startswith("bn1.")) and ("running" in k):
+                rec["bn"][k] = v.detach().clone()
+        out[name] = rec
+        print("heads_train", name, rec["loss"], len(rec["grad_norm"]), "grads,", len(rec["none_grad"]), "without grad")
+    return out
+
+
+def only_heads_train():
+    """python oracle/gen_golden.py headstrain -- just tests/golden/heads_train.pt."""
+    torch.manual_seed(0)
+    import configs as ref_configs
+    tmp = tempfile.mkdtemp()
+    torch.save(synthetic.visual_backbone_state_dict(seed=0), os.path.join(tmp, "res50_ir_0.887.pth"))
+    torch.save(_heads_train(ref_configs, tmp), os.path.join(OUT, "heads_train.pt"))
 
 
 def only_heads_t300():
@@ -256,6 +323,8 @@ def main():
     print("heads", {k: (tuple(v["out"].shape), len(v["keys"])) for k, v in heads.items()})
     heads = _heads(300, ref_configs, tmp, with_keys=False)         # the reference's window length
     torch.save(heads, os.path.join(OUT, "heads_t300.pt"))
+    with torch.enable_grad():
+        torch.save(_heads_train(ref_configs, tmp), os.path.join(OUT, "heads_train.pt"))
     print("heads_t300", {k: tuple(v["out"].shape) for k, v in heads.items()})
 
     # ---- attention maps of the cross-modal encoder (transformer.py:211-215) ---------------------
@@ -283,5 +352,7 @@ def main():
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "heads300":
         only_heads_t300()
+    elif len(sys.argv) > 1 and sys.argv[1] == "headstrain":
+        only_heads_train()
     else:
         main()

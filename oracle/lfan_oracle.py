@@ -340,15 +340,11 @@ def _conv1d(x, w, b, padding, dilation, tf32):
     return F.conv1d(x, w, b, stride=1, padding=padding, dilation=dilation)
 
 
-def head_forward_train(P: SD, buffers: SD, feats: Dict[str, Tensor], modalities: Sequence[str],
-                       modal_dim: int = 32, num_heads: int = 2, seed=None,
-                       p_tcn: float = TCN_DROPOUT, p_fusion: float = FUSION_DROPOUT, tf32: bool = False) -> Tensor:
-    """LFAN.forward after the backbones in TRAINING mode (model.py:511-526 under model.train()):
-    Dropout active after both LeakyReLUs of every TemporalBlock (temporal_convolutional_model.py:
-    28,34) and on the attention output (transformer.py:194); BatchNorm1d uses batch statistics and
-    updates ``buffers`` (running_mean/var with the unbiased variance, momentum 0.1).
-    P: trainable tensors (reference names), feats[m]: [B, T, D_m].  Activations are kept
-    time-major [B, T, C] so that dropout indices match the kernels' layout."""
+def tcn_bn_train(P: SD, buffers: SD, feats: Dict[str, Tensor], modalities: Sequence[str], seed=None,
+                 p_tcn: float = TCN_DROPOUT, tf32: bool = False) -> Dict[str, Tensor]:
+    """TemporalConvNet + BatchNorm1d of every modality in TRAINING mode (what LFAN, CAN and JMT / MT share:
+    model.py:511-515, :672-676, :1155-1159): dropout after both LeakyReLUs of every block, batch statistics,
+    running-stat update in ``buffers``.  feats[m]: [B, T, D_m] -> enc[m]: [B, T, C_m]."""
     enc = {}
     for mi, m in enumerate(modalities):
         x = feats[m]
@@ -380,6 +376,19 @@ def head_forward_train(P: SD, buffers: SD, feats: Dict[str, Tensor], modalities:
         if f"bn.{m}.num_batches_tracked" in buffers:
             buffers[f"bn.{m}.num_batches_tracked"] += 1
         enc[m] = xb.transpose(1, 2)
+    return enc
+
+
+def head_forward_train(P: SD, buffers: SD, feats: Dict[str, Tensor], modalities: Sequence[str],
+                       modal_dim: int = 32, num_heads: int = 2, seed=None,
+                       p_tcn: float = TCN_DROPOUT, p_fusion: float = FUSION_DROPOUT, tf32: bool = False) -> Tensor:
+    """LFAN.forward after the backbones in TRAINING mode (model.py:511-526 under model.train()):
+    Dropout active after both LeakyReLUs of every TemporalBlock (temporal_convolutional_model.py:
+    28,34) and on the attention output (transformer.py:194); BatchNorm1d uses batch statistics and
+    updates ``buffers`` (running_mean/var with the unbiased variance, momentum 0.1).
+    P: trainable tensors (reference names), feats[m]: [B, T, D_m].  Activations are kept
+    time-major [B, T, C] so that dropout indices match the kernels' layout."""
+    enc = tcn_bn_train(P, buffers, feats, modalities, seed, p_tcn, tf32)
     hd = modal_dim // num_heads
     a = "fusion.layers.self_attn."
     qs, ks, vs = [], [], []
@@ -633,22 +642,33 @@ def _encode_modalities(sd: SD, X: Dict[str, Tensor], modalities: Sequence[str]) 
     return x
 
 
-def _head_tail(sd: SD, c: Tensor) -> Tensor:
-    """fc1 -> BatchNorm1d (eval) over the feature axis -> F.leaky_relu -> fc2 (model.py:678-681, :1161-1164)."""
+def _head_tail(sd: SD, c: Tensor, train_buffers: SD = None) -> Tensor:
+    """fc1 -> BatchNorm1d over the feature axis -> F.leaky_relu -> fc2 (model.py:678-681, :1161-1164).  Eval statistics,
+    or batch statistics (+ running-stat update in ``train_buffers``) in training mode."""
     c = F.linear(c, sd["fc1.weight"], sd["fc1.bias"]).transpose(1, 2)
-    c = _bn_eval(sd, "bn1", c).transpose(1, 2)
+    if train_buffers is None:
+        c = _bn_eval(sd, "bn1", c).transpose(1, 2)
+    else:
+        c = F.batch_norm(c, train_buffers["bn1.running_mean"], train_buffers["bn1.running_var"], sd["bn1.weight"], sd["bn1.bias"],
+                         True, BN_MOMENTUM, BN_EPS).transpose(1, 2)
+        if "bn1.num_batches_tracked" in train_buffers:
+            train_buffers["bn1.num_batches_tracked"] += 1
     return F.linear(F.leaky_relu(c, LEAKY_SLOPE), sd["fc2.weight"], sd["fc2.bias"])
 
 
 def can_forward(sd: SD, X: Dict[str, Tensor], modalities: Sequence[str]) -> Tensor:
     """CAN.forward (model.py:651-684) with AttentionFusion (:552-568): per-modality Linear to 128,
     concat, softmax(Linear(concat)) as an element-wise gate.  Returns [B, T, output_dim]."""
-    x = _encode_modalities(sd, X, modalities)
+    return can_fuse(sd, _encode_modalities(sd, X, modalities), modalities)
+
+
+def can_fuse(sd: SD, x: Dict[str, Tensor], modalities: Sequence[str], train_buffers: SD = None) -> Tensor:
+    """AttentionFusion + tail on the encoded modalities x[m]: [B, C_m, T]."""
     proj = [F.linear(x[m].transpose(1, 2), sd[f"fuse.attn.{i}.weight"], sd[f"fuse.attn.{i}.bias"])
             for i, m in enumerate(modalities)]
     cat = torch.cat(proj, -1)
     gate = torch.softmax(F.linear(cat, sd["fuse.weights.weight"], sd["fuse.weights.bias"]), dim=-1)
-    return _head_tail(sd, gate * cat)
+    return _head_tail(sd, gate * cat, train_buffers)
 
 
 def mha1(sd: SD, p: str, q_in: Tensor, k_in: Tensor, v_in: Tensor) -> Tensor:
@@ -677,7 +697,11 @@ def jmt_forward(sd: SD, X: Dict[str, Tensor], modalities: Sequence[str], model_n
     Note the reference's final stage: the stacked cross-attention outputs [L, B, S, E] are viewed
     as [L*B, S, E] and fed to sequence-first attention modules, so the final encoder and
     self-attention attend over all L*B positions, with the S stack slots as the batch."""
-    x = _encode_modalities(sd, X, modalities)
+    return jmt_fuse(sd, _encode_modalities(sd, X, modalities), model_name)
+
+
+def jmt_fuse(sd: SD, x: Dict[str, Tensor], model_name: str = "JMT", train_buffers: SD = None) -> Tensor:
+    """JMTFusion / MTFusion + tail on the encoded modalities x[m]: [B, C_m, T]."""
     f = "fuse."
     vis = x["video"].permute(2, 0, 1)
     aud = F.linear(x["vggish"].permute(2, 0, 1), sd[f + "augment_audio_feats_dim.weight"], sd[f + "augment_audio_feats_dim.bias"])
@@ -694,7 +718,43 @@ def jmt_forward(sd: SD, X: Dict[str, Tensor], modalities: Sequence[str], model_n
     st = st.view(-1, S, E)
     enc = encoder_block(sd, f + "final_encoder", st)
     out = mha1(sd, f + "final_self_attention", enc, enc, enc).view(L, B, S, E)[:, :, -1, :].permute(1, 0, 2)
-    return _head_tail(sd, out)
+    return _head_tail(sd, out, train_buffers)
+
+
+ALT_TCN_DROPOUT = 0.2       # TemporalConvNet's default, which CAN / JMT do not override (model.py:592-596, :1079-1083)
+
+
+def alt_head_trainable_names(sd: SD, name: str) -> List[str]:
+    """Trainable tensors of CAN / JMT / MT that take part in forward: everything but spatial.*, buffers, the net.{0,4}
+    aliases and the modules that are declared but never called (CAN's conv_c, MT's fuse.reduce_feats_dim: their .grad
+    stays None and torch's optimizers skip them)."""
+    skip = {"CAN": ("conv_c.",), "MT": ("fuse.reduce_feats_dim.",)}.get(name, ())     # MTFusion declares reduce_feats_dim, never calls it
+    return [k for k in trainable_names(sd) if not k.startswith(skip)]
+
+
+def alt_head_forward_train(name: str, P: SD, buffers: SD, feats: Dict[str, Tensor], modalities: Sequence[str], seed=None,
+                           p_tcn: float = ALT_TCN_DROPOUT, tf32: bool = False) -> Tensor:
+    """CAN / JMT / MT forward in TRAINING mode on pre-encoded features feats[m]: [B, T, D_m] (the frozen backbones
+    stay in eval mode): TCN dropout + BatchNorm1d batch statistics (bn.<m> and bn1)."""
+    enc = tcn_bn_train(P, buffers, feats, modalities, seed, p_tcn, tf32)
+    x = {m: enc[m].transpose(1, 2) for m in modalities}
+    if name == "CAN":
+        return can_fuse(P, x, modalities, buffers)
+    return jmt_fuse(P, x, name, buffers)
+
+
+def alt_head_train_grads(name: str, sd: SD, feats: Dict[str, Tensor], labels: Tensor, modalities: Sequence[str], seed=None,
+                         p_tcn: float = ALT_TCN_DROPOUT, tf32: bool = False):
+    """(loss, grads, buffers, logits) of one mean-cross-entropy training step of CAN / JMT / MT (trainer.py:365-391)."""
+    names = alt_head_trainable_names(sd, name)
+    P = {k: sd[k].detach().clone().requires_grad_(True) for k in names}
+    buffers = {k: v.detach().clone() for k, v in sd.items() if (k.startswith("bn.") or k.startswith("bn1.")) and k not in P}
+    with torch.enable_grad():
+        logits = alt_head_forward_train(name, P, buffers, feats, modalities, seed, p_tcn, tf32)
+        loss = F.cross_entropy(logits.reshape(-1, logits.shape[-1]), labels.reshape(-1).long())
+        gl = torch.autograd.grad(loss, [P[k] for k in names], allow_unused=True)
+    grads = {k: (g if g is not None else torch.zeros_like(P[k])) for k, g in zip(names, gl)}
+    return loss.detach(), grads, buffers, logits.detach()
 
 
 
