@@ -345,24 +345,26 @@ def test_ce_loss_ignore_index_and_out_of_range_labels():
     with torch.enable_grad():
         ref = torch.nn.functional.cross_entropy(ref_in, labels)
         ref.backward()
-    loss = torch.empty(1, device=dev)
-    dl = torch.full((777, 7), 9.0, device=dev)
-    _capi.check(_capi.lib().cer_ce_loss(logits.to(dev).data_ptr(), labels.to(dev).data_ptr(), 777, 7, loss.data_ptr(), dl.data_ptr(),
-                                        _capi.current_stream_ptr()))
+    ld = logits.to(dev)                                    # device operands stay referenced until the results are read
+
+    def ce(lab, want_grad):
+        lab_d = lab.to(dev)
+        loss = torch.empty(1, device=dev)
+        dl = torch.full((777, 7), 9.0, device=dev) if want_grad else None
+        _capi.check(_capi.lib().cer_ce_loss(ld.data_ptr(), lab_d.data_ptr(), 777, 7, loss.data_ptr(), None if dl is None else dl.data_ptr(),
+                                            _capi.current_stream_ptr()))
+        torch.cuda.synchronize()
+        return loss.cpu(), None if dl is None else dl.cpu()
+
+    loss, dl = ce(labels, True)
     assert abs(loss.item() - ref.item()) < 1e-5
-    assert (dl.cpu() - ref_in.grad).abs().max().item() < 1e-7
+    assert (dl - ref_in.grad).abs().max().item() < 1e-7
     # out-of-range labels are never used as an index: they behave like ignored rows
     lab2 = labels.clone()
     lab2[labels == -100] = 7
     lab2[0] = -3 if labels[0] == -100 else lab2[0]
-    loss2 = torch.empty(1, device=dev)
-    _capi.check(_capi.lib().cer_ce_loss(logits.to(dev).data_ptr(), lab2.to(dev).data_ptr(), 777, 7, loss2.data_ptr(), None,
-                                        _capi.current_stream_ptr()))
-    assert abs(loss2.item() - ref.item()) < 1e-5
-    none = torch.full((777,), -100)
-    _capi.check(_capi.lib().cer_ce_loss(logits.to(dev).data_ptr(), none.to(dev).data_ptr(), 777, 7, loss2.data_ptr(), None,
-                                        _capi.current_stream_ptr()))
-    assert torch.isnan(loss2).item()
+    assert abs(ce(lab2, False)[0].item() - ref.item()) < 1e-5
+    assert torch.isnan(ce(torch.full((777,), -100), False)[0]).item()
 
 
 # ----------------------------------------------------------------------------------------------
