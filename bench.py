@@ -513,8 +513,17 @@ def measure_alt_heads(dev, reps=10):
         feats = {k: torch.randn(WINDOWS, LENGTH, dims[k], device=dev) for k in mods}
         ms = _events_ms(lambda i: m.forward_features(dict(feats)), reps, warm=2)
         out[name] = {"ms_per_forward": ms, "frames_per_s": WINDOWS * LENGTH / ms * 1e3}
-        del m
-    out["workload"] = "alternative heads on pre-encoded features, 8 windows x 300 frames (head only: TCN + fusion + fc tail)"
+        # one optimisation step of the same head (forward in training mode, CE, hand-written backward, AdamW)
+        from feature_vs_text_compound_emotion_b200.heads_training import AltHeadTrainer
+        with torch.enable_grad():
+            tr = AltHeadTrainer(m.train(), WINDOWS, LENGTH, optimizer={"name": "adamw", "lr": 1e-4, "weight_decay": 1e-4})
+            labels = torch.randint(0, 7, (WINDOWS, LENGTH, 1), device=dev)
+            tms = _events_ms(lambda i: tr.step(feats, labels), 5, warm=2)
+        out[name]["train_ms_per_step"] = tms
+        out[name]["train_frames_per_s"] = WINDOWS * LENGTH / tms * 1e3
+        del m, tr
+    out["workload"] = ("alternative heads on pre-encoded features, 8 windows x 300 frames: head-only forward (TCN + fusion + fc tail) "
+                       "and one training step (TF32 TCN GEMMs, fp32 fusion; AdamW)")
     return out
 
 

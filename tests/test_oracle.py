@@ -275,6 +275,6 @@ def test_alt_head_training_oracle_matches_reference(golden_dir):
             ref = ref if ref is not None else g["grad_sample"][k]
             # CAN agrees to 2e-6; JMT / MT gradients are ill-conditioned in fp32 (two fp32 evaluation orders of the same
             # graph differ by up to ~2e-4 of a tensor norm, the fp64 result lies between them; see tests/test_gpu_heads_train.py)
-            assert float((mine - ref).abs().max()) <= (2e-5 if name == "CAN" else 1e-3) * gn + 1e-5 * scale, (name, k)
+            assert float((mine - ref).abs().max()) <= (2e-5 if name == "CAN" else 1e-3) * gn + 2e-5 * scale, (name, k)
         for k, v in g["bn"].items():
             assert (buffers[k] - v).abs().max().item() < 1e-5, (name, k)
