@@ -6,7 +6,7 @@ FLOP of the path runs in the hand-written kernels behind the C-ABI.
 from __future__ import annotations
 
 import ctypes as C
-from typing import Dict, List, Optional, Sequence
+from typing import List, Optional, Sequence
 
 import torch
 

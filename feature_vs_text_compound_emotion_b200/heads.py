@@ -18,7 +18,7 @@ Two exact savings over the reference's arithmetic (JMT / MT):
 from __future__ import annotations
 
 import os
-from typing import Dict, List
+from typing import Dict
 
 import torch
 from torch import nn

@@ -23,7 +23,7 @@ reference, and are therefore still subject to weight decay.
 from __future__ import annotations
 
 import ctypes as C
-from typing import Dict, List, Optional
+from typing import Dict, Optional
 
 import torch
 
@@ -33,7 +33,6 @@ from ._capi import HeadTrainSpec, check, lib
 from .training import OPT_KINDS, all_reduce_flat
 
 UNUSED = {"CAN": ("conv_c.",), "JMT": (), "MT": ("fuse.reduce_feats_dim.",)}
-ALT_TCN_DROPOUT = 0.2          # TemporalConvNet's default; CAN / JMT do not override it (model.py:592-596, :1079-1083)
 
 
 def _ptr(t):

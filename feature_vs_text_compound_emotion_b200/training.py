@@ -19,10 +19,9 @@ PyTorch is used for memory, streams and the NCCL all-reduce only.
 from __future__ import annotations
 
 import ctypes as C
-from typing import Dict, List, Optional, Sequence
+from typing import Dict, List, Optional
 
 import torch
-from torch import nn
 
 from . import _capi
 from ._capi import HeadTrainSpec, check, lib
