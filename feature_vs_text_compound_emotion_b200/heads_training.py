@@ -428,12 +428,15 @@ class AltHeadTrainer:
                   "cer_optimizer_step")
         self.model.repack()
 
-    def step(self, feats: Dict[str, torch.Tensor], labels: torch.Tensor, seed: Optional[int] = None) -> torch.Tensor:
-        """One optimisation step (trainer.py:365-391): returns the loss as a 1-element device tensor."""
+    def step(self, feats: Dict[str, torch.Tensor], labels: torch.Tensor, seed: Optional[int] = None,
+             sync_grads: bool = True) -> torch.Tensor:
+        """One optimisation step (trainer.py:365-391): returns the loss as a 1-element device tensor.
+        ``sync_grads=False`` skips the gradient all-reduce (a collective: every rank of the group must
+        call it) -- for a step that only some ranks of an initialised process group take."""
         logits = self.forward(feats, seed)
         loss, dl = self.cross_entropy(logits, labels)
         self.backward(dl)
-        self.apply_optimizer(all_reduce_flat(self.grads, self.group))
+        self.apply_optimizer(all_reduce_flat(self.grads, self.group) if sync_grads else 1.0)
         return loss
 
 

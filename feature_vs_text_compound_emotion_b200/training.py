@@ -266,12 +266,15 @@ class HeadTrainer:
                                            _capi.current_stream_ptr()), "cer_optimizer_step")
         self.model.repack()                                   # inference engines hold packed copies of the old weights
 
-    def step(self, X: Dict[str, torch.Tensor], labels: torch.Tensor, seed: Optional[int] = None) -> torch.Tensor:
-        """One optimisation step (trainer.py:365-391): returns the loss as a 1-element device tensor."""
+    def step(self, X: Dict[str, torch.Tensor], labels: torch.Tensor, seed: Optional[int] = None,
+             sync_grads: bool = True) -> torch.Tensor:
+        """One optimisation step (trainer.py:365-391): returns the loss as a 1-element device tensor.
+        ``sync_grads=False`` skips the gradient all-reduce (a collective: every rank of the group must
+        call it) -- for a step that only some ranks of an initialised process group take."""
         logits = self.forward(X, seed)
         loss, dl = self.cross_entropy(logits, labels)
         self.backward(dl)
-        scale = self.all_reduce_grads()
+        scale = self.all_reduce_grads() if sync_grads else 1.0
         self.apply_optimizer(scale)
         return loss
 

@@ -97,3 +97,38 @@ def test_flat_gradient_bucket_all_reduce_world_size_2_gloo():
     assert res == [(0, 0.5, True), (1, 0.5, True)]
     from feature_vs_text_compound_emotion_b200.training import all_reduce_flat
     assert all_reduce_flat(torch.ones(4)) == 1.0          # no process group: nothing to do
+
+
+def test_bench_rank0_only_section_has_no_collective():
+    """bench.py's records after `if rank != 0: return` run on rank 0 alone while the other ranks wait at the
+    final barrier: a collective there (e.g. a trainer step that all-reduces its gradients) deadlocks the
+    multi-GPU launch.  Source-level guard over the functions that section calls."""
+    import ast
+    import inspect
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = open(os.path.join(root, "bench.py")).read()
+    tree = ast.parse(src)
+    funcs = {n.name: n for n in tree.body if isinstance(n, ast.FunctionDef)}
+    run_infer = funcs["run_infer"]
+    cut = next(i for i, st in enumerate(run_infer.body)
+               if isinstance(st, ast.If) and "rank != 0" in ast.get_source_segment(src, st.test))
+    called = set()
+    for st in run_infer.body[cut + 1:]:
+        for n in ast.walk(st):
+            if isinstance(n, ast.Call) and isinstance(n.func, ast.Name) and n.func.id in funcs:
+                called.add(n.func.id)
+            if isinstance(n, ast.Name) and n.id in funcs:            # functions passed by name (side-record table)
+                called.add(n.id)
+    assert {"measure_head_only", "measure_alt_heads", "hbm_rooflines", "time_dominant_conv"} <= called
+    for name in sorted(called):
+        body = ast.get_source_segment(src, funcs[name])
+        assert "dist." not in body and "_timed(" not in body, f"{name} touches the process group"
+        for n in ast.walk(funcs[name]):
+            if isinstance(n, ast.Call) and isinstance(n.func, ast.Attribute) and n.func.attr == "step":
+                kw = {k.arg: k.value for k in n.keywords}
+                assert isinstance(kw.get("sync_grads"), ast.Constant) and kw["sync_grads"].value is False, \
+                    f"{name}: trainer.step() on rank 0 alone must pass sync_grads=False"
+    # and the switch exists on both trainers
+    from feature_vs_text_compound_emotion_b200 import heads_training, training
+    for cls in (training.HeadTrainer, heads_training.AltHeadTrainer):
+        assert "sync_grads" in inspect.signature(cls.step).parameters
