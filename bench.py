@@ -335,18 +335,26 @@ def measure_videos(dev, world, rank, local, dist, n_videos, steps, warmup, with_
     raw, lm, bert = raw_host.to(dev), lm_host.to(dev), bert_host.to(dev)
     votes = {}
 
+    group = max(1, int(os.environ.get("CER_VIDEOS_PER_CALL", "8")))
+
     def run_shard(_):
         local_out = {}
-        for i in mine:
-            T = lengths[i]
-            local_out[i] = windowing.infer_video(m, raw[:T], {"logmel": lm[:T], "bert": bert[:T]})
-            votes[i] = local_out[i]
+        for a in range(0, len(mine), group):
+            ids = mine[a:a + group]
+            if group == 1:
+                T = lengths[ids[0]]
+                outs = [windowing.infer_video(m, raw[:T], {"logmel": lm[:T], "bert": bert[:T]})]
+            else:                                          # frames of `group` videos share the backbone passes
+                outs = windowing.infer_videos(m, [raw[:lengths[i]] for i in ids],
+                                              [{"logmel": lm[:lengths[i]], "bert": bert[:lengths[i]]} for i in ids])
+            for i, o in zip(ids, outs):
+                local_out[i] = votes[i] = o
         return sharding.gather_predictions(local_out, lengths, 7, dev)
 
     total_ms, clocks = _timed(run_shard, steps, warmup, world, dist, dev, local)
     frames_total = sum(lengths)
     rec = {"value": frames_total * steps / (total_ms / 1e3), "ms_per_step": total_ms / steps, "clocks": clocks,
-           "frames_total": frames_total, "n_videos": n_videos,
+           "frames_total": frames_total, "n_videos": n_videos, "videos_per_call": group,
            "windows": sum(len(windowing.window_starts(t)) for t in lengths), "n_mine": sum(lengths[i] for i in mine)}
     if mine:
         rec["example_vote"] = windowing.video_level_prediction(votes[mine[0]])

@@ -113,3 +113,65 @@ def infer_video(model, video: torch.Tensor, feats: Dict[str, torch.Tensor], wind
     start_t = torch.as_tensor(starts, dtype=torch.int32, device=video.device)
     out = stitch_windows(logits, start_t, max(T, window_length))
     return out[:T]
+
+
+def window_index_table(lengths: Sequence[int], window_length: int = 300, hop_length: int = 200):
+    """Window grid of several videos laid end to end: (starts per video, int64 [n_windows_total, window_length]
+    of row numbers into the concatenated frame axis).  A video shorter than the window repeats its last
+    frame, as :func:`gather_windows` does."""
+    starts = [window_starts(int(t), window_length, hop_length) for t in lengths]
+    ar = torch.arange(window_length)
+    rows, off = [], 0
+    for t, st in zip(lengths, starts):
+        rows.append(off + torch.clamp(torch.as_tensor(st).view(-1, 1) + ar, max=int(t) - 1))
+        off += int(t)
+    return starts, torch.cat(rows)
+
+
+@torch.no_grad()
+def infer_videos(model, videos: Sequence[torch.Tensor], feats: Sequence[Dict[str, torch.Tensor]], window_length: int = 300,
+                 hop_length: int = 200, fps: float = 30.0, windows_per_pass: int = 16) -> List[torch.Tensor]:
+    """Several whole videos at once: the same result per video as :func:`infer_video` (the backbones are
+    per-frame and the head is per-window in eval mode, so batch composition cannot change a value), but the
+    frames of all videos go through IR-50 / VGGish back to back in full passes, the windows of all videos
+    go through the head in groups of ``windows_per_pass`` (one CUDA graph, the last group padded by
+    repeating its last window) and only the stitch is per video.  Short videos stop paying for
+    partly-filled launches.  Returns one [T_i, n_out] tensor per video."""
+    from .engine import stitch_windows
+    if len(videos) != len(feats):
+        raise ValueError("one feature dict per video")
+    if not videos:
+        return []
+    dev = videos[0].device
+    lengths = [int(v.shape[0]) for v in videos]
+    frames = torch.cat([preprocess_frames(model, v) if v.dtype == torch.uint8 else v for v in videos])
+    src = {}
+    for m in model.modality:
+        if m == "video":
+            src[m] = model.spatial["visual"](frames)                # every unique frame of every video once
+        elif m == "logmel":
+            ex = torch.cat([f[m] if m in f else wave_to_examples(model, f["wave"], t, fps) for f, t in zip(feats, lengths)])
+            src[m] = model.spatial["audio"](ex)
+        else:
+            src[m] = torch.cat([f[m] for f in feats])
+    del frames
+    starts, idx = window_index_table(lengths, window_length, hop_length)
+    idx = idx.to(dev, non_blocking=True)                            # [n_windows_total, window_length]
+    n_win = idx.shape[0]
+    group = max(1, min(int(windows_per_pass), n_win))
+    logits = None
+    for a in range(0, n_win, group):
+        sel = idx[a:a + group]
+        if sel.shape[0] < group:
+            sel = torch.cat([sel, sel[-1:].expand(group - sel.shape[0], -1)])
+        out = model.forward_features({m: src[m][sel] for m in model.modality})
+        if logits is None:
+            logits = torch.empty(n_win, window_length, out.shape[-1], device=dev)
+        logits[a:a + group] = out[:min(group, n_win - a)]
+    start_all = torch.as_tensor([s0 for st in starts for s0 in st], dtype=torch.int32).to(dev, non_blocking=True)
+    outs, w0 = [], 0
+    for i, st in enumerate(starts):
+        o = stitch_windows(logits[w0:w0 + len(st)], start_all[w0:w0 + len(st)], max(lengths[i], window_length))
+        outs.append(o[:lengths[i]])
+        w0 += len(st)
+    return outs

@@ -212,6 +212,29 @@ def test_infer_video_from_stored_uint8_crops_and_logmel():
     assert windowing.video_level_prediction(out.to(dev))["FRAMES_AVG_LOGITS"] == O.video_level_prediction(want.numpy())["FRAMES_AVG_LOGITS"]
 
 
+def test_infer_videos_equals_per_video_inference():
+    """windowing.infer_videos: the frames of several videos through the backbones in shared passes and their
+    windows through the head in fixed-size groups -- bit for bit what infer_video returns per video (a video
+    shorter than one window, exactly one window, grid + tail window; a padded last head group)."""
+    dev = _dev()
+    from feature_vs_text_compound_emotion_b200 import windowing
+    mods = ["video", "logmel", "bert"]
+    m = _lfan(mods, dev, seed=6)
+    lengths = [120, 300, 530, 301]
+    raw = synthetic.raw_frames_u8(64, seed=71).repeat(9, 1, 1, 1).to(dev)
+    lm = synthetic.logmel_patches(max(lengths), seed=72).to(dev)
+    bert = torch.randn(max(lengths), 768, generator=torch.Generator().manual_seed(73)).to(dev)
+    vids = [raw[7 * i:7 * i + t] for i, t in enumerate(lengths)]
+    feats = [{"logmel": lm[:t], "bert": bert[3 * i:3 * i + t] if 3 * i + t <= bert.shape[0] else bert[:t]} for i, t in enumerate(lengths)]
+    single = [windowing.infer_video(m, v, dict(f)) for v, f in zip(vids, feats)]
+    for wpp in (16, 4):                                   # 8 windows in total: one padded group / two full groups
+        batch = windowing.infer_videos(m, vids, [dict(f) for f in feats], windows_per_pass=wpp)
+        assert [tuple(o.shape) for o in batch] == [(t, 7) for t in lengths]
+        for a, b in zip(single, batch):
+            assert torch.equal(a, b)
+    assert windowing.infer_videos(m, [], []) == []
+
+
 def test_host_prefetcher_matches_direct_calls():
     """Double-buffered H2D staging must not change results or reorder batches."""
     dev = _dev()

@@ -30,6 +30,18 @@ def test_gather_windows_and_short_video_padding():
     assert w[0, :, 0].tolist() == [0, 1, 2, 3, 4, 4, 4, 4]      # last frame repeated
 
 
+def test_window_index_table_matches_per_video_gather():
+    """The multi-video window table addresses the concatenated frame axis exactly as gather_windows does per video
+    (incl. the repeat-last-frame rule for a video shorter than the window)."""
+    lengths = [7, 20, 33, 21, 1]
+    feats = [torch.randn(t, 3, generator=torch.Generator().manual_seed(t)) for t in lengths]
+    starts, idx = windowing.window_index_table(lengths, 20, 8)
+    assert starts == [windowing.window_starts(t, 20, 8) for t in lengths]
+    got = torch.cat(feats)[idx]
+    want = torch.cat([windowing.gather_windows(f, st, 20) for f, st in zip(feats, starts)])
+    assert torch.equal(got, want)
+
+
 def test_shard_videos_balanced_and_complete():
     g = torch.Generator().manual_seed(7)
     lengths = torch.randint(150, 3001, (56,), generator=g).tolist()      # C-EXPR-DB-CHALLENGE has 56 videos
