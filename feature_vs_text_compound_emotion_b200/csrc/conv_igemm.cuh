@@ -43,6 +43,8 @@ struct alignas(64) ConvKernelParams {
   int halo_frames, halo_bands, halo_cts;   // conv_halo_kernel only: frames, 16-row bands and 8-column tiles per frame
   int pool_xor;          // 0: no pooling; else fused MaxPool2d(2,2): the vertical pool partner is lane ^ pool_xor
                          // (8 or 16 = pixels per tile row), the horizontal one lane ^ 1; output is [M/4][Cout]
+  int out_wp;            // 0: dense [M][Cout] output; else the output is a padded raster (conv_raster.cuh) of row pitch out_wp = Wout + 1
+  int rs_wp, rs_P, rs_frames;   // conv_raster2_kernel only: input row pitch W + 1, positions per frame (H + 1) * (W + 1), frames
   const float* bias;     // [bias_classes][Cout]
   const float* alpha;    // [Cout] PReLU slopes or nullptr
   const __nv_bfloat16* res;  // [M][Cout] residual or nullptr
@@ -91,7 +93,8 @@ template <int BN>
 __device__ __forceinline__ void conv_epilogue_core(const ConvKernelParams& p, const float* s_bias, const float* s_alpha,
                                                    uint32_t tmem_acc, int n0, int warp, uint32_t tfull, uint32_t parity,
                                                    bool valid, int cls, size_t out_off, uint32_t tempty,
-                                                   bool pool_store = false, size_t pool_off = 0);
+                                                   bool pool_store = false, size_t pool_off = 0,
+                                                   size_t res_off = ~size_t(0) /* = out_off */, bool zero_store = false);
 
 template <int BN>
 __device__ __forceinline__ void conv_epilogue_tile(const ConvKernelParams& p, const float* s_bias, const float* s_alpha,
@@ -120,16 +123,24 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvKernelParams& p, co
     pool_store = valid && !(oh & 1) && !(ow & 1);
     pool_off = ((static_cast<size_t>(m / hw) * (p.Hout >> 1) + (oh >> 1)) * (p.Wout >> 1) + (ow >> 1)) * p.Cout + n0;
   }
-  conv_epilogue_core<BN>(p, s_bias, s_alpha, tmem_acc, n0, warp, tfull, parity, valid, cls,
-                         static_cast<size_t>(m) * p.Cout + n0, tempty, pool_store, pool_off);
+  const size_t dense_off = static_cast<size_t>(m) * p.Cout + n0;
+  size_t out_off = dense_off;
+  if (p.out_wp) {        // the consumer reads a padded raster: one pad column per row, one pad row per frame
+    const int n = m / hw, rem = m - n * hw;
+    const int oh = rem / p.Wout, ow = rem - oh * p.Wout;
+    out_off = ((static_cast<size_t>(n) * (p.Hout + 1) + oh) * p.out_wp + ow) * p.Cout + n0;
+  }
+  conv_epilogue_core<BN>(p, s_bias, s_alpha, tmem_acc, n0, warp, tfull, parity, valid, cls, out_off, tempty, pool_store,
+                         pool_off, dense_off);
 }
 
 template <int BN>
 __device__ __forceinline__ void conv_epilogue_core(const ConvKernelParams& p, const float* s_bias, const float* s_alpha,
                                                    uint32_t tmem_acc, int n0, int warp, uint32_t tfull, uint32_t parity,
                                                    bool valid, int cls, size_t out_off, uint32_t tempty, bool pool_store,
-                                                   size_t pool_off) {
+                                                   size_t pool_off, size_t res_off, bool zero_store) {
   constexpr int kHalf = BN / 2;
+  if (res_off == ~size_t(0)) res_off = out_off;
   const int quarter = warp & 3;
   const int half = warp >> 2;
   const uint32_t lane_addr = (static_cast<uint32_t>(quarter * 32) << 16);
@@ -143,7 +154,7 @@ __device__ __forceinline__ void conv_epilogue_core(const ConvKernelParams& p, co
   // behind the MMA of this tile
   uint4 rnext[4];
   if (ld_res) {
-    const uint4* rp = reinterpret_cast<const uint4*>(p.res + out_off);
+    const uint4* rp = reinterpret_cast<const uint4*>(p.res + res_off);
 #pragma unroll
     for (int j = 0; j < 4; ++j) rnext[j] = __ldg(rp + j);
   }
@@ -157,7 +168,7 @@ __device__ __forceinline__ void conv_epilogue_core(const ConvKernelParams& p, co
 #pragma unroll
     for (int j = 0; j < 4; ++j) rres[j] = rnext[j];
     if (c0 + 32 < kHalf && ld_res) {
-      const uint4* rp = reinterpret_cast<const uint4*>(p.res + out_off + c0 + 32);
+      const uint4* rp = reinterpret_cast<const uint4*>(p.res + res_off + c0 + 32);
 #pragma unroll
       for (int j = 0; j < 4; ++j) rnext[j] = __ldg(rp + j);
     }
@@ -234,6 +245,10 @@ __device__ __forceinline__ void conv_epilogue_core(const ConvKernelParams& p, co
                              pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), pack_bf16x2(f[8 * j + 6], f[8 * j + 7]));
         }
       }
+    } else if (zero_store) {                 // pad position of a padded-raster output (bf16): must read as the conv's zero padding
+      uint4* op = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + out_off + c0);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) op[j] = make_uint4(0u, 0u, 0u, 0u);
     }
   }
 }

@@ -33,7 +33,8 @@ int load_driver_entry_points();
 bool conv_can_pool(int H, int W, int Cin, int Cout);
 // n_cap: frames the activation allocation holds (tensor-map N extent)
 int build_conv_op(ConvOp* op, const ConvGeom& g, int n_cap);
-int launch_conv(const ConvOp& op, int frames, int num_sms, cudaStream_t st);
+// out_wp != 0: store the output as a padded raster of row pitch out_wp = Wout + 1 (im2col kernels only; conv_raster.cuh)
+int launch_conv(const ConvOp& op, int frames, int num_sms, cudaStream_t st, int out_wp = 0);
 // name of the kernel instantiation launch_conv picks for `op` at `frames` frames / launched last on this thread
 const char* conv_variant_name(const ConvOp& op, int frames, int num_sms);
 const char* conv_last_variant();

@@ -17,6 +17,7 @@
 #include "conv_halo.cuh"
 #include "stem_tc.cuh"
 #include "conv_strip.cuh"
+#include "conv_raster.cuh"
 #include <cstdlib>
 
 namespace cer {
@@ -538,15 +539,19 @@ const char* conv_variant_name(const ConvOp& op, int frames, int num_sms) {
 
 static thread_local const char* g_last_variant = "none";
 const char* conv_last_variant() { return g_last_variant; }
+static void g_last_variant_set(const char* v) { g_last_variant = v; }
 
-int launch_conv(const ConvOp& op, int frames, int num_sms, cudaStream_t st) {
+int launch_conv(const ConvOp& op, int frames, int num_sms, cudaStream_t st, int out_wp) {
   ConvKernelParams p = op.kp;
+  p.out_wp = out_wp;
   p.M = frames * op.hw_out;
   p.num_m_tiles = (p.M + kBlockM - 1) / kBlockM;
   const int tiles = p.num_m_tiles * p.num_n_tiles;
   const ConvVariant var = select_conv_variant(op, frames, num_sms);
   g_last_variant = kVariantNames[var];
   const int grid = std::min(tiles, num_sms);
+  if (out_wp && (var == kVarStrip64 || var == kVarHalo64 || var == kVarHalo128))
+    return set_error(CER_ERR_INVALID, "launch_conv: the halo / strip kernels cannot store a padded raster");
   switch (var) {
     case kVarNone: return CER_OK;
     case kVarStrip64:
@@ -574,6 +579,76 @@ int launch_conv(const ConvOp& op, int frames, int num_sms, cudaStream_t st) {
     case kVar64:          return launch_conv_inst<64, 8, false, false>(p, grid, st);
   }
   return set_error(CER_ERR_INVALID, "launch_conv: unknown variant");
+}
+
+// ------------------------------------------------------------------------------------------
+// Padded-raster stage (conv_raster.cuh): plan-level helpers.
+// ------------------------------------------------------------------------------------------
+static const char* const kRasterName128 = "conv_raster2_kernel<128,3,18,176>";
+static const int kRasterBoxRows128 = 176;
+
+// CER_RASTER=0 keeps the im2col / strip kernels for the identity stages (A/B timing); read when a plan is created.
+bool raster_enabled() {
+  const char* e = getenv("CER_RASTER");
+  return !(e && e[0] == '0');
+}
+
+// can a 3x3/s1/p1 identity unit with these channels over an H x W map run on the raster kernel?
+bool raster_unit_ok(int H, int W, int cin, int depth, int stride, int has_proj) {
+  if (has_proj || stride != 1 || cin != depth || H < 2 || W < 2) return false;
+  // 64 -> 64 stages stay on the strip kernel: the <64,6,9,216> instantiation of the raster kernel (pair MMAs of
+  // N = 64, the stem storing the padded raster) was measured at 2.21 ms for IR-50 stage 1 against 2.07 ms
+  return cin == 128 && kBlockM + 2 * (W + 2) <= kRasterBoxRows128;
+}
+
+// kernel parameters of one raster conv: src / res are padded rasters [n_cap][(H+1)][(W+1)][C], dst too unless
+// out_padded == 0 (dense NHWC for a consumer that is not a raster kernel)
+int build_raster_op(ConvKernelParams* kp, CUtensorMap* tmap_b_half, const ConvGeom& g, int n_cap, int out_padded) {
+  memset(kp, 0, sizeof *kp);
+  const int wp = g.W + 1, P = (g.H + 1) * wp;
+  int rc = make_tiled2d_map_generic(&kp->tmap_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, g.src, n_cap * P, g.Cin,
+                                    kBlockM + 2 * (wp + 1), kBlockK);
+  if (rc) return rc;
+  rc = make_weight_map(tmap_b_half, g.weight, g.Cout, 9 * g.Cin, g.Cout / 2);
+  if (rc) return rc;
+  kp->tmap_b = *tmap_b_half;
+  kp->tmap_a2 = kp->tmap_a;
+  kp->Hout = g.H; kp->Wout = g.W; kp->Cout = g.Cout;
+  kp->cin_chunks = g.Cin / kBlockK; kp->cin_shift = kp->cin_chunks == 2 ? 1 : 0; kp->ksize = 3;
+  kp->ksteps_main = 9 * kp->cin_chunks; kp->ksteps2 = 0;
+  kp->stride = 1; kp->pad = 1; kp->stride2 = 1;
+  kp->num_n_tiles = 1;
+  kp->bias_classes = g.bias_classes;
+  kp->out_fp32 = 0;
+  kp->bias = g.bias; kp->alpha = g.alpha; kp->res = g.res; kp->out = g.dst;
+  kp->rs_wp = wp; kp->rs_P = P;
+  kp->out_wp = out_padded ? wp : 0;
+  return CER_OK;
+}
+
+template <int BN, int SLOTS, int KSTEPS, int BOX_ROWS_MAX>
+static int launch_raster_inst(const ConvKernelParams& p, int ptiles, int num_sms, cudaStream_t st) {
+  using L = RasterSmem<BN, SLOTS, KSTEPS, BOX_ROWS_MAX>;
+  static_assert(L::kTotal <= 232448, "raster conv kernel shared memory exceeds 227 KB");
+  static unsigned long long configured = 0;
+  if (first_use_on_device(&configured))
+    CER_CUDA(cudaFuncSetAttribute(conv_raster2_kernel<BN, SLOTS, KSTEPS, BOX_ROWS_MAX>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  L::kTotal));
+  return launch_conv_kernel(conv_raster2_kernel<BN, SLOTS, KSTEPS, BOX_ROWS_MAX>, 2 * std::min(ptiles, num_sms / 2), kConvThreads,
+                            L::kTotal, st, 2, p);
+}
+
+static const char* raster_variant_name(const ConvKernelParams&) { return kRasterName128; }
+
+int launch_raster(const ConvKernelParams& kp, int frames, int num_sms, cudaStream_t st) {
+  ConvKernelParams p = kp;
+  p.rs_frames = frames;
+  p.M = frames * p.Hout * p.Wout;
+  const long long pos = (long long)frames * p.rs_P;
+  const int ptiles = (int)((pos + 2 * kBlockM - 1) / (2 * kBlockM));
+  if (ptiles == 0) return CER_OK;
+  g_last_variant_set(raster_variant_name(kp));
+  return launch_raster_inst<128, 3, 18, kRasterBoxRows128>(p, ptiles, num_sms, st);
 }
 
 // CER_STEM_TC=0 keeps the CUDA-core stem (A/B timing, exact-fp32 first layer).
@@ -620,6 +695,12 @@ struct cer_ir50 {
   float* fc_out;          // [cap][emb_dim] pre-norm
   size_t act_bytes;       // per activation buffer
   std::vector<ConvOp> ops;          // 2 per unit, then FC
+  // Padded-raster mode (conv_raster.cuh), used by a pass with enough frames (raster_pass): per op, the raster
+  // kernel's parameters when the op runs on it (rast_ok) and whether the op's OUTPUT is then stored as a padded
+  // raster (out_padded; for an im2col producer the pad positions are zeroed by raster_zero_pads_kernel).
+  struct RasterOp { int rast_ok; int out_padded; ConvKernelParams kp; CUtensorMap tmap_b_half; };
+  std::vector<RasterOp> rops;       // 2 per unit
+  int raster_hw;                    // smallest map (pixels per frame) among the raster stages (0: none in this plan)
   struct ActInfo { const void* ptr; int H, W, C; };
   std::vector<ActInfo> unit_out;    // where each unit's output lives
   ActInfo stem_out;
@@ -639,6 +720,77 @@ static size_t max_act_bytes_per_frame(const cer_ir50_weights* w) {
     mx = std::max(mx, (size_t)H * W * u.depth * 2);
   }
   return mx;
+}
+
+// Marks the run of identity units that can use the raster kernel and builds their parameters.  The buffer
+// rotation of cer_ir50_create is replayed so that every op sees the same src / res / dst pointers.
+static int build_raster_stage(cer_ir50* p) {
+  const int n_units = (int)p->units.size();
+  p->rops.assign(2 * n_units, cer_ir50::RasterOp{});
+  p->raster_hw = 0;
+  if (!raster_enabled()) return CER_OK;
+  int H = p->w.in_h, W = p->w.in_w;
+  int cur = 0, tb = 1, nxt = 2;
+  std::vector<int> ok(n_units + 1, 0);
+  {
+    int h = H, w2 = W;
+    for (int i = 0; i < n_units; ++i) {
+      const cer_ir_unit& u = p->units[i];
+      ok[i] = raster_unit_ok(h, w2, u.cin, u.depth, u.stride, u.has_proj);
+      // the tensor a run starts from must be storable as a padded raster: by an im2col kernel (Cin >= 128: never
+      // the halo / strip kernels), not by the stem
+      if (ok[i] && (i == 0 || (!ok[i - 1] && p->units[i - 1].depth < 128))) ok[i] = 0;
+      if (ok[i]) p->raster_hw = p->raster_hw ? std::min(p->raster_hw, h * w2) : h * w2;
+      h = (h - 1) / u.stride + 1; w2 = (w2 - 1) / u.stride + 1;
+    }
+    if (!p->raster_hw) return CER_OK;
+  }
+  for (int i = 0; i < n_units; ++i) {
+    const cer_ir_unit& u = p->units[i];
+    if (ok[i]) {
+      ConvGeom g1{};
+      g1.src = p->buf[cur]; g1.H = H; g1.W = W; g1.Cin = u.cin; g1.ksize = 3; g1.stride = 1; g1.pad = 1;
+      g1.weight = u.w1; g1.bias = u.bias1; g1.bias_classes = 9; g1.alpha = u.alpha; g1.res = nullptr;
+      g1.dst = p->buf[tb]; g1.Cout = u.depth;
+      cer_ir50::RasterOp& r1 = p->rops[2 * i];
+      int rc = build_raster_op(&r1.kp, &r1.tmap_b_half, g1, p->n_cap, /*out_padded*/ 1);
+      if (rc) return rc;
+      r1.rast_ok = 1; r1.out_padded = 1;
+      ConvGeom g2 = g1;
+      g2.src = p->buf[tb]; g2.weight = u.w2; g2.bias = u.bias2; g2.bias_classes = 1; g2.alpha = nullptr;
+      g2.res = reinterpret_cast<const __nv_bfloat16*>(p->buf[cur]); g2.dst = p->buf[nxt];
+      cer_ir50::RasterOp& r2 = p->rops[2 * i + 1];
+      rc = build_raster_op(&r2.kp, &r2.tmap_b_half, g2, p->n_cap, /*out_padded*/ ok[i + 1]);
+      if (rc) return rc;
+      r2.rast_ok = 1; r2.out_padded = ok[i + 1];
+    } else if (ok[i + 1]) {
+      p->rops[2 * i + 1].out_padded = 1;          // im2col producer in front of the stage
+    }
+    H = (H - 1) / u.stride + 1;
+    W = (W - 1) / u.stride + 1;
+    std::swap(cur, nxt);
+  }
+  return CER_OK;
+}
+
+// does a pass over `frames` frames run the raster stage?  (same two-waves-of-pair-tiles rule as the pair kernels)
+static bool raster_pass(const cer_ir50* p, int frames) {
+  return p->raster_hw > 0 && ((long long)frames * p->raster_hw + kBlockM - 1) / kBlockM >= 4LL * p->num_sms;
+}
+
+// one conv op of a pass (op = 0 .. 2U-1 unit convs, 2U = FC)
+static int launch_plan_op(cer_ir50* p, int op, int frames, bool rast, cudaStream_t st) {
+  const int n_units = (int)p->units.size();
+  if (!rast || op >= 2 * n_units) return launch_conv(p->ops[op], frames, p->num_sms, st);
+  const cer_ir50::RasterOp& r = p->rops[op];
+  if (r.rast_ok) return launch_raster(r.kp, frames, p->num_sms, st);
+  if (!r.out_padded) return launch_conv(p->ops[op], frames, p->num_sms, st);
+  const ConvKernelParams& kp = p->ops[op].kp;
+  const long long vecs = (long long)frames * (kp.Hout + kp.Wout + 1) * (kp.Cout / 8);
+  raster_zero_pads_kernel<<<(int)std::min<long long>((vecs + 255) / 256, 4LL * p->num_sms), 256, 0, st>>>(
+      static_cast<__nv_bfloat16*>(kp.out), frames, kp.Hout, kp.Wout, kp.Cout);
+  CER_CUDA(cudaGetLastError());
+  return launch_conv(p->ops[op], frames, p->num_sms, st, kp.Wout + 1);
 }
 
 extern "C" size_t cer_ir50_workspace_bytes(const cer_ir50_weights* w, int64_t frames_per_pass) {
@@ -718,6 +870,8 @@ extern "C" int cer_ir50_create(cer_ir50** out, const cer_ir50_weights* w, int64_
     std::swap(cur, nxt);
   }
   if (H * W * C != w->fc_in || w->emb_dim % 64) { delete p; return set_error(CER_ERR_INVALID, "fc_in / emb_dim mismatch"); }
+  rc = build_raster_stage(p);
+  if (rc) { delete p; return rc; }
   ConvGeom gf{};
   gf.src = p->buf[cur]; gf.H = 1; gf.W = 1; gf.Cin = w->fc_in; gf.ksize = 1; gf.stride = 1; gf.pad = 0;
   gf.weight = w->fc_w; gf.bias = w->fc_bias; gf.bias_classes = 1; gf.dst = p->fc_out; gf.Cout = w->emb_dim;
@@ -730,21 +884,26 @@ extern "C" int cer_ir50_create(cer_ir50** out, const cer_ir50_weights* w, int64_
   return CER_OK;
 }
 
+static int launch_plan_stem(cer_ir50* p, const float* x, int frames, cudaStream_t st) {
+  return launch_stem(x, p->w.stem_w, p->w.stem_bias, p->w.stem_alpha, reinterpret_cast<__nv_bfloat16*>(p->buf[0]), p->stem_out_map,
+                     frames, p->w.in_h, p->w.in_w, p->num_sms, st);
+}
+
 static int run_pass(cer_ir50* p, const float* x, int frames, int last_unit, float* emb_out, cudaStream_t st) {
+  const int n_units = (int)p->units.size();
+  const bool rast = raster_pass(p, frames);
   {
-    int rc = launch_stem(x, p->w.stem_w, p->w.stem_bias, p->w.stem_alpha, reinterpret_cast<__nv_bfloat16*>(p->buf[0]), p->stem_out_map,
-                         frames, p->w.in_h, p->w.in_w, p->num_sms, st);
+    int rc = launch_plan_stem(p, x, frames, st);
     if (rc) return rc;
   }
-  const int n_units = (int)p->units.size();
   for (int i = 0; i < n_units && i <= last_unit; ++i) {
-    int rc = launch_conv(p->ops[2 * i], frames, p->num_sms, st);
+    int rc = launch_plan_op(p, 2 * i, frames, rast, st);
     if (rc) return rc;
-    rc = launch_conv(p->ops[2 * i + 1], frames, p->num_sms, st);
+    rc = launch_plan_op(p, 2 * i + 1, frames, rast, st);
     if (rc) return rc;
   }
   if (last_unit >= n_units) {
-    int rc = launch_conv(p->ops[2 * n_units], frames, p->num_sms, st);
+    int rc = launch_plan_op(p, 2 * n_units, frames, rast, st);
     if (rc) return rc;
     const int wpb = 8;
     l2norm_kernel<<<(frames + wpb - 1) / wpb, wpb * 32, 0, st>>>(p->fc_out, emb_out, frames, p->w.emb_dim);
@@ -776,6 +935,13 @@ extern "C" int64_t cer_ir50_debug_activation(cer_ir50* p, const float* x, int64_
   if (rc) return rc;
   const cer_ir50::ActInfo& a = unit_index < 0 ? p->stem_out : p->unit_out[unit_index];
   const int64_t elems = frames * a.H * a.W * a.C;
+  if (unit_index >= 0 && raster_pass(p, (int)frames) && p->rops[2 * unit_index + 1].out_padded) {
+    const long long vecs = elems / 8;
+    raster_unpad_kernel<<<(int)std::min<long long>((vecs + 255) / 256, 8LL * p->num_sms), 256, 0, st>>>(
+        static_cast<const __nv_bfloat16*>(a.ptr), static_cast<__nv_bfloat16*>(dst_dev), (int)frames, a.H, a.W, a.C);
+    CER_CUDA(cudaGetLastError());
+    return elems;
+  }
   CER_CUDA(cudaMemcpyAsync(dst_dev, a.ptr, (size_t)elems * 2, cudaMemcpyDeviceToDevice, st));
   return elems;
 }
@@ -784,7 +950,9 @@ extern "C" int cer_ir50_op_variant(const cer_ir50* p, int32_t op_index, int64_t 
   if (!p || !buf || buflen <= 0 || op_index < 0 || op_index >= (int)p->ops.size() || n_frames <= 0)
     return set_error(CER_ERR_INVALID, "cer_ir50_op_variant: bad argument");
   const int frames = (int)std::min<int64_t>(p->cap, n_frames);
-  const int n = snprintf(buf, (size_t)buflen, "%s", conv_variant_name(p->ops[op_index], frames, p->num_sms));
+  const bool rast = raster_pass(p, frames) && op_index < (int)p->rops.size() && p->rops[op_index].rast_ok;
+  const int n = snprintf(buf, (size_t)buflen, "%s",
+                         rast ? raster_variant_name(p->rops[op_index].kp) : conv_variant_name(p->ops[op_index], frames, p->num_sms));
   return n < buflen ? n : buflen - 1;
 }
 
@@ -800,11 +968,10 @@ extern "C" int cer_ir50_run_ops(cer_ir50* p, const float* x, int64_t frames, int
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   for (int op = first_op; op <= last_op; ++op) {
     if (op == 0) {
-      int rc = launch_stem(x, p->w.stem_w, p->w.stem_bias, p->w.stem_alpha, reinterpret_cast<__nv_bfloat16*>(p->buf[0]),
-                           p->stem_out_map, (int)frames, p->w.in_h, p->w.in_w, p->num_sms, st);
+      int rc = launch_plan_stem(p, x, (int)frames, st);
       if (rc) return rc;
     } else {
-      int rc = launch_conv(p->ops[op - 1], (int)frames, p->num_sms, st);
+      int rc = launch_plan_op(p, op - 1, (int)frames, raster_pass(p, (int)frames), st);
       if (rc) return rc;
     }
   }
@@ -813,8 +980,14 @@ extern "C" int cer_ir50_run_ops(cer_ir50* p, const float* x, int64_t frames, int
 
 extern "C" int64_t cer_ir50_launches(const cer_ir50* p, int64_t n_frames) {
   if (!p || n_frames <= 0) return 0;
-  const int64_t passes = (n_frames + p->cap - 1) / p->cap;
-  return passes * (1 + 2 * (int64_t)p->units.size() + 2);
+  int64_t total = 0;
+  for (int64_t f0 = 0; f0 < n_frames; f0 += p->cap) {
+    const int frames = (int)std::min<int64_t>(p->cap, n_frames - f0);
+    total += 1 + 2 * (int64_t)p->units.size() + 2;
+    if (raster_pass(p, frames))
+      for (const cer_ir50::RasterOp& r : p->rops) total += (!r.rast_ok && r.out_padded) ? 1 : 0;   // raster_zero_pads_kernel
+  }
+  return total;
 }
 
 extern "C" void cer_ir50_destroy(cer_ir50* p) { delete p; }

@@ -132,9 +132,10 @@ def window_index_table(lengths: Sequence[int], window_length: int = 300, hop_len
 def infer_videos(model, videos: Sequence[torch.Tensor], feats: Sequence[Dict[str, torch.Tensor]], window_length: int = 300,
                  hop_length: int = 200, fps: float = 30.0, windows_per_pass: int = 16) -> List[torch.Tensor]:
     """Several whole videos at once: the same result per video as :func:`infer_video` (the backbones are
-    per-frame and the head is per-window in eval mode, so batch composition cannot change a value), but the
-    frames of all videos go through IR-50 / VGGish back to back in full passes, the windows of all videos
-    go through the head in groups of ``windows_per_pass`` (one CUDA graph, the last group padded by
+    per-frame and the head is per-window in eval mode; values can differ by bf16 rounding only where the
+    IR-50 plan picks another kernel for the larger pass -- the padded-raster stage needs >= 190 frames), but
+    the frames of all videos go through IR-50 / VGGish back to back in full passes, the windows of all
+    videos go through the head in groups of ``windows_per_pass`` (one CUDA graph, the last group padded by
     repeating its last window) and only the stitch is per video.  Short videos stop paying for
     partly-filled launches.  Returns one [T_i, n_out] tensor per video."""
     from .engine import stitch_windows

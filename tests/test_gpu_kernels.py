@@ -117,6 +117,44 @@ def test_stem_and_units_progressively():
         assert err < 3e-2, f"unit {unit}: relative error {err}"
 
 
+def test_raster_stage_matches_im2col_plan(monkeypatch):
+    """IR-50 stage 2 on the padded-raster kernel (passes with enough frames; conv_raster.cuh) against the same
+    plan with CER_RASTER=0 (im2col pair kernel): the unit in front of the stage (stores the padded raster), the
+    stage's units (the last one stores dense NHWC again), the unit behind it and the embeddings.  The two
+    differ only in the order the 1152 products of an output are accumulated in fp32."""
+    dev = _dev()
+    from feature_vs_text_compound_emotion_b200.engine import Ir50Engine
+    sd = synthetic.visual_backbone_state_dict(0)
+    pk = packing.pack_ir50(sd, "backbone.")
+    n = 199                                   # odd count: the last pair tile is ragged, frames end mid-tile
+    x = synthetic.frames(8, seed=23).repeat(25, 1, 1, 1)[:n].contiguous()
+    x = (x + 0.05 * torch.randn(x.shape, generator=torch.Generator().manual_seed(24))).to(dev)
+    monkeypatch.setenv("CER_RASTER", "0")
+    ref = Ir50Engine(pk, dev, frames_per_pass=256)
+    monkeypatch.delenv("CER_RASTER")
+    eng = Ir50Engine(pk, dev, frames_per_pass=256)
+    assert ref.op_variant(2 * 4, n).startswith("conv_igemm2_bres_kernel")
+    assert eng.op_variant(0, n) == ref.op_variant(0, n) == "conv_strip_kernel"          # 64 -> 64 stays on the strip kernel
+    assert [eng.op_variant(op, n) for op in range(2 * 4, 2 * 7)] == ["conv_raster2_kernel<128,3,18,176>"] * 6
+    assert not eng.op_variant(2 * 4, 64).startswith("conv_raster2")          # small passes keep the im2col plan
+    assert eng.launches(n) == ref.launches(n) + 1                               # + raster_zero_pads_kernel
+    for unit in (2, 3, 4, 5, 6, 7):
+        a = ref.debug_activation(x, unit).float()
+        b = eng.debug_activation(x, unit).float()
+        torch.cuda.synchronize()
+        assert a.shape == b.shape
+        scale = a.abs().max().item()
+        assert (a - b).abs().max().item() <= 0.02 * scale, f"unit {unit}"
+        assert (a - b).abs().mean().item() <= 2e-3 * a.abs().mean().item(), f"unit {unit}"
+    ea, eb = ref.forward(x), eng.forward(x)
+    assert F.cosine_similarity(ea, eb, dim=1).min().item() >= 0.9999
+    # a second, smaller pass through the same plan leaves no stale pad data behind
+    small = eng.forward(x[:7])
+    assert F.cosine_similarity(small, ea[:7], dim=1).min().item() >= 0.9999
+    again = eng.forward(x)
+    assert torch.equal(again, eb)
+
+
 def test_ir50_embedding_vs_golden(golden_dir):
     import os
     dev = _dev()

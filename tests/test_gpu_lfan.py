@@ -212,20 +212,25 @@ def test_infer_video_from_stored_uint8_crops_and_logmel():
     assert windowing.video_level_prediction(out.to(dev))["FRAMES_AVG_LOGITS"] == O.video_level_prediction(want.numpy())["FRAMES_AVG_LOGITS"]
 
 
-def test_infer_videos_equals_per_video_inference():
+def test_infer_videos_equals_per_video_inference(monkeypatch):
     """windowing.infer_videos: the frames of several videos through the backbones in shared passes and their
-    windows through the head in fixed-size groups -- bit for bit what infer_video returns per video (a video
-    shorter than one window, exactly one window, grid + tail window; a padded last head group)."""
+    windows through the head in fixed-size groups (a video shorter than one window, exactly one window, grid +
+    tail window; a padded last head group).  With one kernel plan for every pass size (CER_RASTER=0) the result
+    is bit for bit what infer_video returns per video; with the default plan a pass of >= 190 frames runs IR-50
+    stage 2 on the padded-raster kernel, whose fp32 accumulation order differs, so a short video inferred alone
+    and inside a batch agree to bf16 rounding instead."""
     dev = _dev()
     from feature_vs_text_compound_emotion_b200 import windowing
     mods = ["video", "logmel", "bert"]
-    m = _lfan(mods, dev, seed=6)
     lengths = [120, 300, 530, 301]
     raw = synthetic.raw_frames_u8(64, seed=71).repeat(9, 1, 1, 1).to(dev)
     lm = synthetic.logmel_patches(max(lengths), seed=72).to(dev)
     bert = torch.randn(max(lengths), 768, generator=torch.Generator().manual_seed(73)).to(dev)
     vids = [raw[7 * i:7 * i + t] for i, t in enumerate(lengths)]
     feats = [{"logmel": lm[:t], "bert": bert[3 * i:3 * i + t] if 3 * i + t <= bert.shape[0] else bert[:t]} for i, t in enumerate(lengths)]
+
+    monkeypatch.setenv("CER_RASTER", "0")
+    m = _lfan(mods, dev, seed=6)
     single = [windowing.infer_video(m, v, dict(f)) for v, f in zip(vids, feats)]
     for wpp in (16, 4):                                   # 8 windows in total: one padded group / two full groups
         batch = windowing.infer_videos(m, vids, [dict(f) for f in feats], windows_per_pass=wpp)
@@ -233,6 +238,14 @@ def test_infer_videos_equals_per_video_inference():
         for a, b in zip(single, batch):
             assert torch.equal(a, b)
     assert windowing.infer_videos(m, [], []) == []
+
+    monkeypatch.delenv("CER_RASTER")
+    m2 = _lfan(mods, dev, seed=6)                         # default plan: engines are built at the first forward
+    batch2 = windowing.infer_videos(m2, vids, [dict(f) for f in feats])
+    single2 = [windowing.infer_video(m2, v, dict(f)) for v, f in zip(vids, feats)]
+    for a, b, c in zip(single, batch2, single2):
+        assert (a - b).abs().max().item() <= 1e-2 and (a - c).abs().max().item() <= 1e-2
+        assert (a.argmax(-1) == b.argmax(-1)).float().mean().item() >= 0.99
 
 
 def test_host_prefetcher_matches_direct_calls():
