@@ -264,7 +264,6 @@ struct Conv2BresSmem {
 template <int BN, int STAGES, int KSTEPS>
 __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm2_bres_kernel(const __grid_constant__ ConvKernelParams p) {
   using L = Conv2BresSmem<BN, STAGES, KSTEPS>;
-  static_assert(KSTEPS % 2 == 0, "the two A producers split the k-steps evenly");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOffset);
@@ -288,7 +287,10 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm2_bres_kernel(const
     mbar_init(bres_bar, 1);
     fence_barrier_init();
   }
-  if (warp == kProdWarp0 && lane == 0) tma_prefetch_desc(&p.tmap_a);
+  if (warp == kProdWarp0 && lane == 0) {
+    tma_prefetch_desc(&p.tmap_a);
+    if (p.ksteps2 > 0) tma_prefetch_desc(&p.tmap_a2);
+  }
   if (warp == kProdWarp0 + 2 && lane == 0) tma_prefetch_desc(&p.tmap_b);
   if (warp == kMmaWarp) {
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(2 * BN)
@@ -322,17 +324,19 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm2_bres_kernel(const
     }
     __syncwarp();
   } else if (warp == kProdWarp0 || warp == kProdWarp0 + 1) {
-    // ---- A producers: warp q takes the k-steps g = q (mod 2), g counted across all tiles of this pair
+    // ---- A producers: warp q takes the k-steps ks = q (mod 2) of every tile; g = g0 + ks counts the k-steps of this
+    // pair across tiles (KSTEPS may be odd: 9 taps x 2 chunks + one k-step of a fused 1x1 projection)
     const int q = warp - kProdWarp0;
     const int hw = p.Hout * p.Wout;
-    uint32_t g = q;
-    for (int pt = pair; pt < total_ptiles; pt += num_pairs) {
+    uint32_t g0 = 0;
+    for (int pt = pair; pt < total_ptiles; pt += num_pairs, g0 += KSTEPS) {
       const int m0 = (2 * pt + (int)rank) * kBlockM;
       const int n_img = m0 / hw;
       const int rem = m0 - n_img * hw;
       const int oh = rem / p.Wout, ow = rem - oh * p.Wout;
       const int cw = ow * p.stride - p.pad, ch = oh * p.stride - p.pad;
-      for (int ks = q; ks < KSTEPS; ks += 2, g += 2) {
+      for (int ks = q; ks < KSTEPS; ks += 2) {
+        const uint32_t g = g0 + ks;
         const uint32_t stage = g % STAGES, phase = (g / STAGES) & 1;
         mbar_wait_a(empty0 + stage * 8, phase ^ 1);
         int tap = 0, chunk = ks;
@@ -341,8 +345,12 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm2_bres_kernel(const
         if (elect_one()) {
           const uint32_t fb = (full0 + stage * 8) & kPeerBitMask;
           if (rank == 0) mbar_expect_tx_a(fb, 2 * kABytes);
-          tma2_load_im2col_4d(&p.tmap_a, fb, smem_base + stage * kABytes, chunk * kBlockK, cw, ch, n_img, (uint16_t)ss,
-                              (uint16_t)rr);
+          if (ks < p.ksteps_main)
+            tma2_load_im2col_4d(&p.tmap_a, fb, smem_base + stage * kABytes, chunk * kBlockK, cw, ch, n_img, (uint16_t)ss,
+                                (uint16_t)rr);
+          else                                                   // fused 1x1 / stride-2 projection of the unit's input
+            tma2_load_im2col_4d(&p.tmap_a2, fb, smem_base + stage * kABytes, (ks - p.ksteps_main) * kBlockK, ow * p.stride2,
+                                oh * p.stride2, n_img, 0, 0);
         }
         __syncwarp();
       }

@@ -498,11 +498,12 @@ static bool pair_mode_enabled() {
 // launching so that the plan can REPORT its choice (cer_ir50_op_variant / cer_conv_last_variant):
 // bench.py labels its roofline line with the variant that actually ran.
 enum ConvVariant {
-  kVarNone = 0, kVarStrip64, kVarHalo64, kVarHalo128, kVarPairBres128, kVarPair256, kVarPair128,
+  kVarNone = 0, kVarStrip64, kVarHalo64, kVarHalo128, kVarPairBres128, kVarPairBres128Proj, kVarPair256, kVarPair128,
   kVar256Aligned, kVar256, kVar128Bres, kVar128Aligned, kVar128, kVar64Bres9, kVar64Aligned, kVar64
 };
 static const char* const kVariantNames[] = {
   "none", "conv_strip_kernel", "conv_halo_kernel<64>", "conv_halo_kernel<128>", "conv_igemm2_bres_kernel<128,4,18>",
+  "conv_igemm2_bres_kernel<128,4,19>",
   "conv_igemm2_kernel<256,6>", "conv_igemm2_kernel<128,6>", "conv_igemm_kernel<256,4,0,1>", "conv_igemm_kernel<256,4,0,0>",
   "conv_igemm_kernel<128,4,1,0>", "conv_igemm_kernel<128,6,0,1>", "conv_igemm_kernel<128,6,0,0>",
   "conv_igemm_kernel<64,9,1,1>", "conv_igemm_kernel<64,8,0,1>", "conv_igemm_kernel<64,8,0,0>"};
@@ -518,6 +519,10 @@ static ConvVariant select_conv_variant(const ConvOp& op, int frames, int num_sms
   }
   const int grid = std::min(tiles, num_sms);
   const int ksteps = p.ksteps_main + p.ksteps2;
+  // the 128 -> 128 stride-2 conv with its fused 64-channel projection (18 + 1 k-steps): weights resident, CTA pair
+  if (pair_mode_enabled() && pair_bres_enabled() && op.bn == 128 && p.num_n_tiles == 1 && p.ksize == 3 && p.ksteps_main == 18 &&
+      p.ksteps2 == 1 && tiles >= 4 * num_sms && !p.pool_xor)
+    return kVarPairBres128Proj;
   // CTA-pair (cta_group::2) variant: plain 3x3 / 1x1 layers whose k-steps fill the 6-stage ring a whole
   // number of times and that have at least two waves of pair tiles
   if (pair_mode_enabled() && p.ksteps2 == 0 && ksteps % 6 == 0 && tiles >= 4 * num_sms && op.bn >= 128) {
@@ -567,6 +572,7 @@ int launch_conv(const ConvOp& op, int frames, int num_sms, cudaStream_t st, int 
       p.halo_cts = p.Wout / kHaloTileW;
       return var == kVarHalo64 ? launch_halo_inst<64>(p, num_sms, st) : launch_halo_inst<128>(p, num_sms, st);
     case kVarPairBres128: p.tmap_b = op.tmap_b_half; return launch_conv2_bres_inst<128, 4, 18>(p, num_sms, st);
+    case kVarPairBres128Proj: p.tmap_b = op.tmap_b_half; return launch_conv2_bres_inst<128, 4, 19>(p, num_sms, st);
     case kVarPair256:     p.tmap_b = op.tmap_b_half; return launch_conv2_inst<256, 6>(p, num_sms, st);
     case kVarPair128:     p.tmap_b = op.tmap_b_half; return launch_conv2_inst<128, 6>(p, num_sms, st);
     case kVar256Aligned:  return launch_conv_inst<256, 4, false, true>(p, grid, st);

@@ -1,16 +1,14 @@
 #!/bin/bash
-# A/B of an environment switch on the headline bench: tools/ab_env.sh CER_STRIP   (runs =1 then =0)
-VAR=${1:?variable name}
-mkdir -p gpurun_out
-for s in 1 0; do
-  env $VAR=$s timeout 300 python bench.py --no-sub-records --no-library-bar --no-cpu-baseline > gpurun_out/ab_${VAR}_$s.json 2> gpurun_out/ab_${VAR}_$s.err
-  echo "bench rc=$?"
-  python - "$VAR" "$s" <<'PY'
-import json, sys
-var, s = sys.argv[1], sys.argv[2]
-d = json.load(open(f"gpurun_out/ab_{var}_{s}.json"))
-print(f"{var}={s}", round(d["value"]), round(d["ms_per_step"], 3), "long", round(d["long_run"]["value"]), "e2e", round(d["e2e"]["value"]), "ir50 ms", round(d["ir50"]["ms"], 3))
-for r in d["ir50_layers"][:3]:
-    print("   ", r["class"], r["variant"], r["launches"], r["ms"], round(r["tflops"]))
+# A/B of one environment switch on one box: bash tools/ab_env.sh VAR  (runs VAR=0 / default, twice each)
+V=$1
+for r in 0 1 0 1; do
+  if [ $r = 0 ]; then export $V=0; else unset $V; fi
+  timeout 200 python bench.py --steps 20 --warmup 3 --no-cpu-baseline --no-library-bar --no-sub-records 2>/dev/null > gpurun_out/ab_${V}_$r.json
+  python - <<PY
+import json
+j=[json.loads(l) for l in open("gpurun_out/ab_${V}_$r.json") if l.startswith("{")][0]
+print("$V", "off" if $r == 0 else "default", "value", round(j["value"]), "long", round(j["long_run"]["value"]), "e2e", round(j["e2e"]["value"]))
+for L in j["ir50_layers"]:
+    if "s2" in L["class"]: print("   ", L["class"], L["variant"], round(L["ms"],3), round(L["frac_of_burst"],3))
 PY
 done
