@@ -45,11 +45,19 @@ struct alignas(64) ConvKernelParams {
                          // (8 or 16 = pixels per tile row), the horizontal one lane ^ 1; output is [M/4][Cout]
   int out_wp;            // 0: dense [M][Cout] output; else the output is a padded raster (conv_raster.cuh) of row pitch out_wp = Wout + 1
   int rs_wp, rs_P, rs_frames;   // conv_raster2_kernel only: input row pitch W + 1, positions per frame (H + 1) * (W + 1), frames
+  int ctab_flags;        // bit 0: ctab holds the PReLU slopes, bit 1: ctab holds the (single-class) bias -- see kCtab*
   const float* bias;     // [bias_classes][Cout]
   const float* alpha;    // [Cout] PReLU slopes or nullptr
   const __nv_bfloat16* res;  // [M][Cout] residual or nullptr
   void* out;             // [M][Cout]
+  // Per-channel epilogue constants as KERNEL PARAMETERS (constant bank): [0, 512) PReLU slopes, [512, 1024) bias.
+  // A column's constant is the same for every lane of a warp, so the epilogue reads it as a uniform constant
+  // operand instead of an LDS.128 per four columns.  That matters because the LSU's shared-memory wavefronts go
+  // through the same port the tensor core reads its operands from: the table reads were 30 % of that port's
+  // cycles in the N = 64 / N = 128 kernels, whose MMAs need 75-100 % of it.
+  float ctab[1024];
 };
+constexpr int kCtabAlpha = 1, kCtabBias = 2, kCtabMaxCout = 512;
 
 constexpr int kConvThreads = 416;
 constexpr int kEpiWarps = 8;
@@ -182,22 +190,34 @@ __device__ __forceinline__ void conv_epilogue_core(const ConvKernelParams& p, co
       if ((threadIdx.x & 31) == 0) mbar_arrive_relaxed_cluster(tempty);
     }
     float f[32];
+    if (p.ctab_flags & kCtabBias) {            // warp-uniform constant operands (kernel parameter space)
+      const float* cb = p.ctab + 512 + n0 + c0;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float4 b = *reinterpret_cast<const float4*>(sb + c0 + 4 * j);
-      f[4 * j + 0] = __uint_as_float(v[4 * j + 0]) + b.x;
-      f[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + b.y;
-      f[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + b.z;
-      f[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + b.w;
-    }
-    if (has_alpha) {
+      for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) + cb[j];
+    } else {
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const float4 a = *reinterpret_cast<const float4*>(sal + c0 + 4 * j);
-        f[4 * j + 0] = f[4 * j + 0] >= 0.f ? f[4 * j + 0] : f[4 * j + 0] * a.x;
-        f[4 * j + 1] = f[4 * j + 1] >= 0.f ? f[4 * j + 1] : f[4 * j + 1] * a.y;
-        f[4 * j + 2] = f[4 * j + 2] >= 0.f ? f[4 * j + 2] : f[4 * j + 2] * a.z;
-        f[4 * j + 3] = f[4 * j + 3] >= 0.f ? f[4 * j + 3] : f[4 * j + 3] * a.w;
+        const float4 b = *reinterpret_cast<const float4*>(sb + c0 + 4 * j);
+        f[4 * j + 0] = __uint_as_float(v[4 * j + 0]) + b.x;
+        f[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + b.y;
+        f[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + b.z;
+        f[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + b.w;
+      }
+    }
+    if (has_alpha) {
+      if (p.ctab_flags & kCtabAlpha) {
+        const float* ca = p.ctab + n0 + c0;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = f[j] >= 0.f ? f[j] : f[j] * ca[j];
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 a = *reinterpret_cast<const float4*>(sal + c0 + 4 * j);
+          f[4 * j + 0] = f[4 * j + 0] >= 0.f ? f[4 * j + 0] : f[4 * j + 0] * a.x;
+          f[4 * j + 1] = f[4 * j + 1] >= 0.f ? f[4 * j + 1] : f[4 * j + 1] * a.y;
+          f[4 * j + 2] = f[4 * j + 2] >= 0.f ? f[4 * j + 2] : f[4 * j + 2] * a.z;
+          f[4 * j + 3] = f[4 * j + 3] >= 0.f ? f[4 * j + 3] : f[4 * j + 3] * a.w;
+        }
       }
     }
     if (ld_res) {

@@ -32,7 +32,8 @@ int load_driver_entry_points();
 // can a 3x3/s1/p1 conv over an H x W map with these channels fuse the 2x2 max-pool into its epilogue?
 bool conv_can_pool(int H, int W, int Cin, int Cout);
 // n_cap: frames the activation allocation holds (tensor-map N extent)
-int build_conv_op(ConvOp* op, const ConvGeom& g, int n_cap);
+// host_tables: also copy the per-channel epilogue constants into the kernel parameters (synchronous D2H: plan creation only)
+int build_conv_op(ConvOp* op, const ConvGeom& g, int n_cap, bool host_tables = false);
 // out_wp != 0: store the output as a padded raster of row pitch out_wp = Wout + 1 (im2col kernels only; conv_raster.cuh)
 int launch_conv(const ConvOp& op, int frames, int num_sms, cudaStream_t st, int out_wp = 0);
 // name of the kernel instantiation launch_conv picks for `op` at `frames` frames / launched last on this thread

@@ -299,7 +299,30 @@ bool conv_can_pool(int H, int W, int Cin, int Cout) {
   return (W == 8 || W == 16) && (H * W) % 32 == 0 && Cin % 64 == 0;
 }
 
-int build_conv_op(ConvOp* op, const ConvGeom& g, int n_cap) {
+// Copies the per-channel epilogue constants to the host so that they travel as kernel parameters (ConvKernelParams::ctab).
+// Synchronous device-to-host copies: plan creation only (cer_conv_forward builds its op per call and keeps the
+// shared-memory tables).
+static int fill_ctab(ConvKernelParams* kp, const ConvGeom& g) {
+  kp->ctab_flags = 0;
+  if (g.Cout > kCtabMaxCout) return CER_OK;
+  if (g.alpha) {
+    CER_CUDA(cudaMemcpy(kp->ctab, g.alpha, (size_t)g.Cout * sizeof(float), cudaMemcpyDeviceToHost));
+    kp->ctab_flags |= kCtabAlpha;
+  }
+  if (g.bias_classes == 1 && g.bias) {
+    CER_CUDA(cudaMemcpy(kp->ctab + 512, g.bias, (size_t)g.Cout * sizeof(float), cudaMemcpyDeviceToHost));
+    kp->ctab_flags |= kCtabBias;
+  }
+  return CER_OK;
+}
+
+// CER_CTAB=0 keeps every epilogue constant in shared memory (A/B timing); read when a plan is created.
+static bool ctab_enabled() {
+  const char* e = getenv("CER_CTAB");
+  return !(e && e[0] == '0');
+}
+
+int build_conv_op(ConvOp* op, const ConvGeom& g, int n_cap, bool host_tables) {
   if (g.Cin % kBlockK || g.Cin2 % kBlockK || g.Cout % 64) return set_error(CER_ERR_INVALID, "channels must be multiples of 64");
   memset(op, 0, sizeof *op);
   const int Hout = (g.H + 2 * g.pad - g.ksize) / g.stride + 1;
@@ -363,6 +386,7 @@ int build_conv_op(ConvOp* op, const ConvGeom& g, int n_cap) {
     rc = make_strip_map(&op->tmap_strip, g.src, n_cap, g.H, g.W, g.Cin);
     if (rc) return rc;
   }
+  if (host_tables && ctab_enabled()) return fill_ctab(&p, g);
   return CER_OK;
 }
 
@@ -629,6 +653,7 @@ int build_raster_op(ConvKernelParams* kp, CUtensorMap* tmap_b_half, const ConvGe
   kp->bias = g.bias; kp->alpha = g.alpha; kp->res = g.res; kp->out = g.dst;
   kp->rs_wp = wp; kp->rs_P = P;
   kp->out_wp = out_padded ? wp : 0;
+  if (ctab_enabled()) return fill_ctab(kp, g);
   return CER_OK;
 }
 
@@ -851,7 +876,7 @@ extern "C" int cer_ir50_create(cer_ir50** out, const cer_ir50_weights* w, int64_
     g1.weight = u.w1; g1.bias = u.bias1; g1.bias_classes = 9; g1.alpha = u.alpha; g1.res = nullptr;
     g1.dst = p->buf[tb]; g1.Cout = u.depth; g1.out_fp32 = 0;
     ConvOp op1;
-    rc = build_conv_op(&op1, g1, p->n_cap);
+    rc = build_conv_op(&op1, g1, p->n_cap, true);
     if (rc) { delete p; return rc; }
     p->ops.push_back(op1);
 
@@ -865,7 +890,7 @@ extern "C" int cer_ir50_create(cer_ir50** out, const cer_ir50_weights* w, int64_
     g2.weight = u.w2; g2.bias = u.bias2; g2.bias_classes = 1; g2.alpha = nullptr;
     g2.dst = p->buf[nxt]; g2.Cout = u.depth; g2.out_fp32 = 0;
     ConvOp op2;
-    rc = build_conv_op(&op2, g2, p->n_cap);
+    rc = build_conv_op(&op2, g2, p->n_cap, true);
     if (rc) { delete p; return rc; }
     p->ops.push_back(op2);
 
@@ -883,7 +908,7 @@ extern "C" int cer_ir50_create(cer_ir50** out, const cer_ir50_weights* w, int64_
   gf.weight = w->fc_w; gf.bias = w->fc_bias; gf.bias_classes = 1; gf.dst = p->fc_out; gf.Cout = w->emb_dim;
   gf.out_fp32 = 1;
   ConvOp opf;
-  rc = build_conv_op(&opf, gf, p->n_cap);
+  rc = build_conv_op(&opf, gf, p->n_cap, true);
   if (rc) { delete p; return rc; }
   p->ops.push_back(opf);
   *out = p;

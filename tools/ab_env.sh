@@ -8,7 +8,6 @@ for r in 0 1 0 1; do
 import json
 j=[json.loads(l) for l in open("gpurun_out/ab_${V}_$r.json") if l.startswith("{")][0]
 print("$V", "off" if $r == 0 else "default", "value", round(j["value"]), "long", round(j["long_run"]["value"]), "e2e", round(j["e2e"]["value"]))
-for L in j["ir50_layers"]:
-    if "s2" in L["class"]: print("   ", L["class"], L["variant"], round(L["ms"],3), round(L["frac_of_burst"],3))
+print("   ", " | ".join("%s%s:%.3f" % (L["class"].split()[0], L["class"].split()[1], L["ms"]) for L in j["ir50_layers"]))
 PY
 done
