@@ -1,5 +1,6 @@
 """One LFAN forward (BASELINE configs[1] shape) after two warm-up forwards -- the command ncu
-wraps.  64 kernel launches per forward: stem, 48 unit convs, FC, l2norm, 12 TCN blocks, fusion."""
+wraps.  77 kernel launches per forward: stem, 48 unit convs (+ raster_zero_pads_kernel in a raster pass), FC,
+l2norm, 24 TCN launches (two per TemporalBlock), fusion."""
 import os
 import sys
 import warnings
