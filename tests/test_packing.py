@@ -57,3 +57,34 @@ def test_tcn_and_fusion_packing():
     fw = packing.pack_fusion(sd, mods, 32, 2)
     logits, _ = emulate.fusion_packed(fw, [e.reshape(600, -1) for e in enc])
     assert (logits.view(2, 300, 7) - ref).abs().max().item() < 1e-4
+
+
+def test_padded_raster_addressing_equals_zero_padded_conv():
+    """The layout algebra of csrc/conv_raster.cuh on the CPU: store a batch of maps as a padded raster
+    [frames][H+1][W+1][C] (one zero column after every row, one zero row after every frame); then for EVERY
+    position q the input of tap (r, s) is the element at q + (r-1)*(W+1) + (s-1) (zero before / after the
+    tensor), so a 3x3 / pad 1 convolution is nine shifted views of ONE flat tensor -- frame borders included."""
+    g = torch.Generator().manual_seed(5)
+    n, H, W, C, Co = 3, 5, 4, 2, 3
+    x = torch.randn(n, C, H, W, generator=g, dtype=torch.float64)
+    w = torch.randn(Co, C, 3, 3, generator=g, dtype=torch.float64)
+    want = torch.nn.functional.conv2d(x, w, padding=1)                       # [n, Co, H, W]
+    wp, P = W + 1, (H + 1) * (W + 1)
+    ras = torch.zeros(n, H + 1, wp, C, dtype=torch.float64)
+    ras[:, :H, :W] = x.permute(0, 2, 3, 1)
+    flat = ras.reshape(n * P, C)
+    lead = wp + 1                                                            # the most negative offset is -(wp + 1)
+    padded = torch.cat([torch.zeros(lead, C, dtype=torch.float64), flat, torch.zeros(lead, C, dtype=torch.float64)])
+    out = torch.zeros(n * P, Co, dtype=torch.float64)
+    for r in range(3):
+        for s in range(3):
+            off = (r - 1) * wp + (s - 1)
+            view = padded[lead + off: lead + off + n * P]                    # the whole tensor shifted by one tap
+            out += view @ w[:, :, r, s].T
+    got = out.reshape(n, H + 1, wp, Co)[:, :H, :W].permute(0, 3, 1, 2)
+    assert torch.allclose(got, want, atol=1e-12)
+    # the kernel's position -> pixel map and the number of pad positions per frame (raster_zero_pads_kernel)
+    q = torch.arange(n * P)
+    rem = q % P
+    real = (rem // wp < H) & (rem % wp < W)
+    assert int(real.sum()) == n * H * W and int((~real).sum()) == n * (H + wp)
