@@ -81,7 +81,8 @@ int cer_ir50_create(cer_ir50** out, const cer_ir50_weights* w, int64_t frames_pe
 int cer_ir50_forward(cer_ir50* plan, const float* x_nchw_dev, int64_t n_frames, float* emb_out_dev, void* stream);
 /* Debug/inspection: run the stem and units 0..unit_index (-1 = stem only) on `frames`
  * (<= frames_per_pass) frames and copy that unit's bf16 NHWC output to dst_dev
- * (frames*H*W*C bf16).  Returns the element count or a negative cer_status. */
+ * (frames*H*W*C bf16; always dense NHWC -- a unit the plan keeps as a padded raster in this pass,
+ * see DESIGN.md section 5.13, is un-padded on the way).  Returns the element count or a negative cer_status. */
 int64_t cer_ir50_debug_activation(cer_ir50* plan, const float* x_nchw_dev, int64_t frames, int32_t unit_index,
                                   void* dst_dev, void* stream);
 /* Name of the kernel instantiation the plan launches for conv op `op_index` (0 .. 2*n_units - 1: conv1,
@@ -92,7 +93,8 @@ int cer_ir50_op_variant(const cer_ir50* plan, int32_t op_index, int64_t n_frames
  * convs, 2*n_units + 1 = FC) on `frames` <= frames_per_pass frames.  The plan's activation buffers must hold
  * an earlier forward of the same frames.  x_nchw_dev is read by op 0 only. */
 int cer_ir50_run_ops(cer_ir50* plan, const float* x_nchw_dev, int64_t frames, int32_t first_op, int32_t last_op, void* stream);
-/* Number of kernel launches one forward of n_frames enqueues (for bench accounting). */
+/* Number of kernel launches one forward of n_frames enqueues (for bench accounting; depends on the pass sizes:
+ * a pass that runs the padded-raster stage adds one pad-zeroing launch). */
 int64_t cer_ir50_launches(const cer_ir50* plan, int64_t n_frames);
 void cer_ir50_destroy(cer_ir50* plan);
 
