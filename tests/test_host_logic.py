@@ -144,3 +144,31 @@ def test_bench_rank0_only_section_has_no_collective():
     from feature_vs_text_compound_emotion_b200 import heads_training, training
     for cls in (training.HeadTrainer, heads_training.AltHeadTrainer):
         assert "sync_grads" in inspect.signature(cls.step).parameters
+
+
+def test_recorded_bench_line_carries_the_contract_keys():
+    """The last bench line recorded on a B200 (profiles/r02o_bench_n1.json, printed by `python bench.py`) has every
+    key of the bench contract, with consistent values: value = frames / time, roofline.frac = achieved / peak,
+    e2e measured with host copies, launches counted, the CPU baseline run on the reference's own modules."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    line = json.loads(open(os.path.join(root, "profiles", "r02o_bench_n1.json")).read())
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline", "cpu_baseline"):
+        assert k in line, k
+    assert line["metric"] == "frames_per_s" and line["unit"] == "frames/s" and line["higher_is_better"] is True
+    assert line["n_gpus"] == 1 and line["warmup"] >= 3 and line["data"] == "synthetic" and "workload" in line["config"]
+    frames = line["config"]["frames_per_step_per_gpu"]
+    assert abs(line["value"] - frames / (line["ms_per_step"] * 1e-3)) <= 1e-6 * line["value"]
+    e2e = line["e2e"]
+    assert e2e["unit"] == "frames/s" and e2e["h2d_bytes_per_step"] > 0 and e2e["d2h_bytes_per_step"] > 0
+    assert 0 < e2e["value"] <= 1.02 * line["value"]                 # copies cannot make it faster (2 % clock noise)
+    r = line["roofline"]
+    assert r["bound"] == "tensor" and r["unit"] == "TFLOP/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+    assert 0.5 < r["frac"] < 1.0 and r["kernel"].startswith(r["plan_variant_for_this_layer"])
+    assert r["traffic"] is None or r["traffic"] > 0
+    c = line["cpu_baseline"]
+    assert c["kind"] == "reference" and c["cores"] >= 1 and c["unit"] == "frames/s" and c["value"] > 0 and c["sample"]
+    assert line["gpu_launches"] > 0 and line["gpu_launches"] % line["steps"] == 0
+    assert not set(line["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+    for sub in ("long_run", "ir50", "ir50_layers", "roofline_hbm", "head_only", "train", "full", "sweep", "alt_heads"):
+        assert sub in line, sub
