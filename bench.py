@@ -789,8 +789,11 @@ def main():
     torch.cuda.set_device(dev)
     dist = None
     if world > 1:
+        import datetime
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=dev)
+        # no phase of this script keeps a rank away from a collective for more than a minute: a 5-minute watchdog turns
+        # a mismatch into a prompt error instead of NCCL's default 10-minute hang
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=300))
     torch.set_grad_enabled(False)
 
     from feature_vs_text_compound_emotion_b200 import modules
